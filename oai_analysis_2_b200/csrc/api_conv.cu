@@ -1,0 +1,244 @@
+// C-ABI entry points of the tcgen05 implicit-GEMM conv: geometry planner, weight packer, launcher.
+#include "../../include/oai_b200.h"
+#include "api_common.h"
+#include "conv_igemm.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstring>
+#include <vector>
+
+namespace oai {
+
+cudaError_t conv_igemm_launch(const ConvIgemmParams& p, const CUtensorMap& tm0, const CUtensorMap& tm1, int num_sms,
+                              cudaStream_t stream);
+
+namespace {
+
+constexpr int kFlagForcePerTap = 1;
+constexpr int kFlagBaseOffFormula = 2;  // debug: descriptor base_offset = (addr>>7)&7 (measured WRONG on B200)
+constexpr int kFlagForceKd1 = 4;
+constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8;  // 227 KB minus alignment slack and barriers
+
+struct Plan {
+  int mode, kd_per_block, R, nhalf, cph, nblk, nchunk0, nchunk1, k16, TW, TH, n_wbuf, n_astage;
+  uint32_t wblock_bytes, astage_bytes, astage_stride;
+};
+
+int make_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int flags, Plan* pl) {
+  OAI_REQUIRE(D > 0 && H > 0 && W > 0 && c0 > 0 && c1 >= 0 && cout > 0, "conv plan: bad dims");
+  OAI_REQUIRE(c0 % 8 == 0 && c1 % 8 == 0, "conv plan: channel counts must be multiples of 8 (got %d,%d)", c0, c1);
+  pl->TW = W < 128 ? W : 128;
+  OAI_REQUIRE(128 % pl->TW == 0 && W % pl->TW == 0, "conv plan: W=%d must divide or be a multiple of 128", W);
+  pl->TH = 128 / pl->TW;
+  OAI_REQUIRE(H % pl->TH == 0, "conv plan: H=%d not a multiple of the %d-row M tile", H, pl->TH);
+  pl->nhalf = (cout + 255) / 256;
+  OAI_REQUIRE(cout % pl->nhalf == 0, "conv plan: cout=%d not divisible into %d N splits", cout, pl->nhalf);
+  pl->cph = cout / pl->nhalf;
+  OAI_REQUIRE(pl->cph % 32 == 0, "conv plan: cout per split (%d) must be a multiple of 32", pl->cph);
+  int R = 1;
+  for (int r = 1; r <= 8; ++r)
+    if (D % r == 0 && r * pl->cph <= 512) R = r;
+  pl->R = R;
+  pl->nchunk0 = (c0 + 63) / 64;
+  pl->nchunk1 = (c1 + 63) / 64;
+  pl->k16 = (c1 == 0 && c0 <= 32) ? (c0 <= 16 ? 1 : 2) : 4;
+  const int nch = pl->nchunk0 + pl->nchunk1;
+  if (pointwise) {
+    pl->mode = kModePointwise;
+    pl->kd_per_block = 1;
+    pl->wblock_bytes = pl->cph * 128;
+    pl->nblk = nch;
+    pl->n_wbuf = 3;
+  } else if (pl->TW == 128 && pl->cph <= 64 && !(flags & kFlagForcePerTap)) {
+    pl->mode = kModeRowShared;
+    pl->kd_per_block = 3;
+    pl->wblock_bytes = 9 * pl->cph * 128;
+    pl->nblk = nch * 3;
+    pl->n_wbuf = 2;
+  } else {
+    pl->mode = kModePerTap;
+    pl->kd_per_block = (pl->cph <= 128 && !(flags & kFlagForceKd1)) ? 3 : 1;
+    pl->wblock_bytes = pl->kd_per_block * pl->cph * 128;
+    pl->nblk = nch * (pl->kd_per_block == 3 ? 9 : 27);
+    pl->n_wbuf = pl->kd_per_block == 3 ? 2 : 3;
+  }
+  if (pl->mode == kModeRowShared) {
+    pl->astage_bytes = 130 * 128;
+    pl->astage_stride = 17 * 1024;
+  } else {
+    pl->astage_bytes = 128 * 128;
+    pl->astage_stride = 16 * 1024;
+  }
+  const size_t wstride = (pl->wblock_bytes + 1023u) & ~size_t(1023);
+  const size_t left = kSmemBudget - pl->n_wbuf * wstride;
+  int ns = static_cast<int>(left / pl->astage_stride);
+  if (ns > 8) ns = 8;
+  OAI_REQUIRE(ns >= 2, "conv plan: shared memory budget leaves %d A stages", ns);
+  pl->n_astage = ns;
+  return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NDHWC 16-bit activation tensor viewed as a rank-5 TMA tensor (C, W, H, D, N); box = (64, bw, bh, 1, 1).
+int make_act_tmap(CUtensorMap* tm, const void* base, int C, int W, int H, int D, int N, int bw, int bh, int fmt) {
+  EncodeTiledFn fn = encode_fn();
+  OAI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  OAI_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (C=%d W=%d H=%d D=%d N=%d box %dx%d)", (int)r,
+              C, W, H, D, N, bw, bh);
+  return 0;
+}
+
+inline uint16_t to16(float x, int fmt) {
+  if (fmt == 0) {
+    __half h = __float2half_rn(x);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+  }
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+
+}  // namespace
+}  // namespace oai
+
+using namespace oai;
+
+extern "C" int oai_conv3d_igemm_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int flags,
+                                     int* plan) {
+  Plan pl;
+  if (make_plan(D, H, W, c0, c1, cout, pointwise, flags, &pl)) return 1;
+  plan[0] = pl.mode;
+  plan[1] = pl.kd_per_block;
+  plan[2] = pl.R;
+  plan[3] = pl.nhalf;
+  plan[4] = pl.cph;
+  plan[5] = pl.nblk;
+  plan[6] = static_cast<int>(pl.wblock_bytes);
+  plan[7] = pl.nchunk0 + pl.nchunk1;
+  return 0;
+}
+
+extern "C" int oai_pack_conv_weights(const float* w, int cout, int c0, int c1, int D, int H, int W, int pointwise,
+                                     int ab_format, int flags, void* dst, size_t dst_bytes) {
+  Plan pl;
+  if (make_plan(D, H, W, c0, c1, cout, pointwise, flags, &pl)) return 1;
+  const size_t need = static_cast<size_t>(pl.nhalf) * pl.nblk * pl.wblock_bytes;
+  OAI_REQUIRE(dst_bytes >= need, "pack: dst holds %zu bytes, need %zu", dst_bytes, need);
+  const int cin = c0 + c1;
+  const int ktaps = pointwise ? 1 : 27;
+  uint8_t* out = static_cast<uint8_t*>(dst);
+  memset(out, 0, need);
+  for (int nh = 0; nh < pl.nhalf; ++nh) {
+    for (int b = 0; b < pl.nblk; ++b) {
+      uint8_t* blk = out + (static_cast<size_t>(nh) * pl.nblk + b) * pl.wblock_bytes;
+      // decode block exactly as the kernel does
+      int c, kh, kw0, nkw, kdlo, nkd;
+      if (pl.mode == kModeRowShared) {
+        c = b / 3; kh = b % 3; kw0 = 0; nkw = 3; kdlo = 0; nkd = 3;
+      } else if (pl.mode == kModePerTap) {
+        if (pl.kd_per_block == 3) {
+          c = b / 9; const int r = b % 9; kh = r / 3; kw0 = r % 3; nkw = 1; kdlo = 0; nkd = 3;
+        } else {
+          c = b / 27; const int r = b % 27; kh = r / 9; kw0 = (r / 3) % 3; nkw = 1; kdlo = r % 3; nkd = 1;
+        }
+      } else {
+        c = b; kh = 0; kw0 = 0; nkw = 1; kdlo = 0; nkd = 1;
+      }
+      const bool s0 = c < pl.nchunk0;
+      const int cbase = s0 ? c * 64 : c0 + (c - pl.nchunk0) * 64;
+      const int climit = s0 ? c0 : cin;
+      for (int kwi = 0; kwi < nkw; ++kwi) {
+        for (int ti = 0; ti < nkd; ++ti) {
+          const int kd = kdlo + nkd - 1 - ti;
+          const int kw = kw0 + kwi;
+          const int tap = pointwise ? 0 : (kd * 3 + kh) * 3 + kw;
+          for (int co = 0; co < pl.cph; ++co) {
+            const int r = (kwi * nkd + ti) * pl.cph + co;
+            const float* wrow = w + (static_cast<size_t>(nh * pl.cph + co) * cin) * ktaps;
+            for (int j = 0; j < 64; ++j) {
+              const int ci = cbase + j;
+              if (ci >= climit) break;
+              const float v = wrow[static_cast<size_t>(ci) * ktaps + tap];
+              const size_t off = static_cast<size_t>(r) * 128 + (((j >> 3) ^ (r & 7)) << 4) + (j & 7) * 2;
+              const uint16_t h = to16(v, ab_format);
+              memcpy(blk + off, &h, 2);
+            }
+          }
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+extern "C" int oai_conv3d_igemm(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
+                                const void* wpack, size_t wpack_bytes, const float* bias, int cout, int pointwise,
+                                int relu, int ab_format, void* out, long long obase, long long osN, long long osD,
+                                long long osH, long long osW, int flags, void* stream) {
+  Plan pl;
+  if (make_plan(D, H, W, c0, c1, cout, pointwise, flags, &pl)) return 1;
+  OAI_REQUIRE(src0 && wpack && bias && out, "conv: null pointer");
+  OAI_REQUIRE((c1 == 0) == (src1 == nullptr), "conv: src1/c1 mismatch");
+  const size_t need = static_cast<size_t>(pl.nhalf) * pl.nblk * pl.wblock_bytes;
+  OAI_REQUIRE(wpack_bytes == need, "conv: packed weights are %zu bytes, geometry needs %zu", wpack_bytes, need);
+  OAI_REQUIRE(obase % 8 == 0 && osN % 8 == 0 && osD % 8 == 0 && osH % 8 == 0 && osW % 8 == 0,
+              "conv: output strides must keep 16-byte alignment");
+
+  ConvIgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.NT = NT; p.D = D; p.H = H; p.W = W;
+  p.TW = pl.TW; p.TH = pl.TH; p.R = pl.R;
+  p.cout = pl.cph; p.nhalf = pl.nhalf;
+  p.nchunk0 = pl.nchunk0; p.nchunk1 = pl.nchunk1; p.k16_steps = pl.k16;
+  p.mode = pl.mode; p.kd_per_block = pl.kd_per_block; p.nblk = pl.nblk;
+  p.wblock_bytes = pl.wblock_bytes; p.n_wbuf = pl.n_wbuf; p.n_astage = pl.n_astage;
+  p.astage_bytes = pl.astage_bytes; p.astage_stride = pl.astage_stride;
+  p.ab_format = ab_format; p.relu = relu;
+  p.base_off_mode = (flags & kFlagBaseOffFormula) ? 1 : 0;
+  p.wpack = static_cast<const uint8_t*>(wpack);
+  p.bias = bias;
+  p.out = out;
+  p.obase = obase; p.osN = osN; p.osD = osD; p.osH = osH; p.osW = osW;
+  p.nunits = NT * (D / pl.R) * ((H / pl.TH) * (W / pl.TW)) * pl.nhalf;
+
+  const int bw = pl.mode == kModeRowShared ? 130 : pl.TW;
+  const int bh = pl.TH;
+  CUtensorMap tm0, tm1;
+  if (make_act_tmap(&tm0, src0, c0, W, H, D, NT, bw, bh, ab_format)) return 1;
+  if (src1) {
+    if (make_act_tmap(&tm1, src1, c1, W, H, D, NT, bw, bh, ab_format)) return 1;
+  } else {
+    tm1 = tm0;
+  }
+  cudaError_t e = conv_igemm_launch(p, tm0, tm1, num_sms(), static_cast<cudaStream_t>(stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(e, "conv_igemm launch");
+}

@@ -1,0 +1,339 @@
+// tcgen05 implicit-GEMM 3-D convolution for sm_100a (B200).
+//
+// Replaces the cuDNN/oneDNN calls behind nn.Conv3d(k3,p1), nn.ConvTranspose3d(k3,s1,p1) (== conv with flipped
+// weights) and nn.ConvTranspose3d(k2,s2) (== 8 pointwise GEMMs + pixel shuffle) of the reference segmentation UNet
+// (reference: oai_analysis/segmentation/networks.py:80-107 layer builders, :109-149 forward).
+//
+// Design (input-tile stationary, taps stacked along N):
+//   * activations are NDHWC 16-bit; one M tile = 128 voxels of one d-slice (TH x TW patch);
+//   * a unit owns R consecutive output d-slices of one patch: R accumulators of [128 x cout] fp32 in TMEM
+//     (R*cout <= 512 columns);
+//   * an input tile (slice d') feeds the outputs d'-1, d', d'+1 through the taps kd = 2,1,0, whose weight rows sit
+//     next to each other in shared memory, so ONE tcgen05.mma with N = 3*cout (<=256) updates three adjacent
+//     accumulators while reading the A tile from shared memory once;
+//   * in row-shared mode (full-resolution level, TW = W = 128) the A tile is a 130-voxel row (w halo, TMA zero fill)
+//     and the three kw taps are the same buffer shifted by one 128-byte row;
+//   * weights arrive as pre-swizzled blocks by cp.async.bulk and stay resident while the unit walks its input
+//     slices; the K loop can read two sources (decoder skip connection) so torch.cat is never materialised;
+//   * warp roles: 0 = TMA producer (activations), 1 = bulk producer (weights), 2 = MMA issuer + TMEM owner,
+//     4..7 = epilogue (TMEM -> registers -> bias/ReLU -> 16-bit NDHWC store, overlapped per accumulator).
+#include "conv_igemm.cuh"
+#include "ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace oai {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+
+struct BlockInfo {
+  int c, kh, kw, kdlo, nkd;
+};
+
+__device__ __forceinline__ BlockInfo decode_block(const ConvIgemmParams& p, int b) {
+  BlockInfo bi;
+  if (p.mode == kModeRowShared) {
+    bi.c = b / 3;
+    bi.kh = b % 3;
+    bi.kw = 0;
+    bi.kdlo = 0;
+    bi.nkd = 3;
+  } else if (p.mode == kModePerTap) {
+    if (p.kd_per_block == 3) {
+      bi.c = b / 9;
+      const int r = b % 9;
+      bi.kh = r / 3;
+      bi.kw = r % 3;
+      bi.kdlo = 0;
+      bi.nkd = 3;
+    } else {
+      bi.c = b / 27;
+      const int r = b % 27;
+      bi.kh = r / 9;
+      bi.kw = (r / 3) % 3;
+      bi.kdlo = r % 3;
+      bi.nkd = 1;
+    }
+  } else {
+    bi.c = b;
+    bi.kh = 1;
+    bi.kw = 1;
+    bi.kdlo = 1;
+    bi.nkd = 1;
+  }
+  return bi;
+}
+
+struct UnitInfo {
+  int n, d0, h0, w0, nh;
+};
+
+__device__ __forceinline__ UnitInfo decode_unit(const ConvIgemmParams& p, int u) {
+  UnitInfo ui;
+  const int npw = p.W / p.TW, nph = p.H / p.TH;
+  const int np = npw * nph, ndg = p.D / p.R;
+  ui.nh = u % p.nhalf;
+  u /= p.nhalf;
+  const int patch = u % np;
+  u /= np;
+  ui.d0 = (u % ndg) * p.R;
+  ui.n = u / ndg;
+  ui.h0 = (patch / npw) * p.TH;
+  ui.w0 = (patch % npw) * p.TW;
+  return ui;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
+  if (fmt == 0) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                  const __grid_constant__ ConvIgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t wstride = (p.wblock_bytes + 1023u) & ~1023u;
+  uint8_t* wbuf = smem;
+  uint8_t* abuf = wbuf + static_cast<size_t>(p.n_wbuf) * wstride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(abuf + static_cast<size_t>(p.n_astage) * p.astage_stride);
+  uint64_t* full_a = bars;        // [8]
+  uint64_t* empty_a = bars + 8;   // [8]
+  uint64_t* full_w = bars + 16;   // [4]
+  uint64_t* empty_w = bars + 20;  // [4]
+  uint64_t* acc_full = bars + 24;   // [8]
+  uint64_t* acc_empty = bars + 32;  // [8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&full_a[i], 1);
+      mbar_init(&empty_a[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&full_w[i], 1);
+      mbar_init(&empty_w[i], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm0);
+    tma_prefetch_desc(&tm1);
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkw = (p.mode == kModeRowShared) ? 3 : 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ activation producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+        const UnitInfo ui = decode_unit(p, u);
+        for (int b = 0; b < p.nblk; ++b) {
+          const BlockInfo bi = decode_block(p, b);
+          const bool src0 = bi.c < p.nchunk0;
+          const CUtensorMap* tm = src0 ? &tm0 : &tm1;
+          const int cc = (src0 ? bi.c : bi.c - p.nchunk0) * 64;
+          const int kdhi = bi.kdlo + bi.nkd - 1;
+          const int dlo = max(0, ui.d0 + bi.kdlo - 1);
+          const int dhi = min(p.D - 1, ui.d0 + p.R - 1 + kdhi - 1);
+          const int cw = (p.mode == kModeRowShared) ? ui.w0 - 1 : ui.w0 + bi.kw - 1;
+          const int ch = ui.h0 + bi.kh - 1;
+          for (int dp = dlo; dp <= dhi; ++dp) {
+            mbar_wait(&empty_a[stage], phase ^ 1u, 100 + stage);
+            mbar_arrive_expect_tx(&full_a[stage], p.astage_bytes);
+            tma_load_5d(abuf + static_cast<size_t>(stage) * p.astage_stride, tm, &full_a[stage], cc, cw, ch, dp, ui.n);
+            if (++stage == p.n_astage) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      int wb = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+        const UnitInfo ui = decode_unit(p, u);
+        const uint8_t* src = p.wpack + static_cast<size_t>(ui.nh) * p.nblk * p.wblock_bytes;
+        for (int b = 0; b < p.nblk; ++b) {
+          mbar_wait(&empty_w[wb], phase ^ 1u, 200 + wb);
+          mbar_arrive_expect_tx(&full_w[wb], p.wblock_bytes);
+          bulk_load(wbuf + static_cast<size_t>(wb) * wstride, src + static_cast<size_t>(b) * p.wblock_bytes,
+                    p.wblock_bytes, &full_w[wb]);
+          if (++wb == p.n_wbuf) {
+            wb = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0, wb = 0;
+      uint32_t aphase = 0, wphase = 0, it = 0;
+      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
+        const UnitInfo ui = decode_unit(p, u);
+        uint32_t touched = 0, signaled = 0;
+        for (int b = 0; b < p.nblk; ++b) {
+          const BlockInfo bi = decode_block(p, b);
+          const int kdhi = bi.kdlo + bi.nkd - 1;
+          const int dlo = max(0, ui.d0 + bi.kdlo - 1);
+          const int dhi = min(p.D - 1, ui.d0 + p.R - 1 + kdhi - 1);
+          mbar_wait(&full_w[wb], wphase, 300 + wb);
+          tc_fence_after();
+          const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
+          for (int dp = dlo; dp <= dhi; ++dp) {
+            mbar_wait(&full_a[stage], aphase, 400 + stage);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
+            const int a_first = dp - kdhi + 1 - ui.d0;  // accumulator hit by the first (highest-kd) tap
+            const int ti_lo = max(0, -a_first);
+            const int ti_hi = min(bi.nkd - 1, p.R - 1 - a_first);
+            for (int kw = 0; kw < nkw; ++kw) {
+              int ti = ti_lo;
+              while (ti <= ti_hi) {
+                const int a0 = a_first + ti;
+                const uint32_t f = (touched >> a0) & 1u;
+                int len = 1;
+                while (ti + len <= ti_hi && ((touched >> (a0 + len)) & 1u) == f && (len + 1) * p.cout <= 256) ++len;
+                if (!f) {
+                  for (int j = 0; j < len; ++j) mbar_wait(&acc_empty[a0 + j], (it & 1u) ^ 1u, 500 + a0 + j);
+                  tc_fence_after();
+                }
+                const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * p.cout), p.ab_format);
+                const uint32_t a_addr = a_base + static_cast<uint32_t>(kw) * 128u;
+                const uint32_t b_addr = w_base + static_cast<uint32_t>((kw * bi.nkd + ti) * p.cout) * 128u;
+                const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
+                const uint32_t d_addr = tmem_base + static_cast<uint32_t>(a0 * p.cout);
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  if (k16 >= p.k16_steps) break;
+                  const uint64_t adesc = umma_desc_sw128(a_addr + k16 * 32, 1024, boff);
+                  const uint64_t bdesc = umma_desc_sw128(b_addr + k16 * 32, 1024, 0);
+                  umma_f16_ss(d_addr, adesc, bdesc, idesc, (f | (k16 > 0)) ? 1u : 0u);
+                }
+                touched |= ((1u << len) - 1u) << a0;
+                ti += len;
+              }
+            }
+            umma_commit(&empty_a[stage]);
+            if (++stage == p.n_astage) {
+              stage = 0;
+              aphase ^= 1u;
+            }
+            if (b == p.nblk - 1 && a_first >= 0 && a_first < p.R) {
+              umma_commit(&acc_full[a_first]);
+              signaled |= 1u << a_first;
+            }
+          }
+          umma_commit(&empty_w[wb]);
+          if (++wb == p.n_wbuf) {
+            wb = 0;
+            wphase ^= 1u;
+          }
+        }
+        for (int a = 0; a < p.R; ++a)
+          if (!((signaled >> a) & 1u)) umma_commit(&acc_full[a]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int th = m / p.TW, tw = m % p.TW;
+    uint32_t it = 0;
+    uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
+      const UnitInfo ui = decode_unit(p, u);
+      const long long off0 = p.obase + ui.n * p.osN + (ui.h0 + th) * p.osH + (ui.w0 + tw) * p.osW +
+                             static_cast<long long>(ui.nh) * p.cout;
+      const float* bias = p.bias + ui.nh * p.cout;
+      for (int a = 0; a < p.R; ++a) {
+        mbar_wait(&acc_full[a], it & 1u, 600 + a);
+        tc_fence_after();
+        uint16_t* dst = out + off0 + (ui.d0 + a) * p.osD;
+        for (int j = 0; j < p.cout / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a * p.cout + j * 32),
+                        v);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x0 = __uint_as_float(v[2 * i]) + __ldg(bias + j * 32 + 2 * i);
+            float x1 = __uint_as_float(v[2 * i + 1]) + __ldg(bias + j * 32 + 2 * i + 1);
+            if (p.relu) {
+              x0 = fmaxf(x0, 0.f);
+              x1 = fmaxf(x1, 0.f);
+            }
+            o[i] = pack2(x0, x1, p.ab_format);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(dst + j * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[a]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+
+static size_t conv_igemm_smem_bytes(const ConvIgemmParams& p) {
+  const size_t wstride = (p.wblock_bytes + 1023u) & ~size_t(1023);
+  return 1024 + p.n_wbuf * wstride + static_cast<size_t>(p.n_astage) * p.astage_stride + 48 * 8;
+}
+
+cudaError_t conv_igemm_launch(const ConvIgemmParams& p, const CUtensorMap& tm0, const CUtensorMap& tm1, int num_sms,
+                              cudaStream_t stream) {
+  const size_t smem = conv_igemm_smem_bytes(p);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int grid = p.nunits < num_sms ? p.nunits : num_sms;
+  conv_igemm_kernel<<<grid, kThreads, smem, stream>>>(tm0, tm1, p);
+  return cudaGetLastError();
+}
+
+}  // namespace oai

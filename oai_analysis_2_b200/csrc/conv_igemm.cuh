@@ -1,0 +1,45 @@
+// Parameter block shared by the tcgen05 implicit-GEMM conv kernel and its host launcher.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace oai {
+
+enum ConvMode : int {
+  kModeRowShared = 0,  // 3x3x3, M tile = one full 128-wide row; w halo loaded once, kw taps = smem row shifts
+  kModePerTap = 1,     // 3x3x3, one TMA box per (kh,kw) shift; M tile = TH x TW patch
+  kModePointwise = 2,  // 1x1x1 (also each of the 8 sub-filters of a k2 s2 transposed conv)
+};
+
+struct ConvIgemmParams {
+  // activation grid (identical for input and output: stride-1 "same" conv or pointwise)
+  int NT, D, H, W;
+  int TW, TH;       // M tile = TH x TW voxels in one d-slice (TH*TW == 128)
+  int R;            // accumulators per unit = consecutive output d-slices (R*cout <= 512, D % R == 0)
+  int cout;         // N per accumulator (multiple of 16, <= 256)
+  int nhalf;        // N splits (cout_total = nhalf*cout)
+  int nchunk0;      // 64-channel K chunks read from source 0
+  int nchunk1;      // ... then from source 1 (skip connection); 0 if single source
+  int k16_steps;    // K=16 MMA steps per chunk: 4 (64 channels) or 2 (a 32-channel source, upper half TMA zero-filled)
+  int mode;         // ConvMode
+  int kd_per_block; // 3: weights block stacks kd=2,1,0 ; 1: one kd per block
+  int nblk;         // weight blocks per (unit, nhalf)
+  uint32_t wblock_bytes;
+  int n_wbuf;       // weight buffers in smem
+  int n_astage;     // A ring depth
+  uint32_t astage_bytes;  // bytes landed per A stage (expect_tx)
+  uint32_t astage_stride; // smem stride between A stages (1024-aligned)
+  int ab_format;    // 0 fp16, 1 bf16
+  int relu;
+  int base_off_mode;  // row-shared mode: 0 (correct on B200: the swizzle XOR uses absolute smem address bits) or
+                      // 1 = descriptor base_offset = (addr>>7)&7 (kept for the bring-up test; gives wrong results)
+  const uint8_t* wpack;   // [nhalf][nblk][wblock_bytes] pre-swizzled smem images
+  const float* bias;      // [nhalf*cout]
+  // output addressing (element units, 16-bit elements): off = obase + n*osN + d*osD + h*osH + w*osW + nh*cout + c
+  void* out;
+  long long obase, osN, osD, osH, osW;
+  int nunits;
+};
+
+}  // namespace oai

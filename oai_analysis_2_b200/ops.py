@@ -1,0 +1,53 @@
+"""Thin Python wrappers over the C-ABI ops (torch tensors in, torch tensors out; torch is only the allocator)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import c_int, c_ll, c_size, check, lib, ptr, stream_ptr
+
+FLAG_FORCE_PER_TAP = 1
+FLAG_BASE_OFF_FORMULA = 2
+FLAG_FORCE_KD1 = 4
+
+_DT16 = {0: torch.float16, 1: torch.bfloat16}
+
+
+def conv_plan(D, H, W, c0, c1, cout, pointwise=False, flags=0):
+    plan = (c_int * 8)()
+    check(lib.oai_conv3d_igemm_plan(D, H, W, c0, c1, cout, int(pointwise), flags, plan), "conv plan")
+    keys = ("mode", "kd_per_block", "R", "nhalf", "cout_per_half", "nblk", "wblock_bytes", "nchunks")
+    return dict(zip(keys, list(plan)))
+
+
+def pack_conv_weights(w, c0, c1, D, H, W, pointwise=False, ab_format=0, flags=0, device="cuda"):
+    """w: float32 [cout, c0+c1, 3,3,3] (conv orientation) or [cout, c0+c1] when pointwise.  Returns a uint8 tensor."""
+    w = np.ascontiguousarray(w.detach().cpu().numpy() if hasattr(w, "detach") else w, dtype=np.float32)
+    cout = w.shape[0]
+    assert w.shape[1] == c0 + c1
+    pl = conv_plan(D, H, W, c0, c1, cout, pointwise, flags)
+    nbytes = pl["nhalf"] * pl["nblk"] * pl["wblock_bytes"]
+    dst = np.zeros(nbytes, dtype=np.uint8)
+    check(lib.oai_pack_conv_weights(ptr(w), cout, c0, c1, D, H, W, int(pointwise), ab_format, flags, ptr(dst),
+                                    c_size(nbytes)), "pack weights")
+    return torch.from_numpy(dst).to(device)
+
+
+def conv3d_igemm(src0, src1, wpack, bias, cout, pointwise=False, relu=True, ab_format=0, out=None, out_view=None,
+                 flags=0):
+    """src*: [NT, D, H, W, C] 16-bit channels-last.  Returns [NT, D, H, W, cout] unless `out`/`out_view` given.
+
+    out_view = (obase, osN, osD, osH, osW) in elements addresses into `out` (k2s2 transposed-conv scatter).
+    """
+    NT, D, H, W, c0 = src0.shape
+    c1 = 0 if src1 is None else src1.shape[-1]
+    assert src0.is_contiguous() and (src1 is None or src1.is_contiguous())
+    if out is None:
+        out = torch.empty((NT, D, H, W, cout), dtype=_DT16[ab_format], device=src0.device)
+    if out_view is None:
+        out_view = (0, D * H * W * cout, H * W * cout, W * cout, cout)
+    ob, sn, sd, sh, sw = out_view
+    check(lib.oai_conv3d_igemm(ptr(src0), c0, ptr(src1), c1, NT, D, H, W, ptr(wpack), c_size(wpack.numel()),
+                               ptr(bias), cout, int(pointwise), int(relu), ab_format, ptr(out), c_ll(ob), c_ll(sn),
+                               c_ll(sd), c_ll(sh), c_ll(sw), flags, stream_ptr()), "conv3d_igemm")
+    return out
