@@ -64,6 +64,26 @@ OAI_API int oai_conv3d_igemm_plan(int D, int H, int W, int c0, int c1, int cout,
 OAI_API int oai_pack_conv_weights(const float* w, int cout, int c0, int c1, int D, int H, int W, int pointwise, int ab_format,
                           int flags, void* dst, size_t dst_bytes);
 
+/* Tiling geometry arrays used below (all z,y,x): geom[12] = {tile[3], effective[3], overlap[3], grid[3]} exactly as
+ * Partition computes them (image_transforms.py:389-391,404-406); vol_dims[3] = image size. */
+
+/* Partition.__call__ (image_transforms.py:408-446: reflect pad + overlap tiling) fused with the first UNet layer
+ * ec0 = Conv3d(1->c0,k3,p1)[+BN]+ReLU (networks.py:43,84-86).  Reads the float32 volume in place (tiles are never
+ * materialised), writes act16 [ntiles, td, th, tw, c0] for tiles tile0 .. tile0+ntiles-1 (i-major tile order).
+ * w27c: folded weights [27][c0] (tap = (kd*3+kh)*3+kw), bias [c0]. */
+OAI_API int oai_seg_stem(const float* vol, const int* vol_dims, const int* geom, int tile0, int ntiles,
+                         const float* w27c, const float* bias, int c0, void* out, int ab_format, void* stream);
+
+/* nn.MaxPool3d(2) (networks.py:52-54) on act16 [N,D,H,W,C] -> [N,D/2,H/2,W/2,C]. */
+OAI_API int oai_maxpool3d_2(const void* in, void* out, int N, int D, int H, int W, int C, int ab_format, void* stream);
+
+/* dc0 = Conv3d(C->ncls,k1) (networks.py:66,148) + torch.sigmoid (segmenter.py:121) [+ ">0.5" when out_mode==1,
+ * segmenter.py:123-124; out_mode==2 writes raw logits] + Partition.assemble (image_transforms.py:492-513): each tile's interior is written to its
+ * place in out[ncls][VD][VH][VW] (float32), trimmed to the image, with the crop_zyx border shell set to 0. */
+OAI_API int oai_seg_head(const void* act, int C, int ncls, const float* w, const float* b, float* out,
+                         const int* vol_dims, const int* geom, int tile0, int ntiles, const int* crop_zyx, int out_mode,
+                         int ab_format, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,227 @@
+// Bandwidth-bound pieces of the segmentation stage that sit around the tcgen05 convolutions:
+//   stem  : reflect-pad + overlap-tile gather (Partition.__call__, image_transforms.py:408-446) fused with the first
+//           conv ec0 (Conv3d 1->C0 k3 p1 + folded BN + ReLU, networks.py:43) -> NDHWC 16-bit
+//   pool  : MaxPool3d(2) (networks.py:52-54) on NDHWC 16-bit
+//   head  : dc0 (Conv3d 64->n_classes k1, networks.py:66,148) + torch.sigmoid (segmenter.py:121) [+ >0.5,
+//           segmenter.py:123-124] + Partition.assemble crop-and-place with the zeroed border shell
+//           (image_transforms.py:492-513), writing float32 class volumes
+#include "api_common.h"
+#include "seg_misc.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace oai {
+
+__device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
+  if (fmt == 0) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t u, int fmt) {
+  if (fmt == 0) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+// numpy 'reflect' (edge sample not repeated), valid for pads smaller than the axis length
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (n == 1) return 0;
+  const int period = 2 * (n - 1);
+  i %= period;
+  if (i < 0) i += period;
+  return i < n ? i : period - i;
+}
+
+
+constexpr int kStemTW = 32, kStemTH = 4;  // output patch per block (x, y); one d-slice
+
+__global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
+  extern __shared__ __align__(16) float s_stem[];
+  float* s_w = s_stem;                 // 27*c0
+  float* s_b = s_w + 27 * p.c0;        // c0
+  float* s_in = s_b + p.c0;            // [3][kStemTH+2][kStemTW+2]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * p.c0; i += blockDim.x) s_w[i] = p.w[i];
+  for (int i = tid; i < p.c0; i += blockDim.x) s_b[i] = p.b[i];
+
+  const int nbx = (p.tw + kStemTW - 1) / kStemTW, nby = (p.th + kStemTH - 1) / kStemTH;
+  int blk = blockIdx.x;
+  const int bx = blk % nbx; blk /= nbx;
+  const int by = blk % nby; blk /= nby;
+  const int d = blk % p.td; blk /= p.td;
+  const int t = blk;  // tile within batch
+  const int tile = p.tile0 + t;
+  const int tk = tile % p.gw, tj = (tile / p.gw) % p.gh, ti = tile / (p.gw * p.gh);
+  // tile origin in padded coordinates minus the leading pad == image coordinates of tile voxel (0,0,0)
+  const int oz = ti * p.ed - p.od, oy = tj * p.eh - p.oh, ox = tk * p.ew - p.ow;
+  const int x0 = bx * kStemTW, y0 = by * kStemTH;
+
+  constexpr int SW = kStemTW + 2, SH = kStemTH + 2;
+  for (int i = tid; i < 3 * SH * SW; i += blockDim.x) {
+    const int xx = i % SW, yy = (i / SW) % SH, zz = i / (SW * SH);
+    const int lz = d + zz - 1, ly = y0 + yy - 1, lx = x0 + xx - 1;  // tile-local coordinates
+    float v = 0.f;  // conv zero padding at the TILE border
+    if (lz >= 0 && lz < p.td && ly >= 0 && ly < p.th && lx >= 0 && lx < p.tw) {
+      const int gz = reflect_idx(oz + lz, p.VD), gy = reflect_idx(oy + ly, p.VH), gx = reflect_idx(ox + lx, p.VW);
+      v = p.vol[(static_cast<size_t>(gz) * p.VH + gy) * p.VW + gx];
+    }
+    s_in[i] = v;
+  }
+  __syncthreads();
+
+  const int lx = tid % kStemTW, ly = tid / kStemTW;
+  const int x = x0 + lx, y = y0 + ly;
+  if (x >= p.tw || y >= p.th) return;
+  float in[27];
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) in[(kd * 3 + kh) * 3 + kw] = s_in[(kd * SH + ly + kh) * SW + lx + kw];
+  uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) +
+                  ((((static_cast<size_t>(t) * p.td + d) * p.th + y) * p.tw + x) * p.c0);
+  for (int c8 = 0; c8 < p.c0; c8 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = s_b[c8 + j];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4 wa = *reinterpret_cast<const float4*>(s_w + k * p.c0 + c8);
+      const float4 wb = *reinterpret_cast<const float4*>(s_w + k * p.c0 + c8 + 4);
+      acc[0] = fmaf(in[k], wa.x, acc[0]); acc[1] = fmaf(in[k], wa.y, acc[1]);
+      acc[2] = fmaf(in[k], wa.z, acc[2]); acc[3] = fmaf(in[k], wa.w, acc[3]);
+      acc[4] = fmaf(in[k], wb.x, acc[4]); acc[5] = fmaf(in[k], wb.y, acc[5]);
+      acc[6] = fmaf(in[k], wb.z, acc[6]); acc[7] = fmaf(in[k], wb.w, acc[7]);
+    }
+    uint4 o;
+    o.x = pack16(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), p.fmt);
+    o.y = pack16(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f), p.fmt);
+    o.z = pack16(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), p.fmt);
+    o.w = pack16(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f), p.fmt);
+    *reinterpret_cast<uint4*>(dst + c8) = o;
+  }
+}
+
+int stem_launch(const StemParams& p, cudaStream_t st) {
+  const int nbx = (p.tw + kStemTW - 1) / kStemTW, nby = (p.th + kStemTH - 1) / kStemTH;
+  const long long blocks = static_cast<long long>(p.ntiles) * p.td * nby * nbx;
+  const size_t smem = (27 * p.c0 + p.c0 + 3 * (kStemTH + 2) * (kStemTW + 2)) * sizeof(float);
+  stem_kernel<<<static_cast<unsigned>(blocks), 128, smem, st>>>(p);
+  return launched("stem_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ max pool 2x2x2
+__global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N,
+                                                       int D, int H, int W, int C8, int fmt) {
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(N) * Do * Ho * Wo * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int c = r % C8; r /= C8;
+    const int w = r % Wo; r /= Wo;
+    const int h = r % Ho; r /= Ho;
+    const int d = r % Do; r /= Do;
+    const int n = static_cast<int>(r);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t off =
+              ((((static_cast<size_t>(n) * D + 2 * d + dz) * H + 2 * h + dy) * W + 2 * w + dx) * C8) + c;
+          const uint4 v = __ldg(in + off);
+          const float2 a = unpack16(v.x, fmt), b = unpack16(v.y, fmt), cc = unpack16(v.z, fmt), e = unpack16(v.w, fmt);
+          m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], b.x); m[3] = fmaxf(m[3], b.y);
+          m[4] = fmaxf(m[4], cc.x); m[5] = fmaxf(m[5], cc.y); m[6] = fmaxf(m[6], e.x); m[7] = fmaxf(m[7], e.y);
+        }
+    uint4 o;
+    o.x = pack16(m[0], m[1], fmt); o.y = pack16(m[2], m[3], fmt);
+    o.z = pack16(m[4], m[5], fmt); o.w = pack16(m[6], m[7], fmt);
+    out[i] = o;
+  }
+}
+
+int maxpool2_launch(const void* in, void* out, int N, int D, int H, int W, int C, int fmt, cudaStream_t st) {
+  const long long total = static_cast<long long>(N) * (D / 2) * (H / 2) * (W / 2) * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  maxpool2_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const uint4*>(in),
+                                                                   static_cast<uint4*>(out), N, D, H, W, C / 8, fmt);
+  return launched("maxpool2_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------ head
+
+__global__ void __launch_bounds__(128) head_kernel(const HeadParams p) {
+  __shared__ float s_w[8 * 64 + 8];
+  for (int i = threadIdx.x; i < p.ncls * p.C; i += blockDim.x) s_w[i] = p.w[i];
+  for (int i = threadIdx.x; i < p.ncls; i += blockDim.x) s_w[p.ncls * p.C + i] = p.b[i];
+  __syncthreads();
+  // one thread per interior voxel of a tile: interior = [od, od+ed) x [oh, oh+eh) x [ow, ow+ew)
+  const long long per_tile = static_cast<long long>(p.ed) * p.eh * p.ew;
+  const long long total = per_tile * p.ntiles;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int x = r % p.ew; r /= p.ew;
+    const int y = r % p.eh; r /= p.eh;
+    const int z = r % p.ed; r /= p.ed;
+    const int t = static_cast<int>(r);
+    const int tile = p.tile0 + t;
+    const int tk = tile % p.gw, tj = (tile / p.gw) % p.gh, ti = tile / (p.gw * p.gh);
+    const int gz = ti * p.ed + z, gy = tj * p.eh + y, gx = tk * p.ew + x;  // image coordinates
+    if (gz >= p.VD || gy >= p.VH || gx >= p.VW) continue;                 // trimmed (image_transforms.py:504)
+    const bool shell = gz < p.cz || gz >= p.VD - p.cz || gy < p.cy || gy >= p.VH - p.cy || gx < p.cx ||
+                       gx >= p.VW - p.cx;
+    const size_t vox = (((static_cast<size_t>(t) * p.td + z + p.od) * p.th + y + p.oh) * p.tw + x + p.ow);
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.act) + vox * p.C);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (!shell) {
+      for (int c8 = 0; c8 < p.C / 8; ++c8) {
+        const uint4 v = __ldg(src + c8);
+        const float2 a = unpack16(v.x, p.fmt), b = unpack16(v.y, p.fmt), c = unpack16(v.z, p.fmt),
+                     e = unpack16(v.w, p.fmt);
+        const float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, e.x, e.y};
+        for (int k = 0; k < p.ncls; ++k) {
+          const float* wk = s_w + k * p.C + c8 * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k] = fmaf(f[j], wk[j], acc[k]);
+        }
+      }
+    }
+    const size_t o = (static_cast<size_t>(gz) * p.VH + gy) * p.VW + gx;
+    const size_t cls_stride = static_cast<size_t>(p.VD) * p.VH * p.VW;
+    for (int k = 0; k < p.ncls; ++k) {
+      float v = 0.f;
+      if (!shell) {
+        const float logit = acc[k] + s_w[p.ncls * p.C + k];
+        v = p.out_mode == 2 ? logit : 1.f / (1.f + __expf(-logit));
+        if (p.out_mode == 1) v = v > 0.5f ? 1.f : 0.f;
+      }
+      p.out[k * cls_stride + o] = v;
+    }
+  }
+}
+
+int head_launch(const HeadParams& p, cudaStream_t st) {
+  const long long total = static_cast<long long>(p.ed) * p.eh * p.ew * p.ntiles;
+  long long blocks = (total + 127) / 128;
+  const long long cap = static_cast<long long>(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  head_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
+  return launched("head_kernel");
+}
+
+}  // namespace oai

@@ -51,3 +51,39 @@ def conv3d_igemm(src0, src1, wpack, bias, cout, pointwise=False, relu=True, ab_f
                                ptr(bias), cout, int(pointwise), int(relu), ab_format, ptr(out), c_ll(ob), c_ll(sn),
                                c_ll(sd), c_ll(sh), c_ll(sw), flags, stream_ptr()), "conv3d_igemm")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ segmentation misc
+def make_geom(tile_zyx, effective_zyx, overlap_zyx, grid_zyx):
+    """geom[12] = tile, effective, overlap, grid (all z,y,x) as the C ABI expects."""
+    return np.asarray(list(tile_zyx) + list(effective_zyx) + list(overlap_zyx) + list(grid_zyx), dtype=np.int32)
+
+
+def seg_stem(vol, geom, tile0, ntiles, w27c, bias, ab_format=0):
+    """vol: float32 [D,H,W] cuda.  Returns act16 [ntiles, td, th, tw, c0]."""
+    assert vol.dtype == torch.float32 and vol.is_contiguous()
+    dims = np.asarray(vol.shape, dtype=np.int32)
+    c0 = w27c.shape[1]
+    td, th, tw = (int(v) for v in geom[:3])
+    out = torch.empty((ntiles, td, th, tw, c0), dtype=_DT16[ab_format], device=vol.device)
+    check(lib.oai_seg_stem(ptr(vol), ptr(dims), ptr(geom), tile0, ntiles, ptr(w27c), ptr(bias), c0, ptr(out),
+                           ab_format, stream_ptr()), "seg_stem")
+    return out
+
+
+def maxpool2(x, ab_format=0):
+    N, D, H, W, C = x.shape
+    out = torch.empty((N, D // 2, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    check(lib.oai_maxpool3d_2(ptr(x), ptr(out), N, D, H, W, C, ab_format, stream_ptr()), "maxpool3d_2")
+    return out
+
+
+def seg_head(act, w, b, out, geom, tile0, crop_zyx, out_mode=0, ab_format=0):
+    """act: act16 [ntiles, td, th, tw, C]; out: float32 [ncls, VD, VH, VW] (written in place)."""
+    ntiles, C = act.shape[0], act.shape[-1]
+    ncls = w.shape[0]
+    dims = np.asarray(out.shape[1:], dtype=np.int32)
+    crop = np.asarray(crop_zyx, dtype=np.int32)
+    check(lib.oai_seg_head(ptr(act), C, ncls, ptr(w), ptr(b), ptr(out), ptr(dims), ptr(geom), tile0, ntiles,
+                           ptr(crop), out_mode, ab_format, stream_ptr()), "seg_head")
+    return out

@@ -1,0 +1,136 @@
+"""GPU tier: segmentation stage through the C ABI against the oracle / the reference-generated golden fixtures.
+
+Tolerances are the north-star's: probability max-abs error <= 1e-2 and Dice >= 0.999 against the reference masks."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import dice, load_golden, write_seg_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def test_library_loaded_and_counts_launches():
+    _cuda()
+    from oai_analysis_2_b200 import _lib, ops
+    n0 = _lib.launch_count()
+    x = torch.randn(1, 2, 4, 8, 16, device="cuda").half()
+    ops.maxpool2(x)
+    assert _lib.launch_count() == n0 + 1
+
+
+def test_maxpool_matches_torch():
+    _cuda()
+    from oai_analysis_2_b200 import ops
+    x = torch.randn(3, 8, 12, 16, 40, device="cuda").half()
+    got = ops.maxpool2(x)
+    ref = F.max_pool3d(x.permute(0, 4, 1, 2, 3).float(), 2).permute(0, 2, 3, 4, 1)
+    assert torch.equal(got.float(), ref)
+
+
+def test_stem_matches_partition_plus_conv():
+    _cuda()
+    from oai_analysis_2_b200 import ops
+    from oracle.seg_oracle import partition
+    rng = np.random.default_rng(0)
+    vol = rng.standard_normal((11, 37, 29)).astype(np.float32)
+    patch, overlap = [16, 24, 8], (4, 6, 2)   # x,y,z
+    tiles, g = partition(vol, patch, overlap)
+    w = torch.randn(32, 1, 3, 3, 3) * 0.2
+    b = torch.randn(32) * 0.1
+    ref = F.relu(F.conv3d(tiles, w, b, padding=1)).permute(0, 2, 3, 4, 1)
+    geom = ops.make_geom(g["tile"], g["effective"], g["overlap"], g["grid"])
+    got = ops.seg_stem(torch.from_numpy(vol).cuda(), geom, 0, tiles.shape[0],
+                       w.reshape(32, 27).t().contiguous().cuda(), b.cuda())
+    assert (got.float().cpu() - ref).abs().max() < 4e-3
+    part = ops.seg_stem(torch.from_numpy(vol).cuda(), geom, 5, 3, w.reshape(32, 27).t().contiguous().cuda(), b.cuda())
+    assert torch.equal(part, got[5:8])
+
+
+def test_head_matches_sigmoid_assemble():
+    _cuda()
+    from oai_analysis_2_b200 import ops
+    from oracle.seg_oracle import assemble, tiling_geometry
+    shape, patch, overlap = (11, 37, 29), [16, 24, 8], (4, 6, 2)
+    g = tiling_geometry(shape, patch, overlap)
+    T = int(np.prod(g["grid"]))
+    act = torch.randn(T, *g["tile"], 64).half()
+    w, b = torch.randn(2, 64) * 0.3, torch.randn(2)
+    prob = torch.sigmoid(torch.einsum("tdhwc,kc->tkdhw", act.float(), w) + b.view(1, 2, 1, 1, 1))
+    geom = ops.make_geom(g["tile"], g["effective"], g["overlap"], g["grid"])
+    crop = (overlap[2], overlap[0], overlap[1])
+    for mode in (0, 1):
+        out = torch.full((2,) + shape, -7.0, device="cuda")
+        ops.seg_head(act.cuda(), w.cuda(), b.cuda(), out, geom, 0, crop, out_mode=mode)
+        for k in range(2):
+            tiles_k = prob[:, k] if mode == 0 else (prob[:, k] > 0.5).float()
+            ref = assemble(tiles_k.numpy(), g, overlap)
+            err = np.abs(out[k].cpu().numpy() - ref)
+            if mode == 0:
+                assert err.max() < 1e-5
+            else:
+                assert (err > 0).mean() < 1e-4  # a logit within rounding of 0 may flip
+
+
+@pytest.mark.parametrize("name", ["seg_small_pertap", "seg_small_nobn", "seg_prod_tile"])
+def test_segmenter_matches_reference_golden(name, tmp_path):
+    _cuda()
+    from oai_analysis_2_b200.segmentation.segmenter import Segmenter3DInPatchClassWise
+    from oracle.seg_oracle import make_unet_state_dict, synthetic_knee
+    z, m = load_golden(name)
+    sd = make_unet_state_dict(m["seed"], 1, 2, m["bias"], m["BN"], True, m["head_gain"], m["head_bias"])
+    cfg = write_seg_config(tmp_path, sd, m["patch"], m["bias"], m["BN"], m["overlap"])
+    seg = Segmenter3DInPatchClassWise(mode="pred", config=cfg)
+    vol = synthetic_knee(tuple(m["shape"]), m["seed"])
+    fc, tc = seg.segment(vol, if_output_prob_map=True, if_output_itk=False)
+    assert fc.dtype == np.float64 and fc.shape == tuple(m["shape"])
+    e_fc, e_tc = np.abs(fc - z["fc"]).max(), np.abs(tc - z["tc"]).max()
+    fcm, tcm = seg.segment(vol, if_output_prob_map=False, if_output_itk=False)
+    d_fc, d_tc = dice(fcm, z["fc_mask"]), dice(tcm, z["tc_mask"])
+    print(f"{name}: prob max-abs FC {e_fc:.2e} TC {e_tc:.2e}; Dice FC {d_fc:.5f} TC {d_tc:.5f}")
+    assert e_fc <= 1e-2 and e_tc <= 1e-2
+    assert d_fc >= 0.999 and d_tc >= 0.999
+    # border shell is exactly zero (image_transforms.py:509-513)
+    oz, oy, ox = m["overlap"][2], m["overlap"][0], m["overlap"][1]
+    assert fc[:oz].max() == 0 and fc[:, :oy].max() == 0 and fc[:, :, -ox:].max() == 0
+    # itk-style output keeps the input's metadata (image_transforms.py:515-517)
+    from oai_analysis_2_b200 import itk_compat
+    img = itk_compat.Image(vol, spacing=(0.36, 0.36, 0.7), origin=(1, 2, 3))
+    fci, _ = seg.segment(img, if_output_prob_map=True, if_output_itk=True)
+    assert np.allclose(fci.GetSpacing(), (0.36, 0.36, 0.7)) and np.allclose(fci.GetOrigin(), (1, 2, 3))
+    assert np.array_equal(itk_compat.array_from_image(fci), fc)
+
+
+def test_module_forward_matches_oracle_logits():
+    _cuda()
+    from oai_analysis_2_b200.segmentation.networks import UNet
+    from oracle.seg_oracle import make_unet_state_dict, unet_forward
+    sd = make_unet_state_dict(5, 1, 2, True, True, True)
+    net = UNet(1, 2, bias=True, BN=True)
+    net.load_state_dict(sd, strict=True)
+    net.to("cuda").eval()
+    x = torch.rand(2, 1, 16, 128, 64, device="cuda")
+    got = net(x)
+    sd_c = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = unet_forward(sd_c, x, True)
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() < 5e-3 * max(scale, 1.0)
+
+
+def test_missing_checkpoint_raises(tmp_path):
+    _cuda()
+    from oai_analysis_2_b200.segmentation.segmenter import Segmenter3DInPatchClassWise
+    from oracle.seg_oracle import make_unet_state_dict
+    cfg = write_seg_config(tmp_path, make_unet_state_dict(1), [64, 128, 16], True, True, (8, 16, 4))
+    cfg["ckpoint_path"] = str(tmp_path / "nope.pth.tar")
+    with pytest.raises(ValueError):
+        Segmenter3DInPatchClassWise(mode="pred", config=cfg).segment(np.zeros((12, 100, 50), np.float32))
