@@ -84,6 +84,66 @@ OAI_API int oai_seg_head(const void* act, int C, int ncls, const float* w, const
                          const int* vol_dims, const int* geom, int tile0, int ntiles, const int* crop_zyx, int out_mode,
                          int ab_format, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * ICON / GradICON registration  (reference call sites: oai_analysis/registration.py:20,25,
+ * oai_analysis/dask_processing.py:77,85; arithmetic in the un-vendored icon_registration==1.1.2, pyproject.toml:35)
+ * All tensors float32, planar [N][C][D][H][W] with explicit batch / channel strides (elements) so a layer reads and
+ * writes channel slices of the UNet's concatenation buffers in place.  dims arrays are z,y,x.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* icon networks.UNet2 down step / lastConv: Conv3d(k3, p1, stride 1|2) on leaky_relu(in) (when leaky_in)
+ * [+ pad_or_crop(avg_pool3d(in, 2, ceil_mode=True)) when residual], times out_scale.
+ * w packed [cin][27][cout_pad] (tap = (kd*3+kh)*3+kw), bias [cout]. */
+OAI_API int oai_reg_conv3(const float* in, long long in_nstride, long long in_cstride, int cin, const int* in_dims,
+                          const float* w, const float* bias, float* out, long long out_nstride, long long out_cstride,
+                          int cout, int cout_pad, int N, int stride, int leaky_in, int residual, float out_scale,
+                          void* stream);
+
+/* icon networks.UNet2 up step: BatchNorm3d(eval)( ConvTranspose3d(k4,s2,p1)(leaky_relu(in)) +
+ * F.interpolate(in[:, :cout], scale_factor=2, trilinear, align_corners=False) ), cropped to out_dims.
+ * w packed [cin][64][cout] (tap = (kd*4+kh)*4+kw); bn_scale = gamma/sqrt(var+eps), bn_shift = beta - mean*bn_scale. */
+OAI_API int oai_reg_convt4(const float* in, long long in_nstride, long long in_cstride, int cin, const int* in_dims,
+                           const float* w, const float* bias, const float* bn_scale, const float* bn_shift, float* out,
+                           long long out_nstride, long long out_cstride, int cout, const int* out_dims, int N,
+                           void* stream);
+
+/* Composition of displacement maps and image warp, fused (icon network_wrappers.TwoStepRegistration /
+ * FunctionFromVectorField closures; mermaidlite.compute_warped_image_multiNC == F.grid_sample(bilinear, border,
+ * align_corners=True) at 2c-1).  Starting from the identity map of grid_dims (coordinates in [0,1], channel order
+ * z,y,x), applies c <- c + S(fields[k], c) for k = 0..nfields-1 (fields[k] is [3][field_dims[3k..3k+2]]); with
+ * shortcut_first the first field is added without interpolation (FunctionFromVectorField's identity shortcut).
+ * Writes the map to phi_out [3][D][H][W] and/or S(img, c) to img_out [D][H][W] (either may be NULL). */
+OAI_API int oai_compose(const int* grid_dims, int nfields, const float* const* fields, const int* field_dims,
+                        int shortcut_first, const float* img, const int* img_dims, float* phi_out, float* img_out,
+                        void* stream);
+
+/* itk_wrapper.register_pair's F.interpolate(size=..., mode="trilinear", align_corners=False), one channel. */
+OAI_API int oai_resize_trilinear(const float* in, const int* in_dims, float* out, const int* out_dims, void* stream);
+
+/* DownsampleRegistration's F.avg_pool3d(x, 2, ceil_mode=True) on [C][D][H][W]. */
+OAI_API int oai_avgpool3d_2_ceil(const float* in, int C, const int* in_dims, float* out, void* stream);
+
+/* itk_wrapper.create_itk_transform: disp[z][y][x][(x,y,z)] = (phi - identity)[(2,1,0)] * (N - 1), float32. */
+OAI_API int oai_displacement_field(const float* phi, const int* dims, float* disp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ITK-semantics warps  (reference: oai_analysis/dask_processing.py:95-111 deform_probmap_delayed,
+ * test/test_all.py:42-52; transform = R_A o DisplacementFieldTransform o R_B^-1 built by create_itk_transform)
+ * Affines are row-major 3x4 [M | t] in float64 acting on (x,y,z).
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* itk.resample_image_filter(src, transform, LinearInterpolateImageFunction, output grid, default pixel):
+ * out[c][j] = trilinear(src[c], net_to_src_index( q + D(q) )), q = out_index_to_net(j); D = identity outside the
+ * field buffer; neighbours clamped to the edge; default_value outside [-0.5, N-0.5). */
+OAI_API int oai_warp_volume(const float* src, int C, const int* src_dims, const float* disp, const int* field_dims,
+                            const double* out_index_to_net, const double* net_to_src_index, float* out,
+                            const int* out_dims, float default_value, void* stream);
+
+/* itk CompositeTransform::TransformPoint on n physical points (float64 x,y,z): out = net_to_phys(q + D(q)),
+ * q = phys_to_net(p).  (Mesh-vertex warp, reference README.md:34 / SURVEY 3.4.) */
+OAI_API int oai_warp_points(const double* pts, long long n, const float* disp, const int* field_dims,
+                            const double* phys_to_net, const double* net_to_phys, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

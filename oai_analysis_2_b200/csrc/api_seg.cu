@@ -10,9 +10,7 @@ extern "C" int oai_seg_stem(const float* vol, const int* vol_dims, const int* ge
                             const float* w27c, const float* bias, int c0, void* out, int ab_format, void* stream) {
   OAI_REQUIRE(vol && vol_dims && geom && w27c && bias && out, "seg_stem: null pointer");
   OAI_REQUIRE(c0 % 8 == 0 && c0 > 0 && c0 <= 64, "seg_stem: c0=%d must be a multiple of 8 in (0,64]", c0);
-  for (int a = 0; a < 3; ++a)
-    OAI_REQUIRE(geom[6 + a] < vol_dims[a] && geom[0 + a] - geom[6 + a] <= 2 * vol_dims[a] - 2,
-                "seg_stem: reflect padding wider than the volume on axis %d", a);
+  for (int a = 0; a < 3; ++a) OAI_REQUIRE(vol_dims[a] >= 1 && geom[a] >= 1, "seg_stem: empty axis %d", a);
   StemParams p;
   p.vol = vol; p.VD = vol_dims[0]; p.VH = vol_dims[1]; p.VW = vol_dims[2];
   p.td = geom[0]; p.th = geom[1]; p.tw = geom[2];

@@ -1,0 +1,497 @@
+// Registration-stage kernels (fp32 / fp64, CUDA cores -- these ops are bandwidth- or latency-bound, no tensor cores):
+//   * conv3 / convt4      : the layers of icon_registration's tallUNet2 (networks.UNet2.forward) with its residual
+//                           avg-pool / trilinear-upsample shortcuts, BatchNorm(eval), leaky-ReLU and crops fused in
+//   * chain               : composition of displacement maps  c <- c + S(u_k, c)  and the final image warp
+//                           (network_wrappers.TwoStepRegistration closures + mermaidlite.compute_warped_image_multiNC
+//                            == F.grid_sample(bilinear, border, align_corners=True))
+//   * resize / avgpool    : register_pair's F.interpolate(trilinear, align_corners=False) and
+//                           DownsampleRegistration's avg_pool3d(2, ceil_mode=True)
+//   * disp_field          : itk_wrapper.create_itk_transform's (phi - id) * (N - 1), components reversed to x,y,z
+//   * warp_volume/points  : itk.resample_image_filter / TransformPoint through R_A o DisplacementField o R_B^-1
+//                           (oai_analysis/dask_processing.py:100-109), float64 coordinate arithmetic
+#include "api_common.h"
+#include "reg_kernels.cuh"
+
+namespace oai {
+
+namespace {
+
+__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.01f * v; }
+
+// ------------------------------------------------------------------------------------------------ conv k3
+template <int CO_T>
+__global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
+  constexpr int CI_CHUNK = 8;
+  __shared__ __align__(16) float s_w[CI_CHUNK * 27 * CO_T];
+  const int co0 = blockIdx.y * CO_T;
+  const int n = blockIdx.z;
+  const long long nvox = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const bool active = v < nvox;
+  int xo = 0, yo = 0, zo = 0;
+  if (active) {
+    xo = static_cast<int>(v % p.Wo);
+    yo = static_cast<int>((v / p.Wo) % p.Ho);
+    zo = static_cast<int>(v / (static_cast<long long>(p.Wo) * p.Ho));
+  }
+  const int xi0 = xo * p.stride - 1, yi0 = yo * p.stride - 1, zi0 = zo * p.stride - 1;
+  // per-tap offsets / validity (zero padding)
+  int off[27];
+  unsigned valid = 0;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int z = zi0 + kd, y = yi0 + kh, x = xi0 + kw;
+        const int k = (kd * 3 + kh) * 3 + kw;
+        const bool ok = active && z >= 0 && z < p.Di && y >= 0 && y < p.Hi && x >= 0 && x < p.Wi;
+        off[k] = ok ? (z * p.Hi + y) * p.Wi + x : 0;
+        valid |= (ok ? 1u : 0u) << k;
+      }
+  float acc[CO_T];
+#pragma unroll
+  for (int j = 0; j < CO_T; ++j) acc[j] = 0.f;
+  const float* in_n = p.in + n * p.in_nstride;
+  for (int ci0 = 0; ci0 < p.cin; ci0 += CI_CHUNK) {
+    const int nci = min(CI_CHUNK, p.cin - ci0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nci * 27 * CO_T; i += blockDim.x) {
+      const int j = i % CO_T, k = (i / CO_T) % 27, c = i / (CO_T * 27);
+      const int co = co0 + j;
+      s_w[i] = co < p.cout_pad ? p.w[(static_cast<size_t>(ci0 + c) * 27 + k) * p.cout_pad + co] : 0.f;
+    }
+    __syncthreads();
+    for (int c = 0; c < nci; ++c) {
+      const float* plane = in_n + (ci0 + c) * p.in_cstride;
+      const float* wc = s_w + c * 27 * CO_T;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        float x = ((valid >> k) & 1u) ? __ldg(plane + off[k]) : 0.f;
+        if (p.leaky_in) x = leaky(x);
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(x, wc[k * CO_T + j], acc[j]);
+      }
+    }
+  }
+  if (!active) return;
+  float* out_n = p.out + n * p.out_nstride;
+  const long long ovox = (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + xo;
+#pragma unroll
+  for (int j = 0; j < CO_T; ++j) {
+    const int co = co0 + j;
+    if (co >= p.cout) break;
+    float r = acc[j] + p.bias[co];
+    if (p.residual) {
+      const int cs = co - (p.cout - p.cin);  // zero padding sits in front of the pooled channels
+      if (cs >= 0) {
+        const float* plane = in_n + cs * p.in_cstride;
+        float s = 0.f;
+        int cnt = 0;
+        for (int dz = 0; dz < 2; ++dz)
+          for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+              const int z = 2 * zo + dz, y = 2 * yo + dy, x = 2 * xo + dx;
+              if (z < p.Di && y < p.Hi && x < p.Wi) {
+                s += plane[(static_cast<size_t>(z) * p.Hi + y) * p.Wi + x];
+                ++cnt;
+              }
+            }
+        r += s / static_cast<float>(cnt);
+      }
+    }
+    out_n[co * p.out_cstride + ovox] = r * p.out_scale;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ convT k4 s2 p1
+// Each thread produces the two x-adjacent outputs (2j, 2j+1) of one (zo, yo) row position for CO_T channels.
+template <int CO_T>
+__global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
+  constexpr int CI_CHUNK = 4;
+  __shared__ __align__(16) float s_w[CI_CHUNK * 64 * CO_T];
+  const int co0 = blockIdx.y * CO_T;
+  const int n = blockIdx.z;
+  const int Wp = (p.Wo + 1) / 2;
+  const long long nthr = static_cast<long long>(p.Do) * p.Ho * Wp;
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const bool active = v < nthr;
+  int j = 0, yo = 0, zo = 0;
+  if (active) {
+    j = static_cast<int>(v % Wp);
+    yo = static_cast<int>((v / Wp) % p.Ho);
+    zo = static_cast<int>(v / (static_cast<long long>(Wp) * p.Ho));
+  }
+  // o = 2 i - 1 + k  =>  k = (o+1)%2 + 2 t, i = (o + 1 - k)/2, t in {0,1}
+  int kz[2], iz[2], ky[2], iy[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    kz[t] = ((zo + 1) & 1) + 2 * t;
+    iz[t] = (zo + 1 - kz[t]) / 2;
+    ky[t] = ((yo + 1) & 1) + 2 * t;
+    iy[t] = (yo + 1 - ky[t]) / 2;
+  }
+  // x inputs j-1, j, j+1 ; output 2j uses (kx=1,ix=j),(kx=3,ix=j-1) ; output 2j+1 uses (kx=0,ix=j+1),(kx=2,ix=j)
+  float acc0[CO_T], acc1[CO_T];
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c) acc0[c] = acc1[c] = 0.f;
+  const float* in_n = p.in + n * p.in_nstride;
+  for (int ci0 = 0; ci0 < p.cin; ci0 += CI_CHUNK) {
+    const int nci = min(CI_CHUNK, p.cin - ci0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nci * 64 * CO_T; i += blockDim.x) {
+      const int c = i % CO_T, k = (i / CO_T) % 64, ci = i / (CO_T * 64);
+      const int co = co0 + c;
+      s_w[i] = co < p.cout ? p.w[(static_cast<size_t>(ci0 + ci) * 64 + k) * p.cout + co] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int ci = 0; ci < nci; ++ci) {
+      const float* plane = in_n + (ci0 + ci) * p.in_cstride;
+      const float* wc = s_w + ci * 64 * CO_T;
+#pragma unroll
+      for (int tz = 0; tz < 2; ++tz) {
+        const int z = iz[tz];
+        if (z < 0 || z >= p.Di) continue;
+#pragma unroll
+        for (int ty = 0; ty < 2; ++ty) {
+          const int y = iy[ty];
+          if (y < 0 || y >= p.Hi) continue;
+          const float* row = plane + (static_cast<size_t>(z) * p.Hi + y) * p.Wi;
+          const float xm = (j - 1 >= 0 && j - 1 < p.Wi) ? leaky(__ldg(row + j - 1)) : 0.f;
+          const float xc = (j < p.Wi) ? leaky(__ldg(row + j)) : 0.f;
+          const float xp = (j + 1 < p.Wi) ? leaky(__ldg(row + j + 1)) : 0.f;
+          const float* wk = wc + ((kz[tz] * 4 + ky[ty]) * 4) * CO_T;
+#pragma unroll
+          for (int c = 0; c < CO_T; ++c) {
+            acc0[c] = fmaf(xc, wk[1 * CO_T + c], acc0[c]);
+            acc0[c] = fmaf(xm, wk[3 * CO_T + c], acc0[c]);
+            acc1[c] = fmaf(xp, wk[0 * CO_T + c], acc1[c]);
+            acc1[c] = fmaf(xc, wk[2 * CO_T + c], acc1[c]);
+          }
+        }
+      }
+    }
+  }
+  if (!active) return;
+  // residual: F.interpolate(in[:, :cout], scale_factor=2, trilinear, align_corners=False) on the RAW input
+  int z0, z1, y0, y1;
+  float lz, ly;
+  {
+    float s = fmaxf(0.5f * (zo + 0.5f) - 0.5f, 0.f);
+    z0 = static_cast<int>(s); z1 = z0 + (z0 < p.Di - 1 ? 1 : 0); lz = s - z0;
+    s = fmaxf(0.5f * (yo + 0.5f) - 0.5f, 0.f);
+    y0 = static_cast<int>(s); y1 = y0 + (y0 < p.Hi - 1 ? 1 : 0); ly = s - y0;
+  }
+  float* out_n = p.out + n * p.out_nstride;
+#pragma unroll
+  for (int xx = 0; xx < 2; ++xx) {
+    const int xo = 2 * j + xx;
+    if (xo >= p.Wo) break;
+    const float s = fmaxf(0.5f * (xo + 0.5f) - 0.5f, 0.f);
+    const int x0 = static_cast<int>(s), x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
+    const float lx = s - x0;
+    const long long ovox = (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + xo;
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) {
+      const int co = co0 + c;
+      if (co >= p.cout) break;
+      const float* pl = in_n + co * p.in_cstride;
+      auto at = [&](int z, int y, int x) { return pl[(static_cast<size_t>(z) * p.Hi + y) * p.Wi + x]; };
+      const float r = (1.f - lz) * ((1.f - ly) * ((1.f - lx) * at(z0, y0, x0) + lx * at(z0, y0, x1)) +
+                                    ly * ((1.f - lx) * at(z0, y1, x0) + lx * at(z0, y1, x1))) +
+                      lz * ((1.f - ly) * ((1.f - lx) * at(z1, y0, x0) + lx * at(z1, y0, x1)) +
+                            ly * ((1.f - lx) * at(z1, y1, x0) + lx * at(z1, y1, x1)));
+      const float a = (xx == 0 ? acc0[c] : acc1[c]) + p.bias[co] + r;
+      out_n[co * p.out_cstride + ovox] = a * p.bn_scale[co] + p.bn_shift[co];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ sampling helpers
+// F.grid_sample(bilinear, border, align_corners=True) at normalised coordinate g = 2c-1 along each axis.
+struct Tri {
+  int i0[3], i1[3];
+  float t[3];
+};
+__device__ __forceinline__ Tri tri_setup(float cz, float cy, float cx, int D, int H, int W) {
+  Tri r;
+  const float c[3] = {cz, cy, cx};
+  const int n[3] = {D, H, W};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float g = c[a] * 2.f - 1.f;
+    float pix = ((g + 1.f) / 2.f) * static_cast<float>(n[a] - 1);
+    pix = fminf(fmaxf(pix, 0.f), static_cast<float>(n[a] - 1));
+    const float f = floorf(pix);
+    r.i0[a] = static_cast<int>(f);
+    r.i1[a] = min(r.i0[a] + 1, n[a] - 1);
+    r.t[a] = pix - f;
+  }
+  return r;
+}
+__device__ __forceinline__ float tri_sample(const float* __restrict__ v, const Tri& q, int H, int W) {
+  const size_t z0 = static_cast<size_t>(q.i0[0]) * H, z1 = static_cast<size_t>(q.i1[0]) * H;
+  const float v000 = __ldg(v + (z0 + q.i0[1]) * W + q.i0[2]), v001 = __ldg(v + (z0 + q.i0[1]) * W + q.i1[2]);
+  const float v010 = __ldg(v + (z0 + q.i1[1]) * W + q.i0[2]), v011 = __ldg(v + (z0 + q.i1[1]) * W + q.i1[2]);
+  const float v100 = __ldg(v + (z1 + q.i0[1]) * W + q.i0[2]), v101 = __ldg(v + (z1 + q.i0[1]) * W + q.i1[2]);
+  const float v110 = __ldg(v + (z1 + q.i1[1]) * W + q.i0[2]), v111 = __ldg(v + (z1 + q.i1[1]) * W + q.i1[2]);
+  const float tz = q.t[0], ty = q.t[1], tx = q.t[2];
+  return (1.f - tz) * ((1.f - ty) * ((1.f - tx) * v000 + tx * v001) + ty * ((1.f - tx) * v010 + tx * v011)) +
+         tz * ((1.f - ty) * ((1.f - tx) * v100 + tx * v101) + ty * ((1.f - tx) * v110 + tx * v111));
+}
+
+__global__ void __launch_bounds__(256) chain_kernel(const ChainParams p) {
+  const long long nvox = static_cast<long long>(p.D) * p.H * p.W;
+  const double sz = 1.0 / (p.D - 1), sy = 1.0 / (p.H - 1), sx = 1.0 / (p.W - 1);
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvox;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(v % p.W), y = static_cast<int>((v / p.W) % p.H),
+              z = static_cast<int>(v / (static_cast<long long>(p.W) * p.H));
+    float cz = static_cast<float>(z * sz), cy = static_cast<float>(y * sy), cx = static_cast<float>(x * sx);
+    for (int f = 0; f < p.nfields; ++f) {
+      const float* u = p.u[f];
+      const size_t plane = static_cast<size_t>(p.ud[f]) * p.uh[f] * p.uw[f];
+      float dz, dy, dx;
+      if (f == 0 && p.shortcut_first) {
+        dz = __ldg(u + v); dy = __ldg(u + plane + v); dx = __ldg(u + 2 * plane + v);
+      } else {
+        const Tri q = tri_setup(cz, cy, cx, p.ud[f], p.uh[f], p.uw[f]);
+        dz = tri_sample(u, q, p.uh[f], p.uw[f]);
+        dy = tri_sample(u + plane, q, p.uh[f], p.uw[f]);
+        dx = tri_sample(u + 2 * plane, q, p.uh[f], p.uw[f]);
+      }
+      cz += dz; cy += dy; cx += dx;
+    }
+    if (p.phi_out) {
+      p.phi_out[v] = cz; p.phi_out[nvox + v] = cy; p.phi_out[2 * nvox + v] = cx;
+    }
+    if (p.img_out) {
+      const Tri q = tri_setup(cz, cy, cx, p.id, p.ih, p.iw);
+      p.img_out[v] = tri_sample(p.img, q, p.ih, p.iw);
+    }
+  }
+}
+
+// F.interpolate(mode="trilinear", align_corners=False, size=(Do,Ho,Wo)) of a single-channel volume
+__global__ void __launch_bounds__(256) resize_trilinear_kernel(const float* __restrict__ in, int Di, int Hi, int Wi,
+                                                               float* __restrict__ out, int Do, int Ho, int Wo) {
+  const long long nvox = static_cast<long long>(Do) * Ho * Wo;
+  const float rz = static_cast<float>(Di) / Do, ry = static_cast<float>(Hi) / Ho, rx = static_cast<float>(Wi) / Wo;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvox;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(v % Wo), y = static_cast<int>((v / Wo) % Ho),
+              z = static_cast<int>(v / (static_cast<long long>(Wo) * Ho));
+    const float fz = fmaxf(rz * (z + 0.5f) - 0.5f, 0.f), fy = fmaxf(ry * (y + 0.5f) - 0.5f, 0.f),
+                fx = fmaxf(rx * (x + 0.5f) - 0.5f, 0.f);
+    const int z0 = min(static_cast<int>(fz), Di - 1), y0 = min(static_cast<int>(fy), Hi - 1),
+              x0 = min(static_cast<int>(fx), Wi - 1);
+    const int z1 = z0 + (z0 < Di - 1), y1 = y0 + (y0 < Hi - 1), x1 = x0 + (x0 < Wi - 1);
+    const float lz = fz - z0, ly = fy - y0, lx = fx - x0;
+    auto at = [&](int zz, int yy, int xx) { return __ldg(in + (static_cast<size_t>(zz) * Hi + yy) * Wi + xx); };
+    out[v] = (1.f - lz) * ((1.f - ly) * ((1.f - lx) * at(z0, y0, x0) + lx * at(z0, y0, x1)) +
+                           ly * ((1.f - lx) * at(z0, y1, x0) + lx * at(z0, y1, x1))) +
+             lz * ((1.f - ly) * ((1.f - lx) * at(z1, y0, x0) + lx * at(z1, y0, x1)) +
+                   ly * ((1.f - lx) * at(z1, y1, x0) + lx * at(z1, y1, x1)));
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool2_ceil_kernel(const float* __restrict__ in, int C, int Di, int Hi,
+                                                            int Wi, float* __restrict__ out) {
+  const int Do = (Di + 1) / 2, Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
+  const long long n = static_cast<long long>(C) * Do * Ho * Wo;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = v;
+    const int x = r % Wo; r /= Wo;
+    const int y = r % Ho; r /= Ho;
+    const int z = r % Do; r /= Do;
+    const float* pl = in + r * (static_cast<size_t>(Di) * Hi * Wi);
+    float s = 0.f;
+    int cnt = 0;
+    for (int dz = 0; dz < 2; ++dz)
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          const int zz = 2 * z + dz, yy = 2 * y + dy, xx = 2 * x + dx;
+          if (zz < Di && yy < Hi && xx < Wi) {
+            s += __ldg(pl + (static_cast<size_t>(zz) * Hi + yy) * Wi + xx);
+            ++cnt;
+          }
+        }
+    out[v] = s / static_cast<float>(cnt);
+  }
+}
+
+// disp[z][y][x][(x,y,z)] = (phi - identity)[(2,1,0)] * (N - 1)
+__global__ void __launch_bounds__(256) disp_field_kernel(const float* __restrict__ phi, int D, int H, int W,
+                                                         float* __restrict__ disp) {
+  const long long nvox = static_cast<long long>(D) * H * W;
+  const double sz = 1.0 / (D - 1), sy = 1.0 / (H - 1), sx = 1.0 / (W - 1);
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvox;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(v % W), y = static_cast<int>((v / W) % H),
+              z = static_cast<int>(v / (static_cast<long long>(W) * H));
+    const float iz = static_cast<float>(z * sz), iy = static_cast<float>(y * sy), ix = static_cast<float>(x * sx);
+    disp[3 * v + 0] = (phi[2 * nvox + v] - ix) * static_cast<float>(W - 1);
+    disp[3 * v + 1] = (phi[nvox + v] - iy) * static_cast<float>(H - 1);
+    disp[3 * v + 2] = (phi[v] - iz) * static_cast<float>(D - 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ ITK-style warps
+__device__ __forceinline__ void affine_apply(const Affine3& a, const double in[3], double out[3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) out[r] = a.m[3 * r] * in[0] + a.m[3 * r + 1] * in[1] + a.m[3 * r + 2] * in[2] + a.t[r];
+}
+
+// q (x,y,z lattice coordinate) += trilinear(disp, q) when q is inside the field buffer [-0.5, n-0.5)
+__device__ __forceinline__ void displace(const float* __restrict__ disp, int FD, int FH, int FW, double q[3]) {
+  const int n[3] = {FW, FH, FD};
+  bool inside = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) inside = inside && q[a] >= -0.5 && q[a] < n[a] - 0.5;
+  if (!inside) return;
+  int i0[3], i1[3];
+  double t[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double f = floor(q[a]);
+    t[a] = q[a] - f;
+    const int b = static_cast<int>(f);
+    i0[a] = min(max(b, 0), n[a] - 1);
+    i1[a] = min(max(b + 1, 0), n[a] - 1);
+  }
+  double d[3] = {0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ix = (c & 1) ? i1[0] : i0[0], iy = (c & 2) ? i1[1] : i0[1], iz = (c & 4) ? i1[2] : i0[2];
+    const double w = ((c & 1) ? t[0] : 1.0 - t[0]) * ((c & 2) ? t[1] : 1.0 - t[1]) * ((c & 4) ? t[2] : 1.0 - t[2]);
+    const float* e = disp + ((static_cast<size_t>(iz) * FH + iy) * FW + ix) * 3;
+    d[0] += w * __ldg(e); d[1] += w * __ldg(e + 1); d[2] += w * __ldg(e + 2);
+  }
+  q[0] += d[0]; q[1] += d[1]; q[2] += d[2];
+}
+
+__global__ void __launch_bounds__(256) warp_volume_kernel(const WarpVolumeParams p) {
+  const long long nvox = static_cast<long long>(p.OD) * p.OH * p.OW;
+  const size_t splane = static_cast<size_t>(p.SD) * p.SH * p.SW;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvox;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double j[3] = {static_cast<double>(v % p.OW), static_cast<double>((v / p.OW) % p.OH),
+                         static_cast<double>(v / (static_cast<long long>(p.OW) * p.OH))};
+    double q[3], s[3];
+    affine_apply(p.out_index_to_net, j, q);
+    displace(p.disp, p.FD, p.FH, p.FW, q);
+    affine_apply(p.net_to_src_index, q, s);
+    const int n[3] = {p.SW, p.SH, p.SD};
+    bool inside = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) inside = inside && s[a] >= -0.5 && s[a] < n[a] - 0.5;
+    if (!inside) {
+      for (int c = 0; c < p.C; ++c) p.out[c * nvox + v] = p.default_value;
+      continue;
+    }
+    int i0[3], i1[3];
+    double t[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double f = floor(s[a]);
+      t[a] = s[a] - f;
+      const int b = static_cast<int>(f);
+      i0[a] = min(max(b, 0), n[a] - 1);
+      i1[a] = min(max(b + 1, 0), n[a] - 1);
+    }
+    for (int c = 0; c < p.C; ++c) {
+      const float* src = p.src + c * splane;
+      double acc = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int ix = (k & 1) ? i1[0] : i0[0], iy = (k & 2) ? i1[1] : i0[1], iz = (k & 4) ? i1[2] : i0[2];
+        const double w = ((k & 1) ? t[0] : 1.0 - t[0]) * ((k & 2) ? t[1] : 1.0 - t[1]) * ((k & 4) ? t[2] : 1.0 - t[2]);
+        acc += w * __ldg(src + (static_cast<size_t>(iz) * p.SH + iy) * p.SW + ix);
+      }
+      p.out[c * nvox + v] = static_cast<float>(acc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) warp_points_kernel(const WarpPointsParams p) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < p.n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double pt[3] = {p.pts[3 * i], p.pts[3 * i + 1], p.pts[3 * i + 2]};
+    double q[3], o[3];
+    affine_apply(p.phys_to_net, pt, q);
+    displace(p.disp, p.FD, p.FH, p.FW, q);
+    affine_apply(p.net_to_phys, q, o);
+    p.out[3 * i] = o[0]; p.out[3 * i + 1] = o[1]; p.out[3 * i + 2] = o[2];
+  }
+}
+
+inline unsigned grid_for(long long n, int block, int per_sm) {
+  long long b = (n + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms()) * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b);
+}
+
+}  // namespace
+
+int conv3_launch(const Conv3Params& p, cudaStream_t st) {
+  const long long nvox = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+  const unsigned gx = static_cast<unsigned>((nvox + 127) / 128);
+  if (p.cout <= 4) {
+    dim3 g(gx, (p.cout + 3) / 4, p.N);
+    conv3_kernel<4><<<g, 128, 0, st>>>(p);
+  } else {
+    dim3 g(gx, (p.cout + 15) / 16, p.N);
+    conv3_kernel<16><<<g, 128, 0, st>>>(p);
+  }
+  return launched("conv3_kernel");
+}
+
+int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
+  const long long nthr = static_cast<long long>(p.Do) * p.Ho * ((p.Wo + 1) / 2);
+  dim3 g(static_cast<unsigned>((nthr + 127) / 128), (p.cout + 15) / 16, p.N);
+  convt4_kernel<16><<<g, 128, 0, st>>>(p);
+  return launched("convt4_kernel");
+}
+
+int chain_launch(const ChainParams& p, cudaStream_t st) {
+  const long long n = static_cast<long long>(p.D) * p.H * p.W;
+  chain_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(p);
+  return launched("chain_kernel");
+}
+
+int resize_trilinear_launch(const float* in, int Di, int Hi, int Wi, float* out, int Do, int Ho, int Wo,
+                            cudaStream_t st) {
+  const long long n = static_cast<long long>(Do) * Ho * Wo;
+  resize_trilinear_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(in, Di, Hi, Wi, out, Do, Ho, Wo);
+  return launched("resize_trilinear_kernel");
+}
+
+int avgpool2_ceil_launch(const float* in, int C, int Di, int Hi, int Wi, float* out, cudaStream_t st) {
+  const long long n = static_cast<long long>(C) * ((Di + 1) / 2) * ((Hi + 1) / 2) * ((Wi + 1) / 2);
+  avgpool2_ceil_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(in, C, Di, Hi, Wi, out);
+  return launched("avgpool2_ceil_kernel");
+}
+
+int disp_field_launch(const float* phi, int D, int H, int W, float* disp, cudaStream_t st) {
+  const long long n = static_cast<long long>(D) * H * W;
+  disp_field_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(phi, D, H, W, disp);
+  return launched("disp_field_kernel");
+}
+
+int warp_volume_launch(const WarpVolumeParams& p, cudaStream_t st) {
+  const long long n = static_cast<long long>(p.OD) * p.OH * p.OW;
+  warp_volume_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(p);
+  return launched("warp_volume_kernel");
+}
+
+int warp_points_launch(const WarpPointsParams& p, cudaStream_t st) {
+  warp_points_kernel<<<grid_for(p.n, 128, 8), 128, 0, st>>>(p);
+  return launched("warp_points_kernel");
+}
+
+}  // namespace oai

@@ -1,0 +1,86 @@
+// Parameter blocks of the registration-stage kernels (reg_kernels.cu) shared with their C-ABI wrappers.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace oai {
+
+// Direct fp32 convolution, kernel 3, pad 1, stride 1 or 2, planar NCDHW tensors with explicit channel strides so a
+// layer can read / write a channel slice of a concatenation buffer in place.
+struct Conv3Params {
+  const float* in;   // [N][cin] planes of Di*Hi*Wi
+  long long in_nstride, in_cstride;
+  int cin, Di, Hi, Wi;
+  const float* w;    // packed [cin][27][cout_pad]
+  const float* bias; // [cout]
+  float* out;        // [N][cout] planes of Do*Ho*Wo
+  long long out_nstride, out_cstride;
+  int cout, cout_pad, Do, Ho, Wo;
+  int N, stride;
+  int leaky_in;      // apply leaky_relu(0.01) to the input on load
+  int residual;      // 1: add pad_or_crop(avg_pool3d(in, 2, ceil_mode=True)) (zero-padded IN FRONT to cout channels)
+  float out_scale;   // multiplies (acc + bias [+ residual])
+};
+
+// Direct fp32 transposed convolution, kernel 4, stride 2, pad 1 (output = 2x input), fused with the icon UNet2 up-path:
+//   out = BN( convT(leaky_relu(in)) + bias + upsample2x_trilinear(in[:, :cout]) ), cropped to (Do,Ho,Wo).
+struct ConvT4Params {
+  const float* in;   // [N][cin] planes of Di*Hi*Wi
+  long long in_nstride, in_cstride;
+  int cin, Di, Hi, Wi;
+  const float* w;    // packed [cin][64][cout]
+  const float* bias, *bn_scale, *bn_shift;  // [cout]
+  float* out;
+  long long out_nstride, out_cstride;
+  int cout, Do, Ho, Wo;  // Do <= 2*Di etc. (crop)
+  int N;
+};
+
+struct ChainParams {
+  int D, H, W;             // grid of the coordinate map being built
+  int nfields;
+  const float* u[4];       // displacement tensors [3][ud][uh][uw] (components z,y,x in [0,1] units), applied in order
+  int ud[4], uh[4], uw[4];
+  int shortcut_first;      // first field has the grid's shape and is added without interpolation
+  const float* img;        // optional image [id][ih][iw] sampled at the final coordinates
+  int id, ih, iw;
+  float* phi_out;          // optional [3][D][H][W]
+  float* img_out;          // optional [D][H][W]
+};
+
+struct Affine3 {
+  double m[9];
+  double t[3];
+};
+
+struct WarpVolumeParams {
+  const float* src;  // [C][SD][SH][SW] image being resampled (prob maps, on image A's grid)
+  int C, SD, SH, SW;
+  const float* disp; // [FD][FH][FW][3] displacement (x,y,z components, network-voxel units)
+  int FD, FH, FW;
+  Affine3 out_index_to_net;   // output index (x,y,z) -> network lattice coordinate (x,y,z)
+  Affine3 net_to_src_index;   // displaced lattice coordinate -> continuous index (x,y,z) of src
+  float* out;        // [C][OD][OH][OW]
+  int OD, OH, OW;
+  float default_value;
+};
+
+struct WarpPointsParams {
+  const double* pts;  // [n][3] physical x,y,z
+  double* out;        // [n][3]
+  long long n;
+  const float* disp;
+  int FD, FH, FW;
+  Affine3 phys_to_net, net_to_phys;
+};
+
+int conv3_launch(const Conv3Params& p, cudaStream_t st);
+int convt4_launch(const ConvT4Params& p, cudaStream_t st);
+int chain_launch(const ChainParams& p, cudaStream_t st);
+int resize_trilinear_launch(const float* in, int Di, int Hi, int Wi, float* out, int Do, int Ho, int Wo,
+                            cudaStream_t st);
+int avgpool2_ceil_launch(const float* in, int C, int Di, int Hi, int Wi, float* out, cudaStream_t st);
+int disp_field_launch(const float* phi, int D, int H, int W, float* disp, cudaStream_t st);
+int warp_volume_launch(const WarpVolumeParams& p, cudaStream_t st);
+int warp_points_launch(const WarpPointsParams& p, cudaStream_t st);
+
+}  // namespace oai

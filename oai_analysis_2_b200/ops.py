@@ -4,7 +4,7 @@ import ctypes
 import numpy as np
 import torch
 
-from ._lib import c_int, c_ll, c_size, check, lib, ptr, stream_ptr
+from ._lib import c_float, c_int, c_ll, c_size, check, lib, ptr, stream_ptr
 
 FLAG_FORCE_PER_TAP = 1
 FLAG_BASE_OFF_FORMULA = 2
@@ -86,4 +86,100 @@ def seg_head(act, w, b, out, geom, tile0, crop_zyx, out_mode=0, ab_format=0):
     crop = np.asarray(crop_zyx, dtype=np.int32)
     check(lib.oai_seg_head(ptr(act), C, ncls, ptr(w), ptr(b), ptr(out), ptr(dims), ptr(geom), tile0, ntiles,
                            ptr(crop), out_mode, ab_format, stream_ptr()), "seg_head")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ registration
+def _dims(*v):
+    return np.asarray(v, dtype=np.int32)
+
+
+def reg_conv3(x, cin, w, bias, out, cout, stride, leaky_in, residual, out_scale=1.0):
+    """x / out: views [N, C, D, H, W] float32 whose channel slice may be part of a larger buffer."""
+    N, _, D, H, W = x.shape
+    check(lib.oai_reg_conv3(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(_dims(D, H, W)), ptr(w), ptr(bias),
+                            ptr(out), c_ll(out.stride(0)), c_ll(out.stride(1)), cout, w.shape[-1], N, stride,
+                            int(leaky_in), int(residual), c_float(out_scale), stream_ptr()), "reg_conv3")
+    return out
+
+
+def reg_convt4(x, cin, w, bias, bn_scale, bn_shift, out, cout):
+    N, _, D, H, W = x.shape
+    od = _dims(*out.shape[2:])
+    check(lib.oai_reg_convt4(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(_dims(D, H, W)), ptr(w),
+                             ptr(bias), ptr(bn_scale), ptr(bn_shift), ptr(out), c_ll(out.stride(0)),
+                             c_ll(out.stride(1)), cout, ptr(od), N, stream_ptr()), "reg_convt4")
+    return out
+
+
+def compose(grid_dims, fields, shortcut_first=False, img=None, want_phi=True, phi_out=None, img_out=None):
+    """fields: list of [3,d,h,w] float32 tensors applied in order.  Returns (phi [3,D,H,W] | None, warped | None)."""
+    dev = fields[0].device if fields else img.device
+    D, H, W = (int(v) for v in grid_dims)
+    arr = (ctypes.c_void_p * 4)(*[f.data_ptr() for f in fields] + [0] * (4 - len(fields)))
+    fd = np.asarray([s for f in fields for s in f.shape[1:]] + [0] * (12 - 3 * len(fields)), dtype=np.int32)
+    for f in fields:
+        assert f.is_contiguous() and f.dtype == torch.float32
+    if want_phi and phi_out is None:
+        phi_out = torch.empty((3, D, H, W), dtype=torch.float32, device=dev)
+    if img is not None and img_out is None:
+        img_out = torch.empty((D, H, W), dtype=torch.float32, device=dev)
+    if img is not None:
+        assert img.is_contiguous() and img_out.is_contiguous()
+    idims = _dims(*img.shape[-3:]) if img is not None else None
+    check(lib.oai_compose(ptr(_dims(D, H, W)), len(fields), arr, ptr(fd), int(shortcut_first), ptr(img), ptr(idims),
+                          ptr(phi_out if want_phi else None), ptr(img_out if img is not None else None),
+                          stream_ptr()), "compose")
+    return (phi_out if want_phi else None), (img_out if img is not None else None)
+
+
+def resize_trilinear(x, out_dims, out=None):
+    if out is None:
+        out = torch.empty(tuple(int(v) for v in out_dims), dtype=torch.float32, device=x.device)
+    assert x.is_contiguous() and out.is_contiguous()
+    check(lib.oai_resize_trilinear(ptr(x), ptr(_dims(*x.shape[-3:])), ptr(out), ptr(_dims(*out.shape[-3:])),
+                                   stream_ptr()), "resize_trilinear")
+    return out
+
+
+def avgpool2_ceil(x):
+    """x: [C, D, H, W] float32 contiguous."""
+    C, D, H, W = x.shape
+    out = torch.empty((C, (D + 1) // 2, (H + 1) // 2, (W + 1) // 2), dtype=torch.float32, device=x.device)
+    check(lib.oai_avgpool3d_2_ceil(ptr(x), C, ptr(_dims(D, H, W)), ptr(out), stream_ptr()), "avgpool3d_2_ceil")
+    return out
+
+
+def displacement_field(phi):
+    _, D, H, W = phi.shape
+    out = torch.empty((D, H, W, 3), dtype=torch.float32, device=phi.device)
+    check(lib.oai_displacement_field(ptr(phi), ptr(_dims(D, H, W)), ptr(out), stream_ptr()), "displacement_field")
+    return out
+
+
+def _affine(M, t):
+    a = np.zeros((3, 4), dtype=np.float64)
+    a[:, :3] = M
+    a[:, 3] = t
+    return np.ascontiguousarray(a)
+
+
+def warp_volume(src, disp, out_index_to_net, net_to_src_index, out_dims, default_value=0.0):
+    """src: [C, SD, SH, SW] float32; disp: [FD, FH, FW, 3]; affines: (M, t) float64 on x,y,z.  Returns [C, *out_dims]."""
+    C = src.shape[0]
+    out = torch.empty((C,) + tuple(int(v) for v in out_dims), dtype=torch.float32, device=src.device)
+    a, b = _affine(*out_index_to_net), _affine(*net_to_src_index)
+    check(lib.oai_warp_volume(ptr(src), C, ptr(_dims(*src.shape[1:])), ptr(disp), ptr(_dims(*disp.shape[:3])), ptr(a),
+                              ptr(b), ptr(out), ptr(_dims(*out.shape[1:])), c_float(default_value), stream_ptr()),
+          "warp_volume")
+    return out
+
+
+def warp_points(pts, disp, phys_to_net, net_to_phys):
+    """pts: [n,3] float64 cuda tensor (x,y,z physical).  Returns [n,3] float64."""
+    assert pts.dtype == torch.float64 and pts.is_contiguous()
+    out = torch.empty_like(pts)
+    a, b = _affine(*phys_to_net), _affine(*net_to_phys)
+    check(lib.oai_warp_points(ptr(pts), c_ll(pts.shape[0]), ptr(disp), ptr(_dims(*disp.shape[:3])), ptr(a), ptr(b),
+                              ptr(out), stream_ptr()), "warp_points")
     return out

@@ -26,9 +26,8 @@ class Partition(object):
             raise ValueError("overlap_size must be smaller than half the patch size")
         self.tiles_grid_size = np.ceil(self.image_size / self.effective_size).astype(int)
         self.padded_size = self.effective_size * self.tiles_grid_size + self.overlap_size * 2 - self.image_size
-        lead, trail = self.overlap_size, self.padded_size - self.overlap_size
-        if np.any(lead >= self.image_size) or np.any(trail >= self.image_size):
-            raise ValueError("image too small for reflect padding with this patch/overlap (numpy.pad would fail too)")
+        if np.any((self.image_size < 2) & (self.padded_size > 0)):
+            raise ValueError("reflect padding needs at least 2 samples along a padded axis")
         return self
 
     @property

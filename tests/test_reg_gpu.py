@@ -1,0 +1,179 @@
+"""GPU tier: registration stage (tallUNet2 kernels, composition, resize) and ITK-semantics warps against the oracles.
+
+Oracles: oracle/reg_oracle.py (torch restatement of icon_registration==1.1.2, parity unpinned) and
+oracle/warp_oracle.py (float64 restatement of the ITK resample / TransformPoint semantics, parity unpinned).
+Tolerances: warped intensities within 1e-4 relative, warped points within 1e-3 mm (north-star)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _smooth(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    lo = torch.randn(1, 1, *[max(2, s // 8) for s in shape], generator=g)
+    return (F.interpolate(lo, size=shape, mode="trilinear", align_corners=True)[0, 0] * scale).contiguous()
+
+
+def test_resize_and_avgpool_match_torch():
+    _cuda()
+    from oai_analysis_2_b200 import ops
+    x = torch.rand(21, 50, 37)
+    for size in [(10, 25, 18), (13, 31, 40), (21, 50, 37), (42, 100, 74)]:
+        ref = F.interpolate(x[None, None], size=size, mode="trilinear", align_corners=False)[0, 0]
+        got = ops.resize_trilinear(x.cuda(), size).cpu()
+        assert (got - ref).abs().max() < 2e-6, size
+    y = torch.rand(3, 9, 12, 7)
+    ref = F.avg_pool3d(y[None], 2, ceil_mode=True)[0]
+    assert (ops.avgpool2_ceil(y.cuda()).cpu() - ref).abs().max() < 1e-6
+
+
+def test_unet2_layers_match_torch():
+    _cuda()
+    from oai_analysis_2_b200 import ops
+    from oracle.reg_oracle import pad_or_crop
+    g = torch.Generator().manual_seed(3)
+    # down step on odd sizes, inside a larger channel buffer
+    N, cin, cout, dims = 2, 16, 32, (9, 12, 11)
+    buf = torch.randn(N, cin + 5, *dims, generator=g)
+    x = buf[:, 5:]
+    w, b = torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.1, torch.randn(cout, generator=g) * 0.1
+    y = F.conv3d(F.leaky_relu(x), w, b, stride=2, padding=1)
+    ref = y + pad_or_crop(F.avg_pool3d(x, 2, ceil_mode=True), cout)
+    out_buf = torch.zeros(N, cout + 3, *ref.shape[2:]).cuda()
+    bufc = buf.cuda()
+    ops.reg_conv3(bufc[:, 5:], cin, w.permute(1, 2, 3, 4, 0).reshape(cin, 27, cout).contiguous().cuda(), b.cuda(),
+                  out_buf[:, 3:], cout, 2, True, True)
+    assert (out_buf[:, 3:].cpu() - ref).abs().max() < 2e-5
+    assert out_buf[:, :3].abs().max() == 0
+    # up step with crop
+    cin, cout, dims, crop = 48, 16, (5, 6, 6), (9, 12, 11)
+    x = torch.randn(N, cin, *dims, generator=g)
+    w, b = torch.randn(cin, cout, 4, 4, 4, generator=g) * 0.05, torch.randn(cout, generator=g) * 0.1
+    gam, bet = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    mean, var = torch.randn(cout, generator=g) * 0.1, torch.rand(cout, generator=g) + 0.5
+    y = F.conv_transpose3d(F.leaky_relu(x), w, b, stride=2, padding=1)
+    ref = y + F.interpolate(x[:, :cout], scale_factor=2, mode="trilinear", align_corners=False)
+    ref = F.batch_norm(ref, mean, var, gam, bet, training=False, eps=1e-5)[:, :, :crop[0], :crop[1], :crop[2]]
+    s = gam.double() / torch.sqrt(var.double() + 1e-5)
+    t = bet.double() - mean.double() * s
+    out = torch.zeros(N, cout, *crop).cuda()
+    ops.reg_convt4(x.cuda(), cin, w.permute(0, 2, 3, 4, 1).reshape(cin, 64, cout).contiguous().cuda(), b.cuda(),
+                   s.float().cuda(), t.float().cuda(), out, cout)
+    assert (out.cpu() - ref).abs().max() < 3e-5
+
+
+def test_tallunet2_matches_oracle():
+    _cuda()
+    from oai_analysis_2_b200.icon_registration.networks import TallUNet2
+    from oracle.reg_oracle import make_unet2_state_dict, unet2_forward
+    sd = make_unet2_state_dict(7)
+    net = TallUNet2()
+    net.load_state_dict(sd)
+    net.to("cuda")
+    dims = (40, 48, 44)
+    A = torch.stack([_smooth(dims, 1) + 0.5, _smooth(dims, 2) + 0.5])
+    B = torch.stack([_smooth(dims, 3) + 0.5, _smooth(dims, 4) + 0.5])
+    got = net(A.cuda(), B.cuda()).cpu()
+    with torch.no_grad():
+        ref = unet2_forward(sd, A[:, None], B[:, None])
+    scale = ref.abs().max().item()
+    assert scale > 1e-3
+    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, scale / 1e-2)
+
+
+def test_compose_matches_oracle_sampling():
+    _cuda()
+    from oai_analysis_2_b200 import ops
+    from oracle.reg_oracle import identity_map, sample
+    full, lo = (20, 24, 22), (10, 12, 11)
+    u = [torch.stack([_smooth(full, 10 + i, 0.05) for i in range(3)]) for _ in range(2)]
+    u += [torch.stack([_smooth(lo, 20 + i, 0.05) for i in range(3)]) for _ in range(2)]
+    img = _smooth(full, 30) + 1.0
+    c = identity_map(full) + u[0][None]
+    for f in u[1:]:
+        c = c + sample(f[None], c)
+    ref_img = sample(img[None, None], c)[0, 0]
+    phi, warped = ops.compose(full, [f.cuda() for f in u], True, img.cuda())
+    assert (phi.cpu() - c[0]).abs().max() < 2e-6
+    assert (warped.cpu() - ref_img).abs().max() < 1e-5
+    # general first step (no shortcut) on a coarser field, image at another resolution
+    c = identity_map(full)
+    c = c + sample(u[2][None], c)
+    img_lo = _smooth(lo, 31) + 1.0
+    ref_img = sample(img_lo[None, None], c)[0, 0]
+    phi, warped = ops.compose(full, [u[2].cuda()], False, img_lo.cuda())
+    assert (phi.cpu() - c[0]).abs().max() < 2e-6
+    assert (warped.cpu() - ref_img).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("shape,native", [((40, 48, 44), (80, 96, 88)), ((80, 192, 192), (80, 192, 192))])
+def test_register_pair_maps_match_oracle(shape, native):
+    _cuda()
+    from oai_analysis_2_b200.icon_registration import itk_wrapper, pretrained_models
+    from oracle import reg_oracle
+    sd = reg_oracle.make_gradicon_state_dict(4321)
+    model = pretrained_models.OAI_knees_gradICON_model(pretrained=False)
+    model.assign_identity_map([1, 1, *shape])
+    model.load_state_dict(sd, strict=True)
+    model.to("cuda")
+    A = (_smooth(native, 40) * 0.3 + 0.5).clamp(0, 1).numpy()
+    B = (_smooth(native, 41) * 0.3 + 0.5).clamp(0, 1).numpy()
+    phi_AB, phi_BA = itk_wrapper.register_pair_device(model, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
+    ref_AB, ref_BA = reg_oracle.register_pair_maps(sd, A, B, shape)
+    ident = reg_oracle.identity_map(shape)
+    vox = torch.tensor([s - 1 for s in shape], dtype=torch.float32).view(1, 3, 1, 1, 1)
+    disp_vox = ((ref_AB - ident) * vox).abs().max().item()
+    e_ab = ((phi_AB.cpu() - ref_AB) * vox).abs().max().item()
+    e_ba = ((phi_BA.cpu() - ref_BA) * vox).abs().max().item()
+    print(f"register {shape}: max displacement {disp_vox:.2f} vox; map error AB {e_ab:.2e} BA {e_ba:.2e} vox")
+    assert disp_vox > 0.5                      # the synthetic weights move things by voxels, not nothing
+    assert e_ab < 2e-3 and e_ba < 2e-3         # 2e-3 voxel ~ 7e-4 mm at 0.36 mm spacing
+
+
+def _geoms():
+    from oracle.warp_oracle import Geometry
+    th = 0.05
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    gA = Geometry((44, 40, 24), (0.36, 0.37, 0.7), (-10.0, 5.0, 2.0), R)
+    gB = Geometry((48, 36, 20), (0.40, 0.35, 0.8), (-12.0, 4.0, 1.0), np.eye(3))
+    return gA, gB
+
+
+def test_warp_volume_and_points_match_itk_oracle():
+    _cuda()
+    from oai_analysis_2_b200 import transforms
+    from oracle import warp_oracle
+    gA, gB = _geoms()
+    net = (12, 20, 22)  # z,y,x
+    rng = np.random.default_rng(5)
+    disp = np.stack([_smooth(net, 50 + i, 2.0).numpy() for i in range(3)], -1).astype(np.float32)
+    prob = rng.random((2, 24, 40, 44)).astype(np.float32)
+    tr_ref = warp_oracle.CompositeTransform(disp.astype(np.float64), gA, gB)
+    tA = transforms.Geometry(gA.size, gA.spacing, gA.origin, gA.direction)
+    tB = transforms.Geometry(gB.size, gB.spacing, gB.origin, gB.direction)
+    tr = transforms.CompositeTransform(torch.from_numpy(disp).cuda(), tA, tB)
+    got = tr.resample_device(torch.from_numpy(prob).cuda(), tA, tB).cpu().numpy()
+    for c in range(2):
+        ref = warp_oracle.resample_image(prob[c], tr_ref, gA, gB)
+        assert (ref > 0).mean() > 0.3
+        assert np.abs(got[c] - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    # points: inside, near the border, and outside the field buffer (identity there)
+    lo = gB.index_to_physical(np.zeros(3)) - 3.0
+    hi = gB.index_to_physical(gB.size - 1.0) + 3.0
+    pts = rng.uniform(lo, hi, (5000, 3))
+    ref = tr_ref.transform_points(pts)
+    got = tr.transform_points(pts)
+    assert np.abs(got - ref).max() < 1e-6
+    assert np.abs(ref - pts).max() > 0.5
+    assert tr.transform_points(np.zeros((0, 3))).shape == (0, 3)
+    assert np.allclose(tr.TransformPoint(pts[0]), ref[0], atol=1e-6)
