@@ -64,6 +64,12 @@ OAI_API int oai_conv3d_igemm_plan(int D, int H, int W, int c0, int c1, int cout,
 OAI_API int oai_pack_conv_weights(const float* w, int cout, int c0, int c1, int D, int H, int W, int pointwise, int ab_format,
                           int flags, void* dst, size_t dst_bytes);
 
+/* Per-launch timing of oai_conv3d_igemm with CUDA events on the launch stream (bench.py's roofline numbers):
+ * between begin and end every conv launch is bracketed by an event pair; end waits for them and returns the summed
+ * kernel time, the number of launches and their algorithmic FLOPs (2*voxels*cout*cin*taps). */
+OAI_API int oai_profile_begin(void);
+OAI_API int oai_profile_end(double* conv_ms, long long* conv_launches, double* conv_flops);
+
 /* Tiling geometry arrays used below (all z,y,x): geom[12] = {tile[3], effective[3], overlap[3], grid[3]} exactly as
  * Partition computes them (image_transforms.py:389-391,404-406); vol_dims[3] = image size. */
 

@@ -43,7 +43,7 @@ def ptr(t):
         return c_void(0)
     if hasattr(t, "data_ptr"):
         return c_void(t.data_ptr())
-    return c_void(t.ctypes.data)
+    return t.ctypes.data_as(c_void)  # keeps a reference to the array alive for the duration of the call
 
 
 def stream_ptr():

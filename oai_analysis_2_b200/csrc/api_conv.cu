@@ -126,10 +126,32 @@ inline uint16_t to16(float x, int fmt) {
   return u;
 }
 
+inline float from16(uint16_t u, int fmt) {
+  if (fmt == 0) {
+    __half h;
+    memcpy(&h, &u, 2);
+    return __half2float(h);
+  }
+  __nv_bfloat16 h;
+  memcpy(&h, &u, 2);
+  return __bfloat162float(h);
+}
+
 }  // namespace
 }  // namespace oai
 
 using namespace oai;
+
+namespace {
+// Optional per-launch timing of the conv kernel (CUDA events on the launch stream) for bench.py's roofline line.
+struct ProfEntry {
+  cudaEvent_t a, b;
+  double flops;
+};
+std::vector<ProfEntry> g_prof;
+size_t g_prof_used = 0;
+bool g_prof_on = false;
+}  // namespace
 
 extern "C" int oai_conv3d_igemm_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int flags,
                                      int* plan) {
@@ -156,6 +178,19 @@ extern "C" int oai_pack_conv_weights(const float* w, int cout, int c0, int c1, i
   const int ktaps = pointwise ? 1 : 27;
   uint8_t* out = static_cast<uint8_t*>(dst);
   memset(out, 0, need);
+  // Round to 16 bits with error feedback along the taps of each (co, ci) filter: the rounding residual of one tap is
+  // carried into the next, so the 27 rounding errors of a filter sum to (almost) zero.  On smooth inputs -- where all
+  // taps see nearly the same activation -- this cancels the systematic part of the weight-quantisation error.
+  std::vector<uint16_t> q(static_cast<size_t>(cout) * cin * ktaps);
+  for (size_t f = 0; f < static_cast<size_t>(cout) * cin; ++f) {
+    double carry = 0.0;
+    for (int t = 0; t < ktaps; ++t) {
+      const double v = static_cast<double>(w[f * ktaps + t]) + carry;
+      const uint16_t h = to16(static_cast<float>(v), ab_format);
+      q[f * ktaps + t] = h;
+      carry = v - static_cast<double>(from16(h, ab_format));
+    }
+  }
   for (int nh = 0; nh < pl.nhalf; ++nh) {
     for (int b = 0; b < pl.nblk; ++b) {
       uint8_t* blk = out + (static_cast<size_t>(nh) * pl.nblk + b) * pl.wblock_bytes;
@@ -182,13 +217,12 @@ extern "C" int oai_pack_conv_weights(const float* w, int cout, int c0, int c1, i
           const int tap = pointwise ? 0 : (kd * 3 + kh) * 3 + kw;
           for (int co = 0; co < pl.cph; ++co) {
             const int r = (kwi * nkd + ti) * pl.cph + co;
-            const float* wrow = w + (static_cast<size_t>(nh * pl.cph + co) * cin) * ktaps;
+            const uint16_t* wrow = q.data() + (static_cast<size_t>(nh * pl.cph + co) * cin) * ktaps;
             for (int j = 0; j < 64; ++j) {
               const int ci = cbase + j;
               if (ci >= climit) break;
-              const float v = wrow[static_cast<size_t>(ci) * ktaps + tap];
+              const uint16_t h = wrow[static_cast<size_t>(ci) * ktaps + tap];
               const size_t off = static_cast<size_t>(r) * 128 + (((j >> 3) ^ (r & 7)) << 4) + (j & 7) * 2;
-              const uint16_t h = to16(v, ab_format);
               memcpy(blk + off, &h, 2);
             }
           }
@@ -238,7 +272,44 @@ extern "C" int oai_conv3d_igemm(const void* src0, int c0, const void* src1, int 
   } else {
     tm1 = tm0;
   }
-  cudaError_t e = conv_igemm_launch(p, tm0, tm1, num_sms(), static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfEntry* pe = nullptr;
+  if (g_prof_on) {
+    if (g_prof_used == g_prof.size()) {
+      ProfEntry ne;
+      if (cudaEventCreate(&ne.a) != cudaSuccess || cudaEventCreate(&ne.b) != cudaSuccess)
+        return fail("conv profile: cannot create events");
+      g_prof.push_back(ne);
+    }
+    pe = &g_prof[g_prof_used++];
+    pe->flops = 2.0 * NT * D * H * W * static_cast<double>(cout) * (c0 + c1) * (pointwise ? 1 : 27);
+    cudaEventRecord(pe->a, st);
+  }
+  cudaError_t e = conv_igemm_launch(p, tm0, tm1, num_sms(), st);
+  if (pe) cudaEventRecord(pe->b, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_cuda(e, "conv_igemm launch");
+}
+
+extern "C" int oai_profile_begin(void) {
+  g_prof_used = 0;
+  g_prof_on = true;
+  return 0;
+}
+
+extern "C" int oai_profile_end(double* conv_ms, long long* conv_launches, double* conv_flops) {
+  g_prof_on = false;
+  double ms = 0, fl = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    if (int rc = check_cuda(cudaEventSynchronize(g_prof[i].b), "conv profile: event sync")) return rc;
+    float t = 0;
+    if (int rc = check_cuda(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b), "conv profile: elapsed")) return rc;
+    ms += t;
+    fl += g_prof[i].flops;
+  }
+  if (conv_ms) *conv_ms = ms;
+  if (conv_launches) *conv_launches = static_cast<long long>(g_prof_used);
+  if (conv_flops) *conv_flops = fl;
+  g_prof_used = 0;
+  return 0;
 }
