@@ -54,6 +54,17 @@ OAI_API int oai_conv3d_igemm(const void* src0, int c0, const void* src1, int c1,
                      int ab_format, void* out, long long obase, long long osN, long long osD, long long osH,
                      long long osW, int flags, void* stream);
 
+/* The last decoder layer fused with the network head and the assembler: dc1 = ConvTranspose3d(64->64,k3,s1,p1)+BN+ReLU
+ * (networks.py:64) feeding dc0 = Conv3d(64->ncls,k1) (networks.py:66,148), torch.sigmoid (segmenter.py:121)
+ * [out_mode 1: ">0.5", segmenter.py:123-124; 2: raw logits] and Partition.assemble's crop-and-place with the zeroed
+ * border shell (image_transforms.py:492-513).  dc0 is evaluated on the fp32 accumulators, the 64-channel activation is
+ * never written.  out: float32 [ncls][vol_dims]; geom / vol_dims / crop_zyx as for oai_seg_head. */
+OAI_API int oai_conv3d_igemm_head(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
+                                  const void* wpack, size_t wpack_bytes, const float* bias, int ab_format, int ncls,
+                                  const float* head_w, const float* head_b, float* out, const int* vol_dims,
+                                  const int* geom, int tile0, const int* crop_zyx, int out_mode, int flags,
+                                  void* stream);
+
 /* Geometry the kernel will use for (D,H,W,cin,cout,pointwise): fills plan[8] =
  * {mode, kd_per_block, R, nhalf, cout_per_half, nblk, wblock_bytes, nchunks}.  Pure host arithmetic (no GPU). */
 OAI_API int oai_conv3d_igemm_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int flags, int* plan);

@@ -19,7 +19,7 @@ namespace {
 constexpr int kFlagForcePerTap = 1;
 constexpr int kFlagBaseOffFormula = 2;  // debug: descriptor base_offset = (addr>>7)&7 (measured WRONG on B200)
 constexpr int kFlagForceKd1 = 4;
-constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8;  // 227 KB minus alignment slack and barriers
+constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8 - 2112;  // 227 KB minus alignment slack, barriers, fused-head weights
 
 struct Plan {
   int mode, kd_per_block, R, nhalf, cph, nblk, nchunk0, nchunk1, k16, TW, TH, n_wbuf, n_astage;
@@ -233,13 +233,47 @@ extern "C" int oai_pack_conv_weights(const float* w, int cout, int c0, int c1, i
   return 0;
 }
 
+static int conv_common(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
+                       const void* wpack, size_t wpack_bytes, const float* bias, int cout, int pointwise, int relu,
+                       int ab_format, void* out, long long obase, long long osN, long long osD, long long osH,
+                       long long osW, int flags, const HeadFuse* head, void* stream);
+
 extern "C" int oai_conv3d_igemm(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
                                 const void* wpack, size_t wpack_bytes, const float* bias, int cout, int pointwise,
                                 int relu, int ab_format, void* out, long long obase, long long osN, long long osD,
                                 long long osH, long long osW, int flags, void* stream) {
+  OAI_REQUIRE(out != nullptr, "conv: null output");
+  return conv_common(src0, c0, src1, c1, NT, D, H, W, wpack, wpack_bytes, bias, cout, pointwise, relu, ab_format, out,
+                     obase, osN, osD, osH, osW, flags, nullptr, stream);
+}
+
+extern "C" int oai_conv3d_igemm_head(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
+                                     const void* wpack, size_t wpack_bytes, const float* bias, int ab_format,
+                                     int ncls, const float* head_w, const float* head_b, float* out,
+                                     const int* vol_dims, const int* geom, int tile0, const int* crop_zyx,
+                                     int out_mode, int flags, void* stream) {
+  OAI_REQUIRE(head_w && head_b && out && vol_dims && geom && crop_zyx, "conv head: null pointer");
+  OAI_REQUIRE(ncls >= 1 && ncls <= 8, "conv head: ncls=%d unsupported", ncls);
+  OAI_REQUIRE(geom[0] == D && geom[1] == H && geom[2] == W, "conv head: tile geometry does not match the layer");
+  HeadFuse hd;
+  hd.enabled = 1; hd.ncls = ncls; hd.out_mode = out_mode; hd.w = head_w; hd.b = head_b; hd.out = out;
+  hd.VD = vol_dims[0]; hd.VH = vol_dims[1]; hd.VW = vol_dims[2];
+  hd.ed = geom[3]; hd.eh = geom[4]; hd.ew = geom[5];
+  hd.od = geom[6]; hd.oh = geom[7]; hd.ow = geom[8];
+  hd.gh = geom[10]; hd.gw = geom[11]; hd.tile0 = tile0;
+  hd.cz = crop_zyx[0]; hd.cy = crop_zyx[1]; hd.cx = crop_zyx[2];
+  return conv_common(src0, c0, src1, c1, NT, D, H, W, wpack, wpack_bytes, bias, 64, 0, 1, ab_format, nullptr, 0, 0, 0,
+                     0, 0, flags, &hd, stream);
+}
+
+static int conv_common(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
+                       const void* wpack, size_t wpack_bytes, const float* bias, int cout, int pointwise, int relu,
+                       int ab_format, void* out, long long obase, long long osN, long long osD, long long osH,
+                       long long osW, int flags, const HeadFuse* head, void* stream) {
   Plan pl;
   if (make_plan(D, H, W, c0, c1, cout, pointwise, flags, &pl)) return 1;
-  OAI_REQUIRE(src0 && wpack && bias && out, "conv: null pointer");
+  OAI_REQUIRE(src0 && wpack && bias, "conv: null pointer");
+  OAI_REQUIRE(!head || (pl.cph == 64 && pl.nhalf == 1), "conv head: the fused head needs a 64-channel layer");
   OAI_REQUIRE((c1 == 0) == (src1 == nullptr), "conv: src1/c1 mismatch");
   const size_t need = static_cast<size_t>(pl.nhalf) * pl.nblk * pl.wblock_bytes;
   OAI_REQUIRE(wpack_bytes == need, "conv: packed weights are %zu bytes, geometry needs %zu", wpack_bytes, need);
@@ -262,6 +296,7 @@ extern "C" int oai_conv3d_igemm(const void* src0, int c0, const void* src1, int 
   p.out = out;
   p.obase = obase; p.osN = osN; p.osD = osD; p.osH = osH; p.osW = osW;
   p.nunits = NT * (D / pl.R) * ((H / pl.TH) * (W / pl.TW)) * pl.nhalf;
+  if (head) p.head = *head;
 
   const int bw = pl.mode == kModeRowShared ? 130 : pl.TW;
   const int bh = pl.TH;

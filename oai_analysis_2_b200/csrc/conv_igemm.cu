@@ -96,6 +96,19 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// acc[k] += sum_i relu(v[i] + bias[i]) * w[k][i] over one 32-column chunk (w rows are 64 floats apart)
+template <int NC>
+__device__ __forceinline__ void head_dot(const uint32_t (&v)[32], const float* __restrict__ bias,
+                                         const float* __restrict__ w, float (&acc)[8], int ncls = NC) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float f = fmaxf(__uint_as_float(v[i]) + __ldg(bias + i), 0.f);
+#pragma unroll
+    for (int k = 0; k < NC; ++k)
+      if (k < ncls) acc[k] = fmaf(f, w[k * 64 + i], acc[k]);
+  }
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -114,6 +127,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   uint64_t* acc_full = bars + 24;   // [8]
   uint64_t* acc_empty = bars + 32;  // [8]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  float* s_head = reinterpret_cast<float*>(bars + 48);  // [ncls*64 + ncls] when the head is fused
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,6 +150,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
+  }
+  if (p.head.enabled) {
+    for (int i = threadIdx.x; i < p.head.ncls * 64; i += blockDim.x) s_head[i] = p.head.w[i];
+    for (int i = threadIdx.x; i < p.head.ncls; i += blockDim.x) s_head[p.head.ncls * 64 + i] = p.head.b[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -278,6 +296,53 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
       for (int a = 0; a < p.R; ++a) {
         mbar_wait(&acc_full[a], it & 1u, 600 + a);
         tc_fence_after();
+        if (p.head.enabled) {
+          // fused dc0 + sigmoid + crop-and-place: only interior voxels of the tile are ever written
+          const HeadFuse& hd = p.head;
+          const int z = ui.d0 + a - hd.od, y = ui.h0 + th - hd.oh, x = ui.w0 + tw - hd.ow;
+          const bool row_in = z >= 0 && z < hd.ed;  // warp-uniform when TH == 1
+          const bool mine = row_in && y >= 0 && y < hd.eh && x >= 0 && x < hd.ew;
+          if (__any_sync(0xffffffffu, mine)) {
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+            for (int j = 0; j < 2; ++j) {
+              uint32_t v[32];
+              tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                static_cast<uint32_t>(a * p.cout + j * 32), v);
+              tmem_ld_wait();
+              switch (hd.ncls) {
+                case 1: head_dot<1>(v, bias + j * 32, s_head + j * 32, acc); break;
+                case 2: head_dot<2>(v, bias + j * 32, s_head + j * 32, acc); break;
+                case 3: head_dot<3>(v, bias + j * 32, s_head + j * 32, acc); break;
+                case 4: head_dot<4>(v, bias + j * 32, s_head + j * 32, acc); break;
+                default: head_dot<8>(v, bias + j * 32, s_head + j * 32, acc, hd.ncls); break;
+              }
+            }
+            if (mine) {
+              const int tile = hd.tile0 + ui.n;
+              const int tk = tile % hd.gw, tj = (tile / hd.gw) % hd.gh, ti = tile / (hd.gw * hd.gh);
+              const int gz = ti * hd.ed + z, gy = tj * hd.eh + y, gx = tk * hd.ew + x;
+              if (gz < hd.VD && gy < hd.VH && gx < hd.VW) {
+                const bool shell = gz < hd.cz || gz >= hd.VD - hd.cz || gy < hd.cy || gy >= hd.VH - hd.cy ||
+                                   gx < hd.cx || gx >= hd.VW - hd.cx;
+                const size_t o = (static_cast<size_t>(gz) * hd.VH + gy) * hd.VW + gx;
+                const size_t cls_stride = static_cast<size_t>(hd.VD) * hd.VH * hd.VW;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  if (k >= hd.ncls) break;
+                  float r = 0.f;
+                  if (!shell) {
+                    const float logit = acc[k] + s_head[hd.ncls * 64 + k];
+                    r = hd.out_mode == 2 ? logit : 1.f / (1.f + __expf(-logit));
+                    if (hd.out_mode == 1) r = r > 0.5f ? 1.f : 0.f;
+                  }
+                  hd.out[k * cls_stride + o] = r;
+                }
+              }
+            }
+          }
+        } else {
         uint16_t* dst = out + off0 + (ui.d0 + a) * p.osD;
         for (int j = 0; j < p.cout / 32; ++j) {
           uint32_t v[32];
@@ -299,6 +364,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
         }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[a]);
@@ -318,7 +384,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 
 static size_t conv_igemm_smem_bytes(const ConvIgemmParams& p) {
   const size_t wstride = (p.wblock_bytes + 1023u) & ~size_t(1023);
-  return 1024 + p.n_wbuf * wstride + static_cast<size_t>(p.n_astage) * p.astage_stride + 48 * 8;
+  return 1024 + p.n_wbuf * wstride + static_cast<size_t>(p.n_astage) * p.astage_stride + 48 * 8 + 2112;
 }
 
 cudaError_t conv_igemm_launch(const ConvIgemmParams& p, const CUtensorMap& tm0, const CUtensorMap& tm1, int num_sms,

@@ -12,6 +12,19 @@ enum ConvMode : int {
   kModePointwise = 2,  // 1x1x1 (also each of the 8 sub-filters of a k2 s2 transposed conv)
 };
 
+// Optional fused epilogue of the last decoder layer: dc0 (1x1x1, C->ncls) + sigmoid (+ >0.5) + Partition.assemble
+// crop-and-place, computed from the fp32 accumulators so the layer's activation is never written.
+struct HeadFuse {
+  int enabled;
+  int ncls, out_mode;             // 0 probability, 1 mask, 2 logit
+  const float* w;                 // [ncls][64]
+  const float* b;                 // [ncls]
+  float* out;                     // [ncls][VD][VH][VW]
+  int VD, VH, VW;
+  int ed, eh, ew, od, oh, ow, gh, gw, tile0;
+  int cz, cy, cx;
+};
+
 struct ConvIgemmParams {
   // activation grid (identical for input and output: stride-1 "same" conv or pointwise)
   int NT, D, H, W;
@@ -40,6 +53,7 @@ struct ConvIgemmParams {
   void* out;
   long long obase, osN, osD, osH, osW;
   int nunits;
+  HeadFuse head;
 };
 
 }  // namespace oai

@@ -183,3 +183,16 @@ def warp_points(pts, disp, phys_to_net, net_to_phys):
     check(lib.oai_warp_points(ptr(pts), c_ll(pts.shape[0]), ptr(disp), ptr(_dims(*disp.shape[:3])), ptr(a), ptr(b),
                               ptr(out), stream_ptr()), "warp_points")
     return out
+
+
+def conv3d_igemm_head(src0, wpack, bias, head_w, head_b, out, geom, tile0, crop_zyx, out_mode=0, ab_format=0,
+                      flags=0):
+    """Last decoder layer (64->64, k3) fused with dc0 + sigmoid + crop-and-place into out [ncls, VD, VH, VW]."""
+    NT, D, H, W, c0 = src0.shape
+    ncls = head_w.shape[0]
+    dims = np.asarray(out.shape[1:], dtype=np.int32)
+    crop = np.asarray(crop_zyx, dtype=np.int32)
+    check(lib.oai_conv3d_igemm_head(ptr(src0), c0, None, 0, NT, D, H, W, ptr(wpack), c_size(wpack.numel()), ptr(bias),
+                                    ab_format, ncls, ptr(head_w), ptr(head_b), ptr(out), ptr(dims), ptr(geom), tile0,
+                                    ptr(crop), out_mode, flags, stream_ptr()), "conv3d_igemm_head")
+    return out

@@ -179,7 +179,7 @@ class UNet:
         return out
 
     def forward_features(self, P, e0):
-        """networks.py:110-146 from ec1 to dc1 on act16 tensors; e0 is the stem (ec0) output."""
+        """networks.py:110-144 from ec1 to dc2 on act16 tensors; e0 is the stem (ec0) output."""
         fmt = self._fmt()
         syn0 = self._conv(P, "ec1", e0)
         del e0
@@ -192,7 +192,13 @@ class UNet:
         del d7, syn1
         d2 = self._conv(P, "dc2", self._up(P, "dc3", d4), syn0)
         del d4, syn0
-        return self._conv(P, "dc1", d2)
+        return d2
+
+    def head(self, P, d2, out, geom, tile0, crop_zyx, out_mode):
+        """dc1 + dc0 + sigmoid + assemble in one launch (networks.py:145-148, segmenter.py:121-129)."""
+        L = P["dc1"]
+        return ops.conv3d_igemm_head(d2, L["w"], L["b"], P["dc0"]["w"], P["dc0"]["b"], out, geom, tile0, crop_zyx,
+                                     out_mode, self._fmt())
 
     def forward(self, x):
         """Module-style forward on explicit tiles: x [N, 1, D, H, W] float32 (cuda) -> logits [N, n_classes, D, H, W].
@@ -205,9 +211,9 @@ class UNet:
         vol = x.reshape(N * td, th, tw).contiguous().float()
         geom = ops.make_geom((td, th, tw), (td, th, tw), (0, 0, 0), (N, 1, 1))
         e0 = ops.seg_stem(vol, geom, 0, N, P["ec0"]["w"], P["ec0"]["b"], self._fmt())
-        d1 = self.forward_features(P, e0)
+        d2 = self.forward_features(P, e0)
         out = torch.empty((self.n_classes, N * td, th, tw), dtype=torch.float32, device=x.device)
-        ops.seg_head(d1, P["dc0"]["w"], P["dc0"]["b"], out, geom, 0, (0, 0, 0), out_mode=2, ab_format=self._fmt())
+        self.head(P, d2, out, geom, 0, (0, 0, 0), 2)
         return out.view(self.n_classes, N, td, th, tw).transpose(0, 1)
 
     __call__ = forward

@@ -81,10 +81,9 @@ class Segmenter3DInPatchClassWise(Segmenter3DInPatch):
         for t0 in range(0, T, nb):
             n = min(nb, T - t0)
             e0 = ops.seg_stem(volume, geom, t0, n, P["ec0"]["w"], P["ec0"]["b"], fmt)
-            d1 = model.forward_features(P, e0)
-            ops.seg_head(d1, P["dc0"]["w"], P["dc0"]["b"], out, geom, t0, crop_zyx,
-                         out_mode=0 if if_output_prob_map else 1, ab_format=fmt)
-            del d1
+            d2 = model.forward_features(P, e0)
+            model.head(P, d2, out, geom, t0, crop_zyx, 0 if if_output_prob_map else 1)
+            del d2
         return out
 
     def segment(self, image, if_output_prob_map=False, if_output_itk=True):

@@ -96,6 +96,20 @@ def test_segmenter_matches_reference_golden(name, tmp_path):
     fcm, tcm = seg.segment(vol, if_output_prob_map=False, if_output_itk=False)
     d_fc, d_tc = dice(fcm, z["fc_mask"]), dice(tcm, z["tc_mask"])
     print(f"{name}: prob max-abs FC {e_fc:.2e} TC {e_tc:.2e}; Dice FC {d_fc:.5f} TC {d_tc:.5f}")
+    # context: the reference's own GPU path (same torch modules on cuda, cuDNN TF32 convolutions as torch defaults)
+    from oracle.seg_oracle import segment as oracle_segment
+    torch.backends.cudnn.allow_tf32 = True
+    sd_c = {k: v.cuda() for k, v in sd.items()}
+    import oracle.seg_oracle as so
+    _orig = so.unet_forward
+    so.unet_forward = lambda s_, x_, bn_: _orig(s_, x_.cuda(), bn_).cpu()
+    try:
+        rfc, rtc = oracle_segment(vol, sd_c, m["patch"], tuple(m["overlap"]), 4, m["BN"])
+    finally:
+        so.unet_forward = _orig
+        torch.backends.cudnn.allow_tf32 = False
+    print(f"{name}: reference torch-cuda TF32 path vs fp32 CPU golden: prob max-abs {np.abs(rfc - z['fc']).max():.2e} "
+          f"{np.abs(rtc - z['tc']).max():.2e}; Dice {dice(rfc, z['fc_mask']):.5f} {dice(rtc, z['tc_mask']):.5f}")
     assert e_fc <= 1e-2 and e_tc <= 1e-2
     assert d_fc >= 0.999 and d_tc >= 0.999
     # border shell is exactly zero (image_transforms.py:509-513)
