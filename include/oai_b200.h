@@ -54,6 +54,15 @@ OAI_API int oai_conv3d_igemm(const void* src0, int c0, const void* src1, int c1,
                      int ab_format, void* out, long long obase, long long osN, long long osD, long long osH,
                      long long osW, int flags, void* stream);
 
+/* oai_conv3d_igemm restricted to the output sub-box region = {d_lo, d_cnt, h_lo, h_cnt} (full rows in w).  The
+ * reference computes every decoder layer on the whole tile and then keeps only the tile interior
+ * (image_transforms.py:497-503); outputs no kept voxel depends on ("dead halo") need not be computed.  Results inside
+ * the region are identical to the full-layer call; memory outside it is left untouched. */
+OAI_API int oai_conv3d_igemm_region(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
+                                    const void* wpack, size_t wpack_bytes, const float* bias, int cout, int pointwise,
+                                    int relu, int ab_format, void* out, long long obase, long long osN, long long osD,
+                                    long long osH, long long osW, int flags, const int* region, void* stream);
+
 /* The last decoder layer fused with the network head and the assembler: dc1 = ConvTranspose3d(64->64,k3,s1,p1)+BN+ReLU
  * (networks.py:64) feeding dc0 = Conv3d(64->ncls,k1) (networks.py:66,148), torch.sigmoid (segmenter.py:121)
  * [out_mode 1: ">0.5", segmenter.py:123-124; 2: raw logits] and Partition.assemble's crop-and-place with the zeroed
@@ -77,9 +86,10 @@ OAI_API int oai_pack_conv_weights(const float* w, int cout, int c0, int c1, int 
 
 /* Per-launch timing of oai_conv3d_igemm with CUDA events on the launch stream (bench.py's roofline numbers):
  * between begin and end every conv launch is bracketed by an event pair; end waits for them and returns the summed
- * kernel time, the number of launches and their algorithmic FLOPs (2*voxels*cout*cin*taps). */
+ * kernel time, the number of launches, their algorithmic FLOPs (2*voxels*cout*cin*taps over the whole layer, i.e. what
+ * the reference executes) and the FLOPs actually issued (dead-halo rows skipped, see oai_conv3d_igemm_region). */
 OAI_API int oai_profile_begin(void);
-OAI_API int oai_profile_end(double* conv_ms, long long* conv_launches, double* conv_flops);
+OAI_API int oai_profile_end(double* conv_ms, long long* conv_launches, double* conv_flops, double* conv_exec_flops);
 
 /* Tiling geometry arrays used below (all z,y,x): geom[12] = {tile[3], effective[3], overlap[3], grid[3]} exactly as
  * Partition computes them (image_transforms.py:389-391,404-406); vol_dims[3] = image size. */

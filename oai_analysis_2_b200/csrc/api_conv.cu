@@ -26,7 +26,7 @@ struct Plan {
   uint32_t wblock_bytes, astage_bytes, astage_stride;
 };
 
-int make_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int flags, Plan* pl) {
+int make_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int flags, Plan* pl, int d_cnt = 0) {
   OAI_REQUIRE(D > 0 && H > 0 && W > 0 && c0 > 0 && c1 >= 0 && cout > 0, "conv plan: bad dims");
   OAI_REQUIRE(c0 % 8 == 0 && c1 % 8 == 0, "conv plan: channel counts must be multiples of 8 (got %d,%d)", c0, c1);
   pl->TW = W < 128 ? W : 128;
@@ -37,9 +37,10 @@ int make_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int 
   OAI_REQUIRE(cout % pl->nhalf == 0, "conv plan: cout=%d not divisible into %d N splits", cout, pl->nhalf);
   pl->cph = cout / pl->nhalf;
   OAI_REQUIRE(pl->cph % 32 == 0, "conv plan: cout per split (%d) must be a multiple of 32", pl->cph);
+  if (d_cnt <= 0) d_cnt = D;
   int R = 1;
   for (int r = 1; r <= 8; ++r)
-    if (D % r == 0 && r * pl->cph <= 512) R = r;
+    if (d_cnt % r == 0 && r * pl->cph <= 512) R = r;
   pl->R = R;
   pl->nchunk0 = (c0 + 63) / 64;
   pl->nchunk1 = (c1 + 63) / 64;
@@ -146,7 +147,8 @@ namespace {
 // Optional per-launch timing of the conv kernel (CUDA events on the launch stream) for bench.py's roofline line.
 struct ProfEntry {
   cudaEvent_t a, b;
-  double flops;
+  double flops;       // algorithmic: every MAC the reference executes for this layer
+  double exec_flops;  // MACs actually issued (dead-halo rows skipped)
 };
 std::vector<ProfEntry> g_prof;
 size_t g_prof_used = 0;
@@ -236,7 +238,7 @@ extern "C" int oai_pack_conv_weights(const float* w, int cout, int c0, int c1, i
 static int conv_common(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
                        const void* wpack, size_t wpack_bytes, const float* bias, int cout, int pointwise, int relu,
                        int ab_format, void* out, long long obase, long long osN, long long osD, long long osH,
-                       long long osW, int flags, const HeadFuse* head, void* stream);
+                       long long osW, int flags, const HeadFuse* head, const int* region, void* stream);
 
 extern "C" int oai_conv3d_igemm(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
                                 const void* wpack, size_t wpack_bytes, const float* bias, int cout, int pointwise,
@@ -244,7 +246,17 @@ extern "C" int oai_conv3d_igemm(const void* src0, int c0, const void* src1, int 
                                 long long osH, long long osW, int flags, void* stream) {
   OAI_REQUIRE(out != nullptr, "conv: null output");
   return conv_common(src0, c0, src1, c1, NT, D, H, W, wpack, wpack_bytes, bias, cout, pointwise, relu, ab_format, out,
-                     obase, osN, osD, osH, osW, flags, nullptr, stream);
+                     obase, osN, osD, osH, osW, flags, nullptr, nullptr, stream);
+}
+
+extern "C" int oai_conv3d_igemm_region(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
+                                       const void* wpack, size_t wpack_bytes, const float* bias, int cout,
+                                       int pointwise, int relu, int ab_format, void* out, long long obase,
+                                       long long osN, long long osD, long long osH, long long osW, int flags,
+                                       const int* region, void* stream) {
+  OAI_REQUIRE(out != nullptr && region != nullptr, "conv region: null pointer");
+  return conv_common(src0, c0, src1, c1, NT, D, H, W, wpack, wpack_bytes, bias, cout, pointwise, relu, ab_format, out,
+                     obase, osN, osD, osH, osW, flags, nullptr, region, stream);
 }
 
 extern "C" int oai_conv3d_igemm_head(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
@@ -252,6 +264,8 @@ extern "C" int oai_conv3d_igemm_head(const void* src0, int c0, const void* src1,
                                      int ncls, const float* head_w, const float* head_b, float* out,
                                      const int* vol_dims, const int* geom, int tile0, const int* crop_zyx,
                                      int out_mode, int flags, void* stream) {
+  // only the tile interior is ever written, so only the interior rows are computed
+  const int region[4] = {geom[6], geom[3], geom[7], geom[4]};
   OAI_REQUIRE(head_w && head_b && out && vol_dims && geom && crop_zyx, "conv head: null pointer");
   OAI_REQUIRE(ncls >= 1 && ncls <= 8, "conv head: ncls=%d unsupported", ncls);
   OAI_REQUIRE(geom[0] == D && geom[1] == H && geom[2] == W, "conv head: tile geometry does not match the layer");
@@ -263,15 +277,25 @@ extern "C" int oai_conv3d_igemm_head(const void* src0, int c0, const void* src1,
   hd.gh = geom[10]; hd.gw = geom[11]; hd.tile0 = tile0;
   hd.cz = crop_zyx[0]; hd.cy = crop_zyx[1]; hd.cx = crop_zyx[2];
   return conv_common(src0, c0, src1, c1, NT, D, H, W, wpack, wpack_bytes, bias, 64, 0, 1, ab_format, nullptr, 0, 0, 0,
-                     0, 0, flags, &hd, stream);
+                     0, 0, flags, &hd, region, stream);
 }
 
 static int conv_common(const void* src0, int c0, const void* src1, int c1, int NT, int D, int H, int W,
                        const void* wpack, size_t wpack_bytes, const float* bias, int cout, int pointwise, int relu,
                        int ab_format, void* out, long long obase, long long osN, long long osD, long long osH,
-                       long long osW, int flags, const HeadFuse* head, void* stream) {
+                       long long osW, int flags, const HeadFuse* head, const int* region, void* stream) {
+  // region = {d_lo, d_cnt, h_lo, h_cnt}: the output sub-box to compute (full rows in w); h range is widened to whole
+  // M-tile rows.  Everything outside is dead halo the caller never reads.
+  int d_lo = 0, d_cnt = D, h_lo = 0, h_cnt = H;
+  if (region) {
+    d_lo = region[0]; d_cnt = region[1]; h_lo = region[2]; h_cnt = region[3];
+    OAI_REQUIRE(d_lo >= 0 && d_cnt >= 1 && d_lo + d_cnt <= D && h_lo >= 0 && h_cnt >= 1 && h_lo + h_cnt <= H,
+                "conv: region [%d,+%d)x[%d,+%d) outside %dx%d", d_lo, d_cnt, h_lo, h_cnt, D, H);
+  }
   Plan pl;
-  if (make_plan(D, H, W, c0, c1, cout, pointwise, flags, &pl)) return 1;
+  if (make_plan(D, H, W, c0, c1, cout, pointwise, flags, &pl, d_cnt)) return 1;
+  const int hp_lo = h_lo / pl.TH;
+  const int hp_cnt = (h_lo + h_cnt + pl.TH - 1) / pl.TH - hp_lo;
   OAI_REQUIRE(src0 && wpack && bias, "conv: null pointer");
   OAI_REQUIRE(!head || (pl.cph == 64 && pl.nhalf == 1), "conv head: the fused head needs a 64-channel layer");
   OAI_REQUIRE((c1 == 0) == (src1 == nullptr), "conv: src1/c1 mismatch");
@@ -295,7 +319,8 @@ static int conv_common(const void* src0, int c0, const void* src1, int c1, int N
   p.bias = bias;
   p.out = out;
   p.obase = obase; p.osN = osN; p.osD = osD; p.osH = osH; p.osW = osW;
-  p.nunits = NT * (D / pl.R) * ((H / pl.TH) * (W / pl.TW)) * pl.nhalf;
+  p.d_lo = d_lo; p.d_cnt = d_cnt; p.hp_lo = hp_lo; p.hp_cnt = hp_cnt;
+  p.nunits = NT * (d_cnt / pl.R) * (hp_cnt * (W / pl.TW)) * pl.nhalf;
   if (head) p.head = *head;
 
   const int bw = pl.mode == kModeRowShared ? 130 : pl.TW;
@@ -318,6 +343,7 @@ static int conv_common(const void* src0, int c0, const void* src1, int c1, int N
     }
     pe = &g_prof[g_prof_used++];
     pe->flops = 2.0 * NT * D * H * W * static_cast<double>(cout) * (c0 + c1) * (pointwise ? 1 : 27);
+    pe->exec_flops = pe->flops * (static_cast<double>(d_cnt) * hp_cnt * pl.TH) / (static_cast<double>(D) * H);
     cudaEventRecord(pe->a, st);
   }
   cudaError_t e = conv_igemm_launch(p, tm0, tm1, num_sms(), st);
@@ -332,19 +358,22 @@ extern "C" int oai_profile_begin(void) {
   return 0;
 }
 
-extern "C" int oai_profile_end(double* conv_ms, long long* conv_launches, double* conv_flops) {
+extern "C" int oai_profile_end(double* conv_ms, long long* conv_launches, double* conv_flops,
+                               double* conv_exec_flops) {
   g_prof_on = false;
-  double ms = 0, fl = 0;
+  double ms = 0, fl = 0, xfl = 0;
   for (size_t i = 0; i < g_prof_used; ++i) {
     if (int rc = check_cuda(cudaEventSynchronize(g_prof[i].b), "conv profile: event sync")) return rc;
     float t = 0;
     if (int rc = check_cuda(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b), "conv profile: elapsed")) return rc;
     ms += t;
     fl += g_prof[i].flops;
+    xfl += g_prof[i].exec_flops;
   }
   if (conv_ms) *conv_ms = ms;
   if (conv_launches) *conv_launches = static_cast<long long>(g_prof_used);
   if (conv_flops) *conv_flops = fl;
+  if (conv_exec_flops) *conv_exec_flops = xfl;
   g_prof_used = 0;
   return 0;
 }

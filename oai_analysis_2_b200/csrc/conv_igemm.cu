@@ -74,15 +74,15 @@ struct UnitInfo {
 
 __device__ __forceinline__ UnitInfo decode_unit(const ConvIgemmParams& p, int u) {
   UnitInfo ui;
-  const int npw = p.W / p.TW, nph = p.H / p.TH;
-  const int np = npw * nph, ndg = p.D / p.R;
+  const int npw = p.W / p.TW;
+  const int np = npw * p.hp_cnt, ndg = p.d_cnt / p.R;
   ui.nh = u % p.nhalf;
   u /= p.nhalf;
   const int patch = u % np;
   u /= np;
-  ui.d0 = (u % ndg) * p.R;
+  ui.d0 = p.d_lo + (u % ndg) * p.R;
   ui.n = u / ndg;
-  ui.h0 = (patch / npw) * p.TH;
+  ui.h0 = (p.hp_lo + patch / npw) * p.TH;
   ui.w0 = (patch % npw) * p.TW;
   return ui;
 }

@@ -29,7 +29,9 @@ struct ConvIgemmParams {
   // activation grid (identical for input and output: stride-1 "same" conv or pointwise)
   int NT, D, H, W;
   int TW, TH;       // M tile = TH x TW voxels in one d-slice (TH*TW == 128)
-  int R;            // accumulators per unit = consecutive output d-slices (R*cout <= 512, D % R == 0)
+  int R;            // accumulators per unit = consecutive output d-slices (R*cout <= 512, d_cnt % R == 0)
+  int d_lo, d_cnt;  // output region computed: slices [d_lo, d_lo+d_cnt) ...
+  int hp_lo, hp_cnt;  // ... and patch rows [hp_lo, hp_lo+hp_cnt) (units of TH voxel rows); the rest is dead halo
   int cout;         // N per accumulator (multiple of 16, <= 256)
   int nhalf;        // N splits (cout_total = nhalf*cout)
   int nchunk0;      // 64-channel K chunks read from source 0

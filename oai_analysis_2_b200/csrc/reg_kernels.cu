@@ -19,40 +19,32 @@ namespace {
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.01f * v; }
 
 // ------------------------------------------------------------------------------------------------ conv k3
-template <int CO_T>
+// Register-tiled direct convolution: a thread produces XS x-adjacent outputs for CO_T output channels, so every
+// weight vector read from shared memory feeds XS FMAs per channel and every input value feeds up to 3*CO_T.
+template <int CO_T, int XS, int STRIDE>
 __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
   constexpr int CI_CHUNK = 8;
+  constexpr int NIN = (XS - 1) * STRIDE + 3;
   __shared__ __align__(16) float s_w[CI_CHUNK * 27 * CO_T];
   const int co0 = blockIdx.y * CO_T;
   const int n = blockIdx.z;
-  const long long nvox = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+  const int nsx = (p.Wo + XS - 1) / XS;
+  const long long nthr = static_cast<long long>(p.Do) * p.Ho * nsx;
   const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const bool active = v < nvox;
-  int xo = 0, yo = 0, zo = 0;
+  const bool active = v < nthr;
+  int sx = 0, yo = 0, zo = 0;
   if (active) {
-    xo = static_cast<int>(v % p.Wo);
-    yo = static_cast<int>((v / p.Wo) % p.Ho);
-    zo = static_cast<int>(v / (static_cast<long long>(p.Wo) * p.Ho));
+    sx = static_cast<int>(v % nsx);
+    yo = static_cast<int>((v / nsx) % p.Ho);
+    zo = static_cast<int>(v / (static_cast<long long>(nsx) * p.Ho));
   }
-  const int xi0 = xo * p.stride - 1, yi0 = yo * p.stride - 1, zi0 = zo * p.stride - 1;
-  // per-tap offsets / validity (zero padding)
-  int off[27];
-  unsigned valid = 0;
+  const int xo0 = sx * XS;
+  const int xi0 = xo0 * STRIDE - 1, yi0 = yo * STRIDE - 1, zi0 = zo * STRIDE - 1;
+  float acc[XS][CO_T];
 #pragma unroll
-  for (int kd = 0; kd < 3; ++kd)
+  for (int i = 0; i < XS; ++i)
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int z = zi0 + kd, y = yi0 + kh, x = xi0 + kw;
-        const int k = (kd * 3 + kh) * 3 + kw;
-        const bool ok = active && z >= 0 && z < p.Di && y >= 0 && y < p.Hi && x >= 0 && x < p.Wi;
-        off[k] = ok ? (z * p.Hi + y) * p.Wi + x : 0;
-        valid |= (ok ? 1u : 0u) << k;
-      }
-  float acc[CO_T];
-#pragma unroll
-  for (int j = 0; j < CO_T; ++j) acc[j] = 0.f;
+    for (int j = 0; j < CO_T; ++j) acc[i][j] = 0.f;
   const float* in_n = p.in + n * p.in_nstride;
   for (int ci0 = 0; ci0 < p.cin; ci0 += CI_CHUNK) {
     const int nci = min(CI_CHUNK, p.cin - ci0);
@@ -63,67 +55,98 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
       s_w[i] = co < p.cout_pad ? p.w[(static_cast<size_t>(ci0 + c) * 27 + k) * p.cout_pad + co] : 0.f;
     }
     __syncthreads();
+    if (!active) continue;
     for (int c = 0; c < nci; ++c) {
       const float* plane = in_n + (ci0 + c) * p.in_cstride;
       const float* wc = s_w + c * 27 * CO_T;
 #pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        float x = ((valid >> k) & 1u) ? __ldg(plane + off[k]) : 0.f;
-        if (p.leaky_in) x = leaky(x);
+      for (int kd = 0; kd < 3; ++kd) {
+        const int z = zi0 + kd;
+        if (z < 0 || z >= p.Di) continue;
 #pragma unroll
-        for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(x, wc[k * CO_T + j], acc[j]);
+        for (int kh = 0; kh < 3; ++kh) {
+          const int y = yi0 + kh;
+          if (y < 0 || y >= p.Hi) continue;
+          const float* row = plane + (static_cast<size_t>(z) * p.Hi + y) * p.Wi;
+          float xin[NIN];
+#pragma unroll
+          for (int i = 0; i < NIN; ++i) {
+            const int x = xi0 + i;
+            float t = (x >= 0 && x < p.Wi) ? __ldg(row + x) : 0.f;
+            xin[i] = p.leaky_in ? leaky(t) : t;
+          }
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float* wk = wc + ((kd * 3 + kh) * 3 + kw) * CO_T;
+            float wv[CO_T];
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) wv[j] = wk[j];
+#pragma unroll
+            for (int i = 0; i < XS; ++i)
+#pragma unroll
+              for (int j = 0; j < CO_T; ++j) acc[i][j] = fmaf(xin[i * STRIDE + kw], wv[j], acc[i][j]);
+          }
+        }
       }
     }
   }
   if (!active) return;
   float* out_n = p.out + n * p.out_nstride;
-  const long long ovox = (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + xo;
 #pragma unroll
-  for (int j = 0; j < CO_T; ++j) {
-    const int co = co0 + j;
-    if (co >= p.cout) break;
-    float r = acc[j] + p.bias[co];
-    if (p.residual) {
-      const int cs = co - (p.cout - p.cin);  // zero padding sits in front of the pooled channels
-      if (cs >= 0) {
-        const float* plane = in_n + cs * p.in_cstride;
-        float s = 0.f;
-        int cnt = 0;
-        for (int dz = 0; dz < 2; ++dz)
-          for (int dy = 0; dy < 2; ++dy)
-            for (int dx = 0; dx < 2; ++dx) {
-              const int z = 2 * zo + dz, y = 2 * yo + dy, x = 2 * xo + dx;
-              if (z < p.Di && y < p.Hi && x < p.Wi) {
-                s += plane[(static_cast<size_t>(z) * p.Hi + y) * p.Wi + x];
-                ++cnt;
+  for (int i = 0; i < XS; ++i) {
+    const int xo = xo0 + i;
+    if (xo >= p.Wo) break;
+    const long long ovox = (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + xo;
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) {
+      const int co = co0 + j;
+      if (co >= p.cout) break;
+      float r = acc[i][j] + p.bias[co];
+      if (p.residual) {
+        const int cs = co - (p.cout - p.cin);  // zero padding sits in front of the pooled channels
+        if (cs >= 0) {
+          const float* plane = in_n + cs * p.in_cstride;
+          float s = 0.f;
+          int cnt = 0;
+          for (int dz = 0; dz < 2; ++dz)
+            for (int dy = 0; dy < 2; ++dy)
+              for (int dx = 0; dx < 2; ++dx) {
+                const int z = 2 * zo + dz, y = 2 * yo + dy, x = 2 * xo + dx;
+                if (z < p.Di && y < p.Hi && x < p.Wi) {
+                  s += plane[(static_cast<size_t>(z) * p.Hi + y) * p.Wi + x];
+                  ++cnt;
+                }
               }
-            }
-        r += s / static_cast<float>(cnt);
+          r += s / static_cast<float>(cnt);
+        }
       }
+      out_n[co * p.out_cstride + ovox] = r * p.out_scale;
     }
-    out_n[co * p.out_cstride + ovox] = r * p.out_scale;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ convT k4 s2 p1
-// Each thread produces the two x-adjacent outputs (2j, 2j+1) of one (zo, yo) row position for CO_T channels.
-template <int CO_T>
+// A thread produces XP x-adjacent output PAIRS (2*XP outputs) of one (zo, yo) row for CO_T channels.
+// o = 2 i - 1 + k  =>  per axis two taps: k = (o+1)%2 + 2 t, i = (o + 1 - k)/2, t in {0,1}.
+// Along x, output 2j uses (kx=1, ix=j), (kx=3, ix=j-1); output 2j+1 uses (kx=0, ix=j+1), (kx=2, ix=j).
+template <int CO_T, int XP>
 __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
   constexpr int CI_CHUNK = 4;
   __shared__ __align__(16) float s_w[CI_CHUNK * 64 * CO_T];
   const int co0 = blockIdx.y * CO_T;
   const int n = blockIdx.z;
   const int Wp = (p.Wo + 1) / 2;
-  const long long nthr = static_cast<long long>(p.Do) * p.Ho * Wp;
+  const int nsx = (Wp + XP - 1) / XP;
+  const long long nthr = static_cast<long long>(p.Do) * p.Ho * nsx;
   const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const bool active = v < nthr;
-  int j = 0, yo = 0, zo = 0;
+  int sx = 0, yo = 0, zo = 0;
   if (active) {
-    j = static_cast<int>(v % Wp);
-    yo = static_cast<int>((v / Wp) % p.Ho);
-    zo = static_cast<int>(v / (static_cast<long long>(Wp) * p.Ho));
+    sx = static_cast<int>(v % nsx);
+    yo = static_cast<int>((v / nsx) % p.Ho);
+    zo = static_cast<int>(v / (static_cast<long long>(nsx) * p.Ho));
   }
-  // o = 2 i - 1 + k  =>  k = (o+1)%2 + 2 t, i = (o + 1 - k)/2, t in {0,1}
+  const int j0 = sx * XP;
   int kz[2], iz[2], ky[2], iy[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
@@ -132,10 +155,11 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
     ky[t] = ((yo + 1) & 1) + 2 * t;
     iy[t] = (yo + 1 - ky[t]) / 2;
   }
-  // x inputs j-1, j, j+1 ; output 2j uses (kx=1,ix=j),(kx=3,ix=j-1) ; output 2j+1 uses (kx=0,ix=j+1),(kx=2,ix=j)
-  float acc0[CO_T], acc1[CO_T];
+  float acc0[XP][CO_T], acc1[XP][CO_T];
 #pragma unroll
-  for (int c = 0; c < CO_T; ++c) acc0[c] = acc1[c] = 0.f;
+  for (int i = 0; i < XP; ++i)
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) acc0[i][c] = acc1[i][c] = 0.f;
   const float* in_n = p.in + n * p.in_nstride;
   for (int ci0 = 0; ci0 < p.cin; ci0 += CI_CHUNK) {
     const int nci = min(CI_CHUNK, p.cin - ci0);
@@ -159,17 +183,27 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
           const int y = iy[ty];
           if (y < 0 || y >= p.Hi) continue;
           const float* row = plane + (static_cast<size_t>(z) * p.Hi + y) * p.Wi;
-          const float xm = (j - 1 >= 0 && j - 1 < p.Wi) ? leaky(__ldg(row + j - 1)) : 0.f;
-          const float xc = (j < p.Wi) ? leaky(__ldg(row + j)) : 0.f;
-          const float xp = (j + 1 < p.Wi) ? leaky(__ldg(row + j + 1)) : 0.f;
+          float xin[XP + 2];
+#pragma unroll
+          for (int i = 0; i < XP + 2; ++i) {
+            const int x = j0 - 1 + i;
+            xin[i] = (x >= 0 && x < p.Wi) ? leaky(__ldg(row + x)) : 0.f;
+          }
           const float* wk = wc + ((kz[tz] * 4 + ky[ty]) * 4) * CO_T;
+          float w0[CO_T], w1[CO_T], w2[CO_T], w3[CO_T];
 #pragma unroll
           for (int c = 0; c < CO_T; ++c) {
-            acc0[c] = fmaf(xc, wk[1 * CO_T + c], acc0[c]);
-            acc0[c] = fmaf(xm, wk[3 * CO_T + c], acc0[c]);
-            acc1[c] = fmaf(xp, wk[0 * CO_T + c], acc1[c]);
-            acc1[c] = fmaf(xc, wk[2 * CO_T + c], acc1[c]);
+            w0[c] = wk[c]; w1[c] = wk[CO_T + c]; w2[c] = wk[2 * CO_T + c]; w3[c] = wk[3 * CO_T + c];
           }
+#pragma unroll
+          for (int i = 0; i < XP; ++i)
+#pragma unroll
+            for (int c = 0; c < CO_T; ++c) {
+              acc0[i][c] = fmaf(xin[i + 1], w1[c], acc0[i][c]);
+              acc0[i][c] = fmaf(xin[i], w3[c], acc0[i][c]);
+              acc1[i][c] = fmaf(xin[i + 2], w0[c], acc1[i][c]);
+              acc1[i][c] = fmaf(xin[i + 1], w2[c], acc1[i][c]);
+            }
         }
       }
     }
@@ -186,25 +220,28 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
   }
   float* out_n = p.out + n * p.out_nstride;
 #pragma unroll
-  for (int xx = 0; xx < 2; ++xx) {
-    const int xo = 2 * j + xx;
-    if (xo >= p.Wo) break;
-    const float s = fmaxf(0.5f * (xo + 0.5f) - 0.5f, 0.f);
-    const int x0 = static_cast<int>(s), x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
-    const float lx = s - x0;
-    const long long ovox = (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + xo;
+  for (int i = 0; i < XP; ++i) {
 #pragma unroll
-    for (int c = 0; c < CO_T; ++c) {
-      const int co = co0 + c;
-      if (co >= p.cout) break;
-      const float* pl = in_n + co * p.in_cstride;
-      auto at = [&](int z, int y, int x) { return pl[(static_cast<size_t>(z) * p.Hi + y) * p.Wi + x]; };
-      const float r = (1.f - lz) * ((1.f - ly) * ((1.f - lx) * at(z0, y0, x0) + lx * at(z0, y0, x1)) +
-                                    ly * ((1.f - lx) * at(z0, y1, x0) + lx * at(z0, y1, x1))) +
-                      lz * ((1.f - ly) * ((1.f - lx) * at(z1, y0, x0) + lx * at(z1, y0, x1)) +
-                            ly * ((1.f - lx) * at(z1, y1, x0) + lx * at(z1, y1, x1)));
-      const float a = (xx == 0 ? acc0[c] : acc1[c]) + p.bias[co] + r;
-      out_n[co * p.out_cstride + ovox] = a * p.bn_scale[co] + p.bn_shift[co];
+    for (int xx = 0; xx < 2; ++xx) {
+      const int xo = 2 * (j0 + i) + xx;
+      if (xo >= p.Wo) break;
+      const float s = fmaxf(0.5f * (xo + 0.5f) - 0.5f, 0.f);
+      const int x0 = static_cast<int>(s), x1 = x0 + (x0 < p.Wi - 1 ? 1 : 0);
+      const float lx = s - x0;
+      const long long ovox = (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + xo;
+#pragma unroll
+      for (int c = 0; c < CO_T; ++c) {
+        const int co = co0 + c;
+        if (co >= p.cout) break;
+        const float* pl = in_n + co * p.in_cstride;
+        auto at = [&](int z, int y, int x) { return pl[(static_cast<size_t>(z) * p.Hi + y) * p.Wi + x]; };
+        const float r = (1.f - lz) * ((1.f - ly) * ((1.f - lx) * at(z0, y0, x0) + lx * at(z0, y0, x1)) +
+                                      ly * ((1.f - lx) * at(z0, y1, x0) + lx * at(z0, y1, x1))) +
+                        lz * ((1.f - ly) * ((1.f - lx) * at(z1, y0, x0) + lx * at(z1, y0, x1)) +
+                              ly * ((1.f - lx) * at(z1, y1, x0) + lx * at(z1, y1, x1)));
+        const float a = (xx == 0 ? acc0[i][c] : acc1[i][c]) + p.bias[co] + r;
+        out_n[co * p.out_cstride + ovox] = a * p.bn_scale[co] + p.bn_shift[co];
+      }
     }
   }
 }
@@ -438,23 +475,34 @@ inline unsigned grid_for(long long n, int block, int per_sm) {
 
 }  // namespace
 
+template <int CO_T, int XS>
+static void conv3_dispatch(const Conv3Params& p, cudaStream_t st) {
+  const long long nthr = static_cast<long long>(p.Do) * p.Ho * ((p.Wo + XS - 1) / XS);
+  dim3 g(static_cast<unsigned>((nthr + 127) / 128), (p.cout + CO_T - 1) / CO_T, p.N);
+  if (p.stride == 1) conv3_kernel<CO_T, XS, 1><<<g, 128, 0, st>>>(p);
+  else conv3_kernel<CO_T, XS, 2><<<g, 128, 0, st>>>(p);
+}
+
 int conv3_launch(const Conv3Params& p, cudaStream_t st) {
   const long long nvox = static_cast<long long>(p.Do) * p.Ho * p.Wo;
-  const unsigned gx = static_cast<unsigned>((nvox + 127) / 128);
-  if (p.cout <= 4) {
-    dim3 g(gx, (p.cout + 3) / 4, p.N);
-    conv3_kernel<4><<<g, 128, 0, st>>>(p);
-  } else {
-    dim3 g(gx, (p.cout + 15) / 16, p.N);
-    conv3_kernel<16><<<g, 128, 0, st>>>(p);
-  }
+  if (p.cout <= 4) conv3_dispatch<4, 8>(p, st);              // lastConv: 18 -> 3 at full resolution
+  else if (nvox * ((p.cout + 7) / 8) >= (1 << 18)) conv3_dispatch<8, 4>(p, st);
+  else conv3_dispatch<8, 1>(p, st);                           // deep levels: few voxels, favour parallelism
   return launched("conv3_kernel");
 }
 
+template <int CO_T, int XP>
+static void convt4_dispatch(const ConvT4Params& p, cudaStream_t st) {
+  const int Wp = (p.Wo + 1) / 2;
+  const long long nthr = static_cast<long long>(p.Do) * p.Ho * ((Wp + XP - 1) / XP);
+  dim3 g(static_cast<unsigned>((nthr + 127) / 128), (p.cout + CO_T - 1) / CO_T, p.N);
+  convt4_kernel<CO_T, XP><<<g, 128, 0, st>>>(p);
+}
+
 int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
-  const long long nthr = static_cast<long long>(p.Do) * p.Ho * ((p.Wo + 1) / 2);
-  dim3 g(static_cast<unsigned>((nthr + 127) / 128), (p.cout + 15) / 16, p.N);
-  convt4_kernel<16><<<g, 128, 0, st>>>(p);
+  const long long nout = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+  if (nout * ((p.cout + 7) / 8) >= (1 << 19)) convt4_dispatch<8, 4>(p, st);
+  else convt4_dispatch<8, 1>(p, st);
   return launched("convt4_kernel");
 }
 

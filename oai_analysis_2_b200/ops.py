@@ -34,7 +34,7 @@ def pack_conv_weights(w, c0, c1, D, H, W, pointwise=False, ab_format=0, flags=0,
 
 
 def conv3d_igemm(src0, src1, wpack, bias, cout, pointwise=False, relu=True, ab_format=0, out=None, out_view=None,
-                 flags=0):
+                 flags=0, region=None):
     """src*: [NT, D, H, W, C] 16-bit channels-last.  Returns [NT, D, H, W, cout] unless `out`/`out_view` given.
 
     out_view = (obase, osN, osD, osH, osW) in elements addresses into `out` (k2s2 transposed-conv scatter).
@@ -47,9 +47,16 @@ def conv3d_igemm(src0, src1, wpack, bias, cout, pointwise=False, relu=True, ab_f
     if out_view is None:
         out_view = (0, D * H * W * cout, H * W * cout, W * cout, cout)
     ob, sn, sd, sh, sw = out_view
-    check(lib.oai_conv3d_igemm(ptr(src0), c0, ptr(src1), c1, NT, D, H, W, ptr(wpack), c_size(wpack.numel()),
-                               ptr(bias), cout, int(pointwise), int(relu), ab_format, ptr(out), c_ll(ob), c_ll(sn),
-                               c_ll(sd), c_ll(sh), c_ll(sw), flags, stream_ptr()), "conv3d_igemm")
+    if region is None:
+        check(lib.oai_conv3d_igemm(ptr(src0), c0, ptr(src1), c1, NT, D, H, W, ptr(wpack), c_size(wpack.numel()),
+                                   ptr(bias), cout, int(pointwise), int(relu), ab_format, ptr(out), c_ll(ob), c_ll(sn),
+                                   c_ll(sd), c_ll(sh), c_ll(sw), flags, stream_ptr()), "conv3d_igemm")
+    else:
+        reg = np.asarray(region, dtype=np.int32)  # d_lo, d_cnt, h_lo, h_cnt: dead halo outside is not computed
+        check(lib.oai_conv3d_igemm_region(ptr(src0), c0, ptr(src1), c1, NT, D, H, W, ptr(wpack),
+                                          c_size(wpack.numel()), ptr(bias), cout, int(pointwise), int(relu), ab_format,
+                                          ptr(out), c_ll(ob), c_ll(sn), c_ll(sd), c_ll(sh), c_ll(sw), flags, ptr(reg),
+                                          stream_ptr()), "conv3d_igemm_region")
     return out
 
 

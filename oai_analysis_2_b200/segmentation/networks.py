@@ -156,41 +156,90 @@ class UNet:
         self._packed[key] = P
         return P
 
-    # ------------------------------------------------------------------ forward pieces
-    def _conv(self, P, name, src0, src1=None):
-        L = P[name]
-        return ops.conv3d_igemm(src0, src1, L["w"], L["b"], L["cout"], False, True, self._fmt())
+    # ------------------------------------------------------------------ dead-halo regions
+    @staticmethod
+    def needed_regions(tile_zyx, overlap_zyx):
+        """Output sub-boxes (inclusive lo/hi per z,y,x) the kept tile interior actually depends on, per decoder
+        layer.  The reference computes every layer on the whole tile and crops afterwards
+        (image_transforms.py:497-503); a k3 conv widens the needed box by 1, a k2s2 up-conv halves it."""
+        t, o = np.asarray(tile_zyx), np.asarray(overlap_zyx)
 
-    def _up(self, P, name, src):
+        def box(lo, hi, lvl):
+            return np.maximum(lo, 0), np.minimum(hi, (t >> lvl) - 1)
+
+        def dil(b, k, lvl):
+            return box(b[0] - k, b[1] + k, lvl)
+
+        R = {}
+        n0 = box(o, t - o - 1, 0)
+        R["dc1"], R["dc2"] = n0, dil(n0, 1, 0)
+        need = dil(n0, 2, 0)
+        for up, a, b, lvl in (("dc3", "dc4", "dc5", 1), ("dc6", "dc7", "dc8", 2)):
+            q = box(need[0] // 2, need[1] // 2, lvl)
+            R[up], R[a], R[b] = q, q, dil(q, 1, lvl)
+            need = dil(q, 2, lvl)
+        R["dc9"] = box(need[0] // 2, need[1] // 2, 3)
+        return R
+
+    @staticmethod
+    def _region_arg(box, dims, cout):
+        """(d_lo, d_cnt, h_lo, h_cnt) for the C ABI; the d count is padded when that buys a larger accumulator group."""
+        (lo, hi), D = box, dims[0]
+        cnt = int(hi[0] - lo[0] + 1)
+        cph = cout if cout <= 256 else cout // 2
+        rmax = max(1, min(8, 512 // cph))
+        best = None
+        for c in range(cnt, min(D, cnt + 3) + 1):
+            r = max(k for k in range(1, rmax + 1) if c % k == 0)
+            cost = c + 0.5 * c / r  # MMA work ~ c, activation loads ~ (r + 2) per group of r
+            if best is None or cost < best[0]:
+                best = (cost, c)
+        c = best[1]
+        d_lo = int(max(0, min(lo[0] - (c - cnt) // 2, D - c)))
+        return (d_lo, c, int(lo[1]), int(hi[1] - lo[1] + 1))
+
+    # ------------------------------------------------------------------ forward pieces
+    def _conv(self, P, name, src0, src1=None, box=None):
+        L = P[name]
+        region = None if box is None else self._region_arg(box, L["dims"], L["cout"])
+        return ops.conv3d_igemm(src0, src1, L["w"], L["b"], L["cout"], False, True, self._fmt(), region=region)
+
+    def _up(self, P, name, src, box=None):
         """ConvTranspose3d(k=2, s=2) + ReLU as 8 pointwise GEMMs scattering into the 2x grid."""
         L = P[name]
         NT, D, H, W, _ = src.shape
         co = L["cout"]
         out = torch.empty((NT, 2 * D, 2 * H, 2 * W, co), dtype=src.dtype, device=src.device)
         sW, sH, sD, sN = 2 * co, 4 * W * co, 8 * H * W * co, 8 * D * H * W * co
+        region = None if box is None else self._region_arg(box, L["dims"], co)
         t = 0
         for a in range(2):
             for b in range(2):
                 for c in range(2):
                     base = ((a * 2 * H + b) * 2 * W + c) * co
                     ops.conv3d_igemm(src, None, L["taps"][t], L["b"], co, True, True, self._fmt(), out=out,
-                                     out_view=(base, sN, sD, sH, sW))
+                                     out_view=(base, sN, sD, sH, sW), region=region)
                     t += 1
         return out
 
-    def forward_features(self, P, e0):
-        """networks.py:110-144 from ec1 to dc2 on act16 tensors; e0 is the stem (ec0) output."""
+    def forward_features(self, P, e0, overlap_zyx=(0, 0, 0)):
+        """networks.py:110-144 from ec1 to dc2 on act16 tensors; e0 is the stem (ec0) output.  With a non-zero
+        overlap only the part of each decoder layer the kept interior depends on is computed."""
         fmt = self._fmt()
+        B = self.needed_regions(e0.shape[1:4], overlap_zyx) if any(overlap_zyx) else {}
+        B = {k: B.get(k) for k in ("dc2", "dc3", "dc4", "dc5", "dc6", "dc7", "dc8", "dc9")}
         syn0 = self._conv(P, "ec1", e0)
         del e0
         syn1 = self._conv(P, "ec3", self._conv(P, "ec2", ops.maxpool2(syn0, fmt)))
         syn2 = self._conv(P, "ec5", self._conv(P, "ec4", ops.maxpool2(syn1, fmt)))
         e7 = self._conv(P, "ec7", self._conv(P, "ec6", ops.maxpool2(syn2, fmt)))
-        d7 = self._conv(P, "dc7", self._conv(P, "dc8", self._up(P, "dc9", e7), syn2))
+        d7 = self._conv(P, "dc7", self._conv(P, "dc8", self._up(P, "dc9", e7, B["dc9"]), syn2, B["dc8"]), None,
+                        B["dc7"])
         del e7, syn2
-        d4 = self._conv(P, "dc4", self._conv(P, "dc5", self._up(P, "dc6", d7), syn1))
+        d4 = self._conv(P, "dc4", self._conv(P, "dc5", self._up(P, "dc6", d7, B["dc6"]), syn1, B["dc5"]), None,
+                        B["dc4"])
         del d7, syn1
-        d2 = self._conv(P, "dc2", self._up(P, "dc3", d4), syn0)
+        d2 = self._conv(P, "dc2", self._up(P, "dc3", d4, B["dc3"]), syn0, B["dc2"])
         del d4, syn0
         return d2
 

@@ -81,7 +81,7 @@ class Segmenter3DInPatchClassWise(Segmenter3DInPatch):
         for t0 in range(0, T, nb):
             n = min(nb, T - t0)
             e0 = ops.seg_stem(volume, geom, t0, n, P["ec0"]["w"], P["ec0"]["b"], fmt)
-            d2 = model.forward_features(P, e0)
+            d2 = model.forward_features(P, e0, part.overlap_size)
             model.head(P, d2, out, geom, t0, crop_zyx, 0 if if_output_prob_map else 1)
             del d2
         return out

@@ -46,7 +46,7 @@ def _box(src, n, dp, ch, cw, cc, bh, bw):
     return out.reshape(bh * bw, 64)
 
 
-def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16"):
+def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", region=None):
     """x0/x1: [NT,D,H,W,C] float16 arrays (x1 may be None); wpack: uint8 array; returns float32 [NT,D,H,W,cout]."""
     f16 = np.float16
     NT, D, H, W, c0 = x0.shape
@@ -60,9 +60,11 @@ def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16"):
     w16 = np.frombuffer(wpack.tobytes(), dtype=np.uint16)
     out = np.zeros((NT, D, H, W, cout), dtype=np.float32)
     nkw = 3 if mode == MODE_ROW_SHARED else 1
+    d_lo, d_cnt, h_lo, h_cnt = region if region is not None else (0, D, 0, H)
+    hp_lo, hp_hi = h_lo // TH, (h_lo + h_cnt + TH - 1) // TH
     for n in range(NT):
-        for d0 in range(0, D, R):
-            for h0 in range(0, H, TH):
+        for d0 in range(d_lo, d_lo + d_cnt, R):
+            for h0 in range(hp_lo * TH, hp_hi * TH, TH):
                 for w0 in range(0, W, TW):
                     for nh in range(nhalf):
                         acc = np.zeros((R, 128, cph), dtype=np.float32)
