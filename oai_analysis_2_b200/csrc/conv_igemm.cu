@@ -213,27 +213,61 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int stage = 0, wb = 0;
-      uint32_t aphase = 0, wphase = 0, it = 0;
-      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
-        const UnitInfo ui = decode_unit(p, u);
-        uint32_t touched = 0, signaled = 0;
-        for (int b = 0; b < p.nblk; ++b) {
-          const BlockInfo bi = decode_block(p, b);
-          const int kdhi = bi.kdlo + bi.nkd - 1;
-          const int dlo = max(0, ui.d0 + bi.kdlo - 1);
-          const int dhi = min(p.D - 1, ui.d0 + p.R - 1 + kdhi - 1);
-          mbar_wait(&full_w[wb], wphase, 300 + wb);
+    // The whole warp walks the (warp-uniform) schedule so the compiler keeps descriptors in uniform registers; one
+    // elected lane issues tcgen05.mma / tcgen05.commit.  The issue thread is the critical resource of this kernel
+    // (one MMA per ~100 tensor-pipe cycles), so the steady state is a fully unrolled sequence of descriptor adds.
+    int stage = 0, wb = 0;
+    uint32_t aphase = 0, wphase = 0, it = 0;
+    const uint32_t cout128 = static_cast<uint32_t>(p.cout) * 128u;
+    const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+                             (static_cast<uint64_t>(2) << 61) | (static_cast<uint64_t>(1) << 16);
+    uint32_t idesc_n[4];
+#pragma unroll
+    for (int n = 1; n <= 3; ++n)
+      idesc_n[n] = umma_idesc_f16(128, static_cast<uint32_t>(min(n * p.cout, 256)), p.ab_format);
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
+      const UnitInfo ui = decode_unit(p, u);
+      uint32_t touched = 0, signaled = 0;
+      for (int b = 0; b < p.nblk; ++b) {
+        const BlockInfo bi = decode_block(p, b);
+        const int kdhi = bi.kdlo + bi.nkd - 1;
+        const int dlo = max(0, ui.d0 + bi.kdlo - 1);
+        const int dhi = min(p.D - 1, ui.d0 + p.R - 1 + kdhi - 1);
+        mbar_wait(&full_w[wb], wphase, 300 + wb);
+        const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
+        for (int dp = dlo; dp <= dhi; ++dp) {
+          mbar_wait(&full_a[stage], aphase, 400 + stage);
           tc_fence_after();
-          const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
-          for (int dp = dlo; dp <= dhi; ++dp) {
-            mbar_wait(&full_a[stage], aphase, 400 + stage);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
-            const int a_first = dp - kdhi + 1 - ui.d0;  // accumulator hit by the first (highest-kd) tap
-            const int ti_lo = max(0, -a_first);
-            const int ti_hi = min(bi.nkd - 1, p.R - 1 - a_first);
+          const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
+          const int a_first = dp - kdhi + 1 - ui.d0;  // accumulator hit by the first (highest-kd) tap
+          const int ti_lo = max(0, -a_first);
+          const int ti_hi = min(bi.nkd - 1, p.R - 1 - a_first);
+          const int nt = ti_hi - ti_lo + 1;
+          const uint32_t span = ((1u << nt) - 1u) << (a_first + ti_lo);
+          if ((touched & span) == span && nt * p.cout <= 256 && !p.base_off_mode) {
+            // steady state: every accumulator of the stack already holds a partial sum -> one N = nt*cout MMA per
+            // (kw, k16); descriptors differ from the stage base by compile-time constants only
+            const uint32_t idesc = idesc_n[nt];
+            const uint32_t d_addr = tmem_base + static_cast<uint32_t>((a_first + ti_lo) * p.cout);
+            const uint32_t a_lo = (a_base & 0x3FFFF) >> 4;
+            const uint32_t b_lo = ((w_base + static_cast<uint32_t>(ti_lo) * cout128) & 0x3FFFF) >> 4;
+            const uint32_t b_kw = (static_cast<uint32_t>(bi.nkd) * cout128) >> 4;
+            if (elect_one()) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                if (kw < nkw) {
+#pragma unroll
+                  for (int k16 = 0; k16 < 4; ++k16) {
+                    if (k16 < p.k16_steps)
+                      umma_f16_ss(d_addr, desc_hi | (a_lo + kw * 8 + k16 * 2), desc_hi | (b_lo + kw * b_kw + k16 * 2),
+                                  idesc, 1u);
+                  }
+                }
+              }
+            }
+          } else {
+            // first touch of an accumulator (overwrite instead of accumulate), N > 256 stacks, or the debug
+            // base-offset mode: general grouping
             for (int kw = 0; kw < nkw; ++kw) {
               int ti = ti_lo;
               while (ti <= ti_hi) {
@@ -247,39 +281,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 }
                 const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * p.cout), p.ab_format);
                 const uint32_t a_addr = a_base + static_cast<uint32_t>(kw) * 128u;
-                const uint32_t b_addr = w_base + static_cast<uint32_t>((kw * bi.nkd + ti) * p.cout) * 128u;
+                const uint32_t b_addr = w_base + static_cast<uint32_t>(kw * bi.nkd + ti) * cout128;
                 const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
                 const uint32_t d_addr = tmem_base + static_cast<uint32_t>(a0 * p.cout);
+                if (elect_one()) {
 #pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16) {
-                  if (k16 >= p.k16_steps) break;
-                  const uint64_t adesc = umma_desc_sw128(a_addr + k16 * 32, 1024, boff);
-                  const uint64_t bdesc = umma_desc_sw128(b_addr + k16 * 32, 1024, 0);
-                  umma_f16_ss(d_addr, adesc, bdesc, idesc, (f | (k16 > 0)) ? 1u : 0u);
+                  for (int k16 = 0; k16 < 4; ++k16) {
+                    if (k16 < p.k16_steps) {
+                      const uint64_t adesc = umma_desc_sw128(a_addr + k16 * 32, 1024, boff);
+                      const uint64_t bdesc = umma_desc_sw128(b_addr + k16 * 32, 1024, 0);
+                      umma_f16_ss(d_addr, adesc, bdesc, idesc, (f | (k16 > 0)) ? 1u : 0u);
+                    }
+                  }
                 }
+                __syncwarp();
                 touched |= ((1u << len) - 1u) << a0;
                 ti += len;
               }
             }
-            umma_commit(&empty_a[stage]);
-            if (++stage == p.n_astage) {
-              stage = 0;
-              aphase ^= 1u;
-            }
-            if (b == p.nblk - 1 && a_first >= 0 && a_first < p.R) {
-              umma_commit(&acc_full[a_first]);
-              signaled |= 1u << a_first;
-            }
           }
-          umma_commit(&empty_w[wb]);
-          if (++wb == p.n_wbuf) {
-            wb = 0;
-            wphase ^= 1u;
+          const bool last_block = (b == p.nblk - 1) && a_first >= 0 && a_first < p.R;
+          if (elect_one()) {
+            umma_commit(&empty_a[stage]);
+            if (last_block) umma_commit(&acc_full[a_first]);
+          }
+          __syncwarp();
+          if (last_block) signaled |= 1u << a_first;
+          if (++stage == p.n_astage) {
+            stage = 0;
+            aphase ^= 1u;
           }
         }
+        if (elect_one()) umma_commit(&empty_w[wb]);
+        __syncwarp();
+        if (++wb == p.n_wbuf) {
+          wb = 0;
+          wphase ^= 1u;
+        }
+      }
+      if (elect_one()) {
         for (int a = 0; a < p.R; ++a)
           if (!((signaled >> a) & 1u)) umma_commit(&acc_full[a]);
       }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue

@@ -36,7 +36,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 }
 
 
-constexpr int kStemTW = 32, kStemTH = 4;  // output patch per block (x, y); one d-slice
+constexpr int kStemTW = 128, kStemTH = 4, kStemXS = 4;  // block: 4 rows x 128 x of one d-slice; thread: 4 x-voxels
 
 __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
   extern __shared__ __align__(16) float s_stem[];
@@ -66,43 +66,52 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
     float v = 0.f;  // conv zero padding at the TILE border
     if (lz >= 0 && lz < p.td && ly >= 0 && ly < p.th && lx >= 0 && lx < p.tw) {
       const int gz = reflect_idx(oz + lz, p.VD), gy = reflect_idx(oy + ly, p.VH), gx = reflect_idx(ox + lx, p.VW);
-      v = p.vol[(static_cast<size_t>(gz) * p.VH + gy) * p.VW + gx];
+      v = __ldg(p.vol + (static_cast<size_t>(gz) * p.VH + gy) * p.VW + gx);
     }
     s_in[i] = v;
   }
   __syncthreads();
 
-  const int lx = tid % kStemTW, ly = tid / kStemTW;
+  const int lx = (tid % (kStemTW / kStemXS)) * kStemXS, ly = tid / (kStemTW / kStemXS);
   const int x = x0 + lx, y = y0 + ly;
   if (x >= p.tw || y >= p.th) return;
-  float in[27];
+  float in[9][kStemXS + 2];
 #pragma unroll
   for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) in[(kd * 3 + kh) * 3 + kw] = s_in[(kd * SH + ly + kh) * SW + lx + kw];
+      for (int i = 0; i < kStemXS + 2; ++i) in[kd * 3 + kh][i] = s_in[(kd * SH + ly + kh) * SW + lx + i];
   uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) +
                   ((((static_cast<size_t>(t) * p.td + d) * p.th + y) * p.tw + x) * p.c0);
   for (int c8 = 0; c8 < p.c0; c8 += 8) {
-    float acc[8];
+    float acc[kStemXS][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = s_b[c8 + j];
+    for (int v = 0; v < kStemXS; ++v)
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const float4 wa = *reinterpret_cast<const float4*>(s_w + k * p.c0 + c8);
-      const float4 wb = *reinterpret_cast<const float4*>(s_w + k * p.c0 + c8 + 4);
-      acc[0] = fmaf(in[k], wa.x, acc[0]); acc[1] = fmaf(in[k], wa.y, acc[1]);
-      acc[2] = fmaf(in[k], wa.z, acc[2]); acc[3] = fmaf(in[k], wa.w, acc[3]);
-      acc[4] = fmaf(in[k], wb.x, acc[4]); acc[5] = fmaf(in[k], wb.y, acc[5]);
-      acc[6] = fmaf(in[k], wb.z, acc[6]); acc[7] = fmaf(in[k], wb.w, acc[7]);
+      for (int j = 0; j < 8; ++j) acc[v][j] = s_b[c8 + j];
+#pragma unroll
+    for (int r = 0; r < 9; ++r)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4 wa = *reinterpret_cast<const float4*>(s_w + (r * 3 + kw) * p.c0 + c8);
+        const float4 wb = *reinterpret_cast<const float4*>(s_w + (r * 3 + kw) * p.c0 + c8 + 4);
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int v = 0; v < kStemXS; ++v)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[v][j] = fmaf(in[r][v + kw], wv[j], acc[v][j]);
+      }
+#pragma unroll
+    for (int v = 0; v < kStemXS; ++v) {
+      if (x + v >= p.tw) break;
+      uint4 o;
+      o.x = pack16(fmaxf(acc[v][0], 0.f), fmaxf(acc[v][1], 0.f), p.fmt);
+      o.y = pack16(fmaxf(acc[v][2], 0.f), fmaxf(acc[v][3], 0.f), p.fmt);
+      o.z = pack16(fmaxf(acc[v][4], 0.f), fmaxf(acc[v][5], 0.f), p.fmt);
+      o.w = pack16(fmaxf(acc[v][6], 0.f), fmaxf(acc[v][7], 0.f), p.fmt);
+      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(v) * p.c0 + c8) = o;
     }
-    uint4 o;
-    o.x = pack16(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), p.fmt);
-    o.y = pack16(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f), p.fmt);
-    o.z = pack16(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), p.fmt);
-    o.w = pack16(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f), p.fmt);
-    *reinterpret_cast<uint4*>(dst + c8) = o;
   }
 }
 

@@ -182,8 +182,9 @@ class UNet:
         return R
 
     @staticmethod
-    def _region_arg(box, dims, cout):
-        """(d_lo, d_cnt, h_lo, h_cnt) for the C ABI; the d count is padded when that buys a larger accumulator group."""
+    def _region_arg(box, dims, cout, pointwise=False):
+        """(d_lo, d_cnt, h_lo, h_cnt) for the C ABI; the d count is padded when that buys a larger accumulator group
+        (a group of r output slices loads r + 2 input slices, so small groups are load-bound)."""
         (lo, hi), D = box, dims[0]
         cnt = int(hi[0] - lo[0] + 1)
         cph = cout if cout <= 256 else cout // 2
@@ -191,7 +192,7 @@ class UNet:
         best = None
         for c in range(cnt, min(D, cnt + 3) + 1):
             r = max(k for k in range(1, rmax + 1) if c % k == 0)
-            cost = c + 0.5 * c / r  # MMA work ~ c, activation loads ~ (r + 2) per group of r
+            cost = c if pointwise else c * (1.0 + 2.0 / r)
             if best is None or cost < best[0]:
                 best = (cost, c)
         c = best[1]
@@ -211,7 +212,7 @@ class UNet:
         co = L["cout"]
         out = torch.empty((NT, 2 * D, 2 * H, 2 * W, co), dtype=src.dtype, device=src.device)
         sW, sH, sD, sN = 2 * co, 4 * W * co, 8 * H * W * co, 8 * D * H * W * co
-        region = None if box is None else self._region_arg(box, L["dims"], co)
+        region = None if box is None else self._region_arg(box, L["dims"], co, True)
         t = 0
         for a in range(2):
             for b in range(2):
