@@ -21,16 +21,21 @@ __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.01f * v
 // ------------------------------------------------------------------------------------------------ conv k3
 // Register-tiled direct convolution: a thread produces XS x-adjacent outputs for CO_T output channels, so every
 // weight vector read from shared memory feeds XS FMAs per channel and every input value feeds up to 3*CO_T.
-template <int CO_T, int XS, int STRIDE>
+// KS > 1 splits the input channels of each chunk over KS thread groups (reduced through shared memory at the end):
+// the deep levels have few voxels and hundreds of channels, so the serial chain per thread is what limits them.
+template <int CO_T, int XS, int STRIDE, int KS>
 __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
   constexpr int CI_CHUNK = 8;
   constexpr int NIN = (XS - 1) * STRIDE + 3;
+  constexpr int NV = 128 / KS;
   __shared__ __align__(16) float s_w[CI_CHUNK * 27 * CO_T];
+  __shared__ float s_red[KS > 1 ? (KS - 1) * NV * XS * CO_T : 1];
   const int co0 = blockIdx.y * CO_T;
   const int n = blockIdx.z;
   const int nsx = (p.Wo + XS - 1) / XS;
   const long long nthr = static_cast<long long>(p.Do) * p.Ho * nsx;
-  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int ks = threadIdx.x / NV, lv = threadIdx.x % NV;
+  const long long v = blockIdx.x * static_cast<long long>(NV) + lv;
   const bool active = v < nthr;
   int sx = 0, yo = 0, zo = 0;
   if (active) {
@@ -40,6 +45,8 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
   }
   const int xo0 = sx * XS;
   const int xi0 = xo0 * STRIDE - 1, yi0 = yo * STRIDE - 1, zi0 = zo * STRIDE - 1;
+  const bool vec_ok = (p.Wi & 3) == 0 && (p.in_cstride & 3) == 0 && (p.in_nstride & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
   float acc[XS][CO_T];
 #pragma unroll
   for (int i = 0; i < XS; ++i)
@@ -56,7 +63,7 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
     }
     __syncthreads();
     if (!active) continue;
-    for (int c = 0; c < nci; ++c) {
+    for (int c = ks; c < nci; c += KS) {
       const float* plane = in_n + (ci0 + c) * p.in_cstride;
       const float* wc = s_w + c * 27 * CO_T;
 #pragma unroll
@@ -69,11 +76,27 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
           if (y < 0 || y >= p.Hi) continue;
           const float* row = plane + (static_cast<size_t>(z) * p.Hi + y) * p.Wi;
           float xin[NIN];
+          if (XS * STRIDE % 4 == 0 && vec_ok) {
+            // xi0 + 1 is a multiple of 4: aligned float4 loads for the body, scalars for the two halo samples
+            xin[0] = xi0 >= 0 ? __ldg(row + xi0) : 0.f;
 #pragma unroll
-          for (int i = 0; i < NIN; ++i) {
-            const int x = xi0 + i;
-            float t = (x >= 0 && x < p.Wi) ? __ldg(row + x) : 0.f;
-            xin[i] = p.leaky_in ? leaky(t) : t;
+            for (int i = 0; i < (NIN - 1) / 4; ++i) {
+              const float4 m = (xi0 + 1 + 4 * i < p.Wi) ? __ldg(reinterpret_cast<const float4*>(row + xi0 + 1) + i)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+              xin[1 + 4 * i] = m.x; xin[2 + 4 * i] = m.y; xin[3 + 4 * i] = m.z; xin[4 + 4 * i] = m.w;
+            }
+#pragma unroll
+            for (int i = 1 + 4 * ((NIN - 1) / 4); i < NIN; ++i) xin[i] = (xi0 + i < p.Wi) ? __ldg(row + xi0 + i) : 0.f;
+          } else {
+#pragma unroll
+            for (int i = 0; i < NIN; ++i) {
+              const int x = xi0 + i;
+              xin[i] = (x >= 0 && x < p.Wi) ? __ldg(row + x) : 0.f;
+            }
+          }
+          if (p.leaky_in) {
+#pragma unroll
+            for (int i = 0; i < NIN; ++i) xin[i] = leaky(xin[i]);
           }
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
@@ -89,6 +112,22 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
         }
       }
     }
+  }
+  if (KS > 1) {
+    if (ks > 0) {
+#pragma unroll
+      for (int i = 0; i < XS; ++i)
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) s_red[((ks - 1) * NV + lv) * XS * CO_T + i * CO_T + j] = acc[i][j];
+    }
+    __syncthreads();
+    if (ks > 0) return;
+#pragma unroll
+    for (int k = 1; k < KS; ++k)
+#pragma unroll
+      for (int i = 0; i < XS; ++i)
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[i][j] += s_red[((k - 1) * NV + lv) * XS * CO_T + i * CO_T + j];
   }
   if (!active) return;
   float* out_n = p.out + n * p.out_nstride;
@@ -129,16 +168,19 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
 // A thread produces XP x-adjacent output PAIRS (2*XP outputs) of one (zo, yo) row for CO_T channels.
 // o = 2 i - 1 + k  =>  per axis two taps: k = (o+1)%2 + 2 t, i = (o + 1 - k)/2, t in {0,1}.
 // Along x, output 2j uses (kx=1, ix=j), (kx=3, ix=j-1); output 2j+1 uses (kx=0, ix=j+1), (kx=2, ix=j).
-template <int CO_T, int XP>
+template <int CO_T, int XP, int KS>
 __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
   constexpr int CI_CHUNK = 4;
+  constexpr int NV = 128 / KS;
   __shared__ __align__(16) float s_w[CI_CHUNK * 64 * CO_T];
+  __shared__ float s_red[KS > 1 ? (KS - 1) * NV * 2 * XP * CO_T : 1];
   const int co0 = blockIdx.y * CO_T;
   const int n = blockIdx.z;
   const int Wp = (p.Wo + 1) / 2;
   const int nsx = (Wp + XP - 1) / XP;
   const long long nthr = static_cast<long long>(p.Do) * p.Ho * nsx;
-  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int ks = threadIdx.x / NV, lv = threadIdx.x % NV;
+  const long long v = blockIdx.x * static_cast<long long>(NV) + lv;
   const bool active = v < nthr;
   int sx = 0, yo = 0, zo = 0;
   if (active) {
@@ -147,6 +189,8 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
     zo = static_cast<int>(v / (static_cast<long long>(nsx) * p.Ho));
   }
   const int j0 = sx * XP;
+  const bool vec_ok = (p.Wi & 3) == 0 && (p.in_cstride & 3) == 0 && (p.in_nstride & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
   int kz[2], iz[2], ky[2], iy[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
@@ -171,7 +215,7 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
     }
     __syncthreads();
     if (!active) continue;
-    for (int ci = 0; ci < nci; ++ci) {
+    for (int ci = ks; ci < nci; ci += KS) {
       const float* plane = in_n + (ci0 + ci) * p.in_cstride;
       const float* wc = s_w + ci * 64 * CO_T;
 #pragma unroll
@@ -184,11 +228,21 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
           if (y < 0 || y >= p.Hi) continue;
           const float* row = plane + (static_cast<size_t>(z) * p.Hi + y) * p.Wi;
           float xin[XP + 2];
+          if (XP == 4 && vec_ok) {
+            const float4 m = (j0 < p.Wi) ? __ldg(reinterpret_cast<const float4*>(row + j0))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            xin[0] = j0 > 0 ? __ldg(row + j0 - 1) : 0.f;
+            xin[1] = m.x; xin[2] = m.y; xin[3] = m.z; xin[4] = m.w;
+            xin[XP + 1] = (j0 + 4 < p.Wi) ? __ldg(row + j0 + 4) : 0.f;
+          } else {
 #pragma unroll
-          for (int i = 0; i < XP + 2; ++i) {
-            const int x = j0 - 1 + i;
-            xin[i] = (x >= 0 && x < p.Wi) ? leaky(__ldg(row + x)) : 0.f;
+            for (int i = 0; i < XP + 2; ++i) {
+              const int x = j0 - 1 + i;
+              xin[i] = (x >= 0 && x < p.Wi) ? __ldg(row + x) : 0.f;
+            }
           }
+#pragma unroll
+          for (int i = 0; i < XP + 2; ++i) xin[i] = leaky(xin[i]);
           const float* wk = wc + ((kz[tz] * 4 + ky[ty]) * 4) * CO_T;
           float w0[CO_T], w1[CO_T], w2[CO_T], w3[CO_T];
 #pragma unroll
@@ -207,6 +261,28 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
         }
       }
     }
+  }
+  if (KS > 1) {
+    if (ks > 0) {
+#pragma unroll
+      for (int i = 0; i < XP; ++i)
+#pragma unroll
+        for (int c = 0; c < CO_T; ++c) {
+          s_red[((ks - 1) * NV + lv) * 2 * XP * CO_T + (2 * i) * CO_T + c] = acc0[i][c];
+          s_red[((ks - 1) * NV + lv) * 2 * XP * CO_T + (2 * i + 1) * CO_T + c] = acc1[i][c];
+        }
+    }
+    __syncthreads();
+    if (ks > 0) return;
+#pragma unroll
+    for (int k = 1; k < KS; ++k)
+#pragma unroll
+      for (int i = 0; i < XP; ++i)
+#pragma unroll
+        for (int c = 0; c < CO_T; ++c) {
+          acc0[i][c] += s_red[((k - 1) * NV + lv) * 2 * XP * CO_T + (2 * i) * CO_T + c];
+          acc1[i][c] += s_red[((k - 1) * NV + lv) * 2 * XP * CO_T + (2 * i + 1) * CO_T + c];
+        }
   }
   if (!active) return;
   // residual: F.interpolate(in[:, :cout], scale_factor=2, trilinear, align_corners=False) on the RAW input
@@ -475,34 +551,37 @@ inline unsigned grid_for(long long n, int block, int per_sm) {
 
 }  // namespace
 
-template <int CO_T, int XS>
+template <int CO_T, int XS, int KS>
 static void conv3_dispatch(const Conv3Params& p, cudaStream_t st) {
   const long long nthr = static_cast<long long>(p.Do) * p.Ho * ((p.Wo + XS - 1) / XS);
-  dim3 g(static_cast<unsigned>((nthr + 127) / 128), (p.cout + CO_T - 1) / CO_T, p.N);
-  if (p.stride == 1) conv3_kernel<CO_T, XS, 1><<<g, 128, 0, st>>>(p);
-  else conv3_kernel<CO_T, XS, 2><<<g, 128, 0, st>>>(p);
+  constexpr int NV = 128 / KS;
+  dim3 g(static_cast<unsigned>((nthr + NV - 1) / NV), (p.cout + CO_T - 1) / CO_T, p.N);
+  if (p.stride == 1) conv3_kernel<CO_T, XS, 1, KS><<<g, 128, 0, st>>>(p);
+  else conv3_kernel<CO_T, XS, 2, KS><<<g, 128, 0, st>>>(p);
 }
 
 int conv3_launch(const Conv3Params& p, cudaStream_t st) {
   const long long nvox = static_cast<long long>(p.Do) * p.Ho * p.Wo;
-  if (p.cout <= 4) conv3_dispatch<4, 8>(p, st);              // lastConv: 18 -> 3 at full resolution
-  else if (nvox * ((p.cout + 7) / 8) >= (1 << 18)) conv3_dispatch<8, 4>(p, st);
-  else conv3_dispatch<8, 1>(p, st);                           // deep levels: few voxels, favour parallelism
+  if (p.cout <= 4) conv3_dispatch<4, 8, 1>(p, st);              // lastConv: 18 -> 3 at full resolution
+  else if (nvox * ((p.cout + 7) / 8) >= (1 << 18)) conv3_dispatch<8, 4, 1>(p, st);
+  else if (p.cin >= 32) conv3_dispatch<8, 1, 4>(p, st);          // deep levels: few voxels, many channels
+  else conv3_dispatch<8, 1, 1>(p, st);
   return launched("conv3_kernel");
 }
 
-template <int CO_T, int XP>
+template <int CO_T, int XP, int KS>
 static void convt4_dispatch(const ConvT4Params& p, cudaStream_t st) {
   const int Wp = (p.Wo + 1) / 2;
   const long long nthr = static_cast<long long>(p.Do) * p.Ho * ((Wp + XP - 1) / XP);
-  dim3 g(static_cast<unsigned>((nthr + 127) / 128), (p.cout + CO_T - 1) / CO_T, p.N);
-  convt4_kernel<CO_T, XP><<<g, 128, 0, st>>>(p);
+  constexpr int NV = 128 / KS;
+  dim3 g(static_cast<unsigned>((nthr + NV - 1) / NV), (p.cout + CO_T - 1) / CO_T, p.N);
+  convt4_kernel<CO_T, XP, KS><<<g, 128, 0, st>>>(p);
 }
 
 int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
   const long long nout = static_cast<long long>(p.Do) * p.Ho * p.Wo;
-  if (nout * ((p.cout + 7) / 8) >= (1 << 19)) convt4_dispatch<8, 4>(p, st);
-  else convt4_dispatch<8, 1>(p, st);
+  if (nout * ((p.cout + 7) / 8) >= (1 << 19)) convt4_dispatch<8, 4, 1>(p, st);
+  else convt4_dispatch<8, 1, 4>(p, st);                         // deep levels: split the channel loop 4 ways
   return launched("convt4_kernel");
 }
 
