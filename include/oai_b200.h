@@ -63,6 +63,17 @@ OAI_API int oai_conv3d_igemm_region(const void* src0, int c0, const void* src1, 
                                     int relu, int ab_format, void* out, long long obase, long long osN, long long osD,
                                     long long osH, long long osW, int flags, const int* region, void* stream);
 
+/* nn.ConvTranspose3d(k=2, s=2) [+BN+ReLU folded] (networks.py:56,59,62) in one launch: out[co, 2z+a, 2y+b, 2x+c] =
+ * sum_ci in[ci,z,y,x] * w[co][ci][a][b][c] + bias[co].  Each input M tile is loaded once and multiplied with the 8
+ * sub-filters stacked along N; the epilogue scatters every tap into the 2x grid.  src: act16 [NT,D,H,W,cin];
+ * out: act16 [NT,2D,2H,2W,cout]; w for the packer: float32 [cout][cin][2][2][2] (conv orientation);
+ * region (may be NULL) = {d_lo, d_cnt, h_lo, h_cnt} on the INPUT grid. */
+OAI_API int oai_pack_convt2_weights(const float* w, int cout, int cin, int D, int H, int W, int ab_format, void* dst,
+                                    size_t dst_bytes);
+OAI_API int oai_convt2_igemm(const void* src, int cin, int NT, int D, int H, int W, const void* wpack,
+                             size_t wpack_bytes, const float* bias, int cout, int relu, int ab_format, void* out,
+                             const int* region, void* stream);
+
 /* The last decoder layer fused with the network head and the assembler: dc1 = ConvTranspose3d(64->64,k3,s1,p1)+BN+ReLU
  * (networks.py:64) feeding dc0 = Conv3d(64->ncls,k1) (networks.py:66,148), torch.sigmoid (segmenter.py:121)
  * [out_mode 1: ">0.5", segmenter.py:123-124; 2: raw logits] and Partition.assemble's crop-and-place with the zeroed
@@ -75,7 +86,8 @@ OAI_API int oai_conv3d_igemm_head(const void* src0, int c0, const void* src1, in
                                   void* stream);
 
 /* Geometry the kernel will use for (D,H,W,cin,cout,pointwise): fills plan[8] =
- * {mode, kd_per_block, R, nhalf, cout_per_half, nblk, wblock_bytes, nchunks}.  Pure host arithmetic (no GPU). */
+ * {mode, kd_per_block (tap groups when pointwise == 2), R, nhalf, cout_per_half, nblk, wblock_bytes, nchunks}.
+ * pointwise: 0 = 3x3x3, 1 = 1x1x1, 2 = ConvTranspose3d(k2,s2).  Pure host arithmetic (no GPU). */
 OAI_API int oai_conv3d_igemm_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int flags, int* plan);
 
 /* Pack float32 conv weights [cout][cin][3][3][3] (or [cout][cin] when pointwise) into the pre-swizzled

@@ -22,7 +22,7 @@ constexpr int kFlagForceKd1 = 4;
 constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8 - 2112;  // 227 KB minus alignment slack, barriers, fused-head weights
 
 struct Plan {
-  int mode, kd_per_block, R, nhalf, cph, nblk, nchunk0, nchunk1, k16, TW, TH, n_wbuf, n_astage;
+  int mode, kd_per_block, R, Rd, up_groups, nhalf, cph, nblk, nchunk0, nchunk1, k16, TW, TH, n_wbuf, n_astage;
   uint32_t wblock_bytes, astage_bytes, astage_stride;
 };
 
@@ -42,11 +42,23 @@ int make_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int 
   for (int r = 1; r <= 8; ++r)
     if (d_cnt % r == 0 && r * pl->cph <= 512) R = r;
   pl->R = R;
+  pl->Rd = R;
+  pl->up_groups = 1;
   pl->nchunk0 = (c0 + 63) / 64;
   pl->nchunk1 = (c1 + 63) / 64;
   pl->k16 = (c1 == 0 && c0 <= 32) ? (c0 <= 16 ? 1 : 2) : 4;
   const int nch = pl->nchunk0 + pl->nchunk1;
-  if (pointwise) {
+  if (pointwise == 2) {
+    // ConvTranspose3d(k2,s2): the unit's accumulators are taps of one M tile
+    pl->mode = kModeUp2;
+    pl->kd_per_block = 1;
+    pl->R = 512 / pl->cph < 8 ? 512 / pl->cph : 8;
+    pl->Rd = 1;
+    pl->up_groups = 8 / pl->R;
+    pl->wblock_bytes = pl->R * pl->cph * 128;
+    pl->nblk = nch;
+    pl->n_wbuf = 2;
+  } else if (pointwise) {
     pl->mode = kModePointwise;
     pl->kd_per_block = 1;
     pl->wblock_bytes = pl->cph * 128;
@@ -160,7 +172,7 @@ extern "C" int oai_conv3d_igemm_plan(int D, int H, int W, int c0, int c1, int co
   Plan pl;
   if (make_plan(D, H, W, c0, c1, cout, pointwise, flags, &pl)) return 1;
   plan[0] = pl.mode;
-  plan[1] = pl.kd_per_block;
+  plan[1] = pl.mode == kModeUp2 ? pl.up_groups : pl.kd_per_block;
   plan[2] = pl.R;
   plan[3] = pl.nhalf;
   plan[4] = pl.cph;
@@ -299,7 +311,7 @@ static int conv_common(const void* src0, int c0, const void* src1, int c1, int N
   OAI_REQUIRE(src0 && wpack && bias, "conv: null pointer");
   OAI_REQUIRE(!head || (pl.cph == 64 && pl.nhalf == 1), "conv head: the fused head needs a 64-channel layer");
   OAI_REQUIRE((c1 == 0) == (src1 == nullptr), "conv: src1/c1 mismatch");
-  const size_t need = static_cast<size_t>(pl.nhalf) * pl.nblk * pl.wblock_bytes;
+  const size_t need = static_cast<size_t>(pl.nhalf) * pl.up_groups * pl.nblk * pl.wblock_bytes;
   OAI_REQUIRE(wpack_bytes == need, "conv: packed weights are %zu bytes, geometry needs %zu", wpack_bytes, need);
   OAI_REQUIRE(obase % 8 == 0 && osN % 8 == 0 && osD % 8 == 0 && osH % 8 == 0 && osW % 8 == 0,
               "conv: output strides must keep 16-byte alignment");
@@ -320,9 +332,15 @@ static int conv_common(const void* src0, int c0, const void* src1, int c1, int N
   p.out = out;
   p.obase = obase; p.osN = osN; p.osD = osD; p.osH = osH; p.osW = osW;
   p.d_lo = d_lo; p.d_cnt = d_cnt; p.hp_lo = hp_lo; p.hp_cnt = hp_cnt;
-  p.nunits = NT * (d_cnt / pl.R) * (hp_cnt * (W / pl.TW)) * pl.nhalf;
+  p.Rd = pl.Rd; p.up_groups = pl.up_groups;
+  p.nunits = NT * (d_cnt / pl.Rd) * (hp_cnt * (W / pl.TW)) * pl.up_groups * pl.nhalf;
+  if (pl.mode == kModeUp2) {
+    for (int t = 0; t < 8; ++t)
+      p.tap_off[t] = ((static_cast<long long>(t >> 2) * 2 * H + ((t >> 1) & 1)) * 2 * W + (t & 1)) * cout;
+  }
   if (head) p.head = *head;
 
+  OAI_REQUIRE(pl.mode != kModeUp2 || (c1 == 0 && !head), "conv: up2 mode takes one source and no fused head");
   const int bw = pl.mode == kModeRowShared ? 130 : pl.TW;
   const int bh = pl.TH;
   CUtensorMap tm0, tm1;
@@ -376,4 +394,45 @@ extern "C" int oai_profile_end(double* conv_ms, long long* conv_launches, double
   if (conv_exec_flops) *conv_exec_flops = xfl;
   g_prof_used = 0;
   return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------- ConvTranspose3d k2 s2
+extern "C" int oai_pack_convt2_weights(const float* w, int cout, int cin, int D, int H, int W, int ab_format,
+                                       void* dst, size_t dst_bytes) {
+  Plan pl;
+  if (make_plan(D, H, W, cin, 0, cout, 2, 0, &pl)) return 1;
+  const size_t need = static_cast<size_t>(pl.nhalf) * pl.up_groups * pl.nblk * pl.wblock_bytes;
+  OAI_REQUIRE(dst_bytes >= need, "pack up2: dst holds %zu bytes, need %zu", dst_bytes, need);
+  uint8_t* out = static_cast<uint8_t*>(dst);
+  memset(out, 0, need);
+  for (int nh = 0; nh < pl.nhalf; ++nh)
+    for (int tg = 0; tg < pl.up_groups; ++tg)
+      for (int b = 0; b < pl.nblk; ++b) {
+        uint8_t* blk = out + ((static_cast<size_t>(nh) * pl.up_groups + tg) * pl.nblk + b) * pl.wblock_bytes;
+        for (int ti = 0; ti < pl.R; ++ti) {
+          const int tap = tg * pl.R + ti;
+          for (int co = 0; co < pl.cph; ++co) {
+            const int r = ti * pl.cph + co;
+            const float* wrow = w + static_cast<size_t>(nh * pl.cph + co) * cin * 8;
+            for (int j = 0; j < 64; ++j) {
+              const int ci = b * 64 + j;
+              if (ci >= cin) break;
+              const uint16_t h = to16(wrow[static_cast<size_t>(ci) * 8 + tap], ab_format);
+              const size_t off = static_cast<size_t>(r) * 128 + (((j >> 3) ^ (r & 7)) << 4) + (j & 7) * 2;
+              memcpy(blk + off, &h, 2);
+            }
+          }
+        }
+      }
+  return 0;
+}
+
+extern "C" int oai_convt2_igemm(const void* src, int cin, int NT, int D, int H, int W, const void* wpack,
+                                size_t wpack_bytes, const float* bias, int cout, int relu, int ab_format, void* out,
+                                const int* region, void* stream) {
+  OAI_REQUIRE(out != nullptr, "convt2: null output");
+  const long long c = cout;
+  return conv_common(src, cin, nullptr, 0, NT, D, H, W, wpack, wpack_bytes, bias, cout, 2, relu, ab_format, out, 0,
+                     8ll * D * H * W * c, 8ll * H * W * c, 4ll * W * c, 2 * c, 0, nullptr, region, stream);
 }

@@ -32,6 +32,7 @@ constexpr int kTmemCols = 512;
 
 struct BlockInfo {
   int c, kh, kw, kdlo, nkd;
+  int ns;  // taps stacked along N in this block's weight rows (== nkd except kModeUp2)
 };
 
 __device__ __forceinline__ BlockInfo decode_block(const ConvIgemmParams& p, int b) {
@@ -65,22 +66,26 @@ __device__ __forceinline__ BlockInfo decode_block(const ConvIgemmParams& p, int 
     bi.kdlo = 1;
     bi.nkd = 1;
   }
+  bi.ns = (p.mode == kModeUp2) ? p.R : bi.nkd;
   return bi;
 }
 
 struct UnitInfo {
   int n, d0, h0, w0, nh;
+  int tg;  // kModeUp2: tap group
 };
 
 __device__ __forceinline__ UnitInfo decode_unit(const ConvIgemmParams& p, int u) {
   UnitInfo ui;
   const int npw = p.W / p.TW;
-  const int np = npw * p.hp_cnt, ndg = p.d_cnt / p.R;
+  const int np = npw * p.hp_cnt, ndg = p.d_cnt / p.Rd;
   ui.nh = u % p.nhalf;
   u /= p.nhalf;
+  ui.tg = u % p.up_groups;
+  u /= p.up_groups;
   const int patch = u % np;
   u /= np;
-  ui.d0 = p.d_lo + (u % ndg) * p.R;
+  ui.d0 = p.d_lo + (u % ndg) * p.Rd;
   ui.n = u / ndg;
   ui.h0 = (p.hp_lo + patch / npw) * p.TH;
   ui.w0 = (patch % npw) * p.TW;
@@ -176,7 +181,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           const int cc = (src0 ? bi.c : bi.c - p.nchunk0) * 64;
           const int kdhi = bi.kdlo + bi.nkd - 1;
           const int dlo = max(0, ui.d0 + bi.kdlo - 1);
-          const int dhi = min(p.D - 1, ui.d0 + p.R - 1 + kdhi - 1);
+          const int dhi = min(p.D - 1, ui.d0 + p.Rd - 1 + kdhi - 1);
           const int cw = (p.mode == kModeRowShared) ? ui.w0 - 1 : ui.w0 + bi.kw - 1;
           const int ch = ui.h0 + bi.kh - 1;
           for (int dp = dlo; dp <= dhi; ++dp) {
@@ -198,7 +203,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
         const UnitInfo ui = decode_unit(p, u);
-        const uint8_t* src = p.wpack + static_cast<size_t>(ui.nh) * p.nblk * p.wblock_bytes;
+        const uint8_t* src = p.wpack + static_cast<size_t>(ui.nh * p.up_groups + ui.tg) * p.nblk * p.wblock_bytes;
         for (int b = 0; b < p.nblk; ++b) {
           mbar_wait(&empty_w[wb], phase ^ 1u, 200 + wb);
           mbar_arrive_expect_tx(&full_w[wb], p.wblock_bytes);
@@ -221,10 +226,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     const uint32_t cout128 = static_cast<uint32_t>(p.cout) * 128u;
     const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
                              (static_cast<uint64_t>(2) << 61) | (static_cast<uint64_t>(1) << 16);
-    uint32_t idesc_n[4];
-#pragma unroll
-    for (int n = 1; n <= 3; ++n)
-      idesc_n[n] = umma_idesc_f16(128, static_cast<uint32_t>(min(n * p.cout, 256)), p.ab_format);
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
       const UnitInfo ui = decode_unit(p, u);
       uint32_t touched = 0, signaled = 0;
@@ -232,39 +233,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         const BlockInfo bi = decode_block(p, b);
         const int kdhi = bi.kdlo + bi.nkd - 1;
         const int dlo = max(0, ui.d0 + bi.kdlo - 1);
-        const int dhi = min(p.D - 1, ui.d0 + p.R - 1 + kdhi - 1);
+        const int dhi = min(p.D - 1, ui.d0 + p.Rd - 1 + kdhi - 1);
         mbar_wait(&full_w[wb], wphase, 300 + wb);
         const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
         for (int dp = dlo; dp <= dhi; ++dp) {
           mbar_wait(&full_a[stage], aphase, 400 + stage);
           tc_fence_after();
           const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
-          const int a_first = dp - kdhi + 1 - ui.d0;  // accumulator hit by the first (highest-kd) tap
+          // accumulator hit by the first stacked tap (highest kd; tap 0 of the group for kModeUp2)
+          const int a_first = (p.mode == kModeUp2) ? 0 : dp - kdhi + 1 - ui.d0;
           const int ti_lo = max(0, -a_first);
-          const int ti_hi = min(bi.nkd - 1, p.R - 1 - a_first);
+          const int ti_hi = min(bi.ns - 1, p.R - 1 - a_first);
           const int nt = ti_hi - ti_lo + 1;
           const uint32_t span = ((1u << nt) - 1u) << (a_first + ti_lo);
-          if ((touched & span) == span && nt * p.cout <= 256 && !p.base_off_mode) {
-            // steady state: every accumulator of the stack already holds a partial sum -> one N = nt*cout MMA per
-            // (kw, k16); descriptors differ from the stage base by compile-time constants only
-            const uint32_t idesc = idesc_n[nt];
-            const uint32_t d_addr = tmem_base + static_cast<uint32_t>((a_first + ti_lo) * p.cout);
+          if ((touched & span) == span && !p.base_off_mode) {
+            // steady state: every accumulator of the stack already holds a partial sum -> MMAs of N = (up to
+            // 256/cout taps)*cout per (kw, k16); descriptors differ from the stage base by constants only
+            const int per = max(1, 256 / p.cout);
             const uint32_t a_lo = (a_base & 0x3FFFF) >> 4;
-            const uint32_t b_lo = ((w_base + static_cast<uint32_t>(ti_lo) * cout128) & 0x3FFFF) >> 4;
-            const uint32_t b_kw = (static_cast<uint32_t>(bi.nkd) * cout128) >> 4;
-            if (elect_one()) {
+            const uint32_t b_kw = (static_cast<uint32_t>(bi.ns) * cout128) >> 4;
+            const bool leader = elect_one();
+            for (int g0 = 0; g0 < nt; g0 += per) {
+              const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(min(per, nt - g0) * p.cout), p.ab_format);
+              const uint32_t d_addr = tmem_base + static_cast<uint32_t>((a_first + ti_lo + g0) * p.cout);
+              const uint32_t b_lo = ((w_base + static_cast<uint32_t>(ti_lo + g0) * cout128) & 0x3FFFF) >> 4;
+              if (leader) {
 #pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-                if (kw < nkw) {
+                for (int kw = 0; kw < 3; ++kw) {
+                  if (kw < nkw) {
 #pragma unroll
-                  for (int k16 = 0; k16 < 4; ++k16) {
-                    if (k16 < p.k16_steps)
-                      umma_f16_ss(d_addr, desc_hi | (a_lo + kw * 8 + k16 * 2), desc_hi | (b_lo + kw * b_kw + k16 * 2),
-                                  idesc, 1u);
+                    for (int k16 = 0; k16 < 4; ++k16) {
+                      if (k16 < p.k16_steps)
+                        umma_f16_ss(d_addr, desc_hi | (a_lo + kw * 8 + k16 * 2),
+                                    desc_hi | (b_lo + kw * b_kw + k16 * 2), idesc, 1u);
+                    }
                   }
                 }
               }
             }
+            __syncwarp();
           } else {
             // first touch of an accumulator (overwrite instead of accumulate), N > 256 stacks, or the debug
             // base-offset mode: general grouping
@@ -281,7 +288,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 }
                 const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * p.cout), p.ab_format);
                 const uint32_t a_addr = a_base + static_cast<uint32_t>(kw) * 128u;
-                const uint32_t b_addr = w_base + static_cast<uint32_t>(kw * bi.nkd + ti) * cout128;
+                const uint32_t b_addr = w_base + static_cast<uint32_t>(kw * bi.ns + ti) * cout128;
                 const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
                 const uint32_t d_addr = tmem_base + static_cast<uint32_t>(a0 * p.cout);
                 if (elect_one()) {
@@ -387,7 +394,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             }
           }
         } else {
-        uint16_t* dst = out + off0 + (ui.d0 + a) * p.osD;
+        uint16_t* dst = (p.mode == kModeUp2) ? out + off0 + ui.d0 * p.osD + p.tap_off[ui.tg * p.R + a]
+                                             : out + off0 + (ui.d0 + a) * p.osD;
         for (int j = 0; j < p.cout / 32; ++j) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a * p.cout + j * 32),

@@ -9,7 +9,9 @@ namespace oai {
 enum ConvMode : int {
   kModeRowShared = 0,  // 3x3x3, M tile = one full 128-wide row; w halo loaded once, kw taps = smem row shifts
   kModePerTap = 1,     // 3x3x3, one TMA box per (kh,kw) shift; M tile = TH x TW patch
-  kModePointwise = 2,  // 1x1x1 (also each of the 8 sub-filters of a k2 s2 transposed conv)
+  kModePointwise = 2,  // 1x1x1
+  kModeUp2 = 3,        // ConvTranspose3d(k=2, s=2): the accumulators of a unit are sub-filters (taps) of ONE input
+                       // M tile, stacked along N; the epilogue scatters each tap into the 2x output grid
 };
 
 // Optional fused epilogue of the last decoder layer: dc0 (1x1x1, C->ncls) + sigmoid (+ >0.5) + Partition.assemble
@@ -30,6 +32,9 @@ struct ConvIgemmParams {
   int NT, D, H, W;
   int TW, TH;       // M tile = TH x TW voxels in one d-slice (TH*TW == 128)
   int R;            // accumulators per unit = consecutive output d-slices (R*cout <= 512, d_cnt % R == 0)
+  int Rd;           // d-slices per unit (== R except kModeUp2, where R counts taps and Rd == 1)
+  int up_groups;    // kModeUp2: tap groups per M tile (8 / R)
+  long long tap_off[8];  // kModeUp2: output element offset of tap (a,b,c) = ((a*2H + b)*2W + c)*cout
   int d_lo, d_cnt;  // output region computed: slices [d_lo, d_lo+d_cnt) ...
   int hp_lo, hp_cnt;  // ... and patch rows [hp_lo, hp_lo+hp_cnt) (units of TH voxel rows); the rest is dead halo
   int cout;         // N per accumulator (multiple of 16, <= 256)

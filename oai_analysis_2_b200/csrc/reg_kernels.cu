@@ -25,7 +25,7 @@ __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.01f * v
 // the deep levels have few voxels and hundreds of channels, so the serial chain per thread is what limits them.
 template <int CO_T, int XS, int STRIDE, int KS>
 __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
-  constexpr int CI_CHUNK = 8;
+  constexpr int CI_CHUNK = KS > 1 ? 16 : 8;
   constexpr int NIN = (XS - 1) * STRIDE + 3;
   constexpr int NV = 128 / KS;
   __shared__ __align__(16) float s_w[CI_CHUNK * 27 * CO_T];
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
 // Along x, output 2j uses (kx=1, ix=j), (kx=3, ix=j-1); output 2j+1 uses (kx=0, ix=j+1), (kx=2, ix=j).
 template <int CO_T, int XP, int KS>
 __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
-  constexpr int CI_CHUNK = 4;
+  constexpr int CI_CHUNK = KS > 1 ? 16 : 4;
   constexpr int NV = 128 / KS;
   __shared__ __align__(16) float s_w[CI_CHUNK * 64 * CO_T];
   __shared__ float s_red[KS > 1 ? (KS - 1) * NV * 2 * XP * CO_T : 1];
@@ -563,7 +563,7 @@ static void conv3_dispatch(const Conv3Params& p, cudaStream_t st) {
 int conv3_launch(const Conv3Params& p, cudaStream_t st) {
   const long long nvox = static_cast<long long>(p.Do) * p.Ho * p.Wo;
   if (p.cout <= 4) conv3_dispatch<4, 8, 1>(p, st);              // lastConv: 18 -> 3 at full resolution
-  else if (nvox * ((p.cout + 7) / 8) >= (1 << 18)) conv3_dispatch<8, 4, 1>(p, st);
+  else if (nvox * ((p.cout + 7) / 8) >= (1 << 16)) conv3_dispatch<8, 4, 1>(p, st);
   else if (p.cin >= 32) conv3_dispatch<8, 1, 4>(p, st);          // deep levels: few voxels, many channels
   else conv3_dispatch<8, 1, 1>(p, st);
   return launched("conv3_kernel");
@@ -580,7 +580,7 @@ static void convt4_dispatch(const ConvT4Params& p, cudaStream_t st) {
 
 int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
   const long long nout = static_cast<long long>(p.Do) * p.Ho * p.Wo;
-  if (nout * ((p.cout + 7) / 8) >= (1 << 19)) convt4_dispatch<8, 4, 1>(p, st);
+  if (nout * ((p.cout + 7) / 8) >= (1 << 17)) convt4_dispatch<8, 4, 1>(p, st);
   else convt4_dispatch<8, 1, 4>(p, st);                         // deep levels: split the channel loop 4 ways
   return launched("convt4_kernel");
 }

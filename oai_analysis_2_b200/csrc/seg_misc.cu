@@ -36,13 +36,16 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 }
 
 
-constexpr int kStemTW = 128, kStemTH = 4, kStemXS = 4;  // block: 4 rows x 128 x of one d-slice; thread: 4 x-voxels
+constexpr int kStemTW = 128, kStemTH = 4, kStemXS = 4;  // block: 4 rows x 128 x, walks all d-slices; thread: 4 x-voxels
 
+// One block owns a (4-row x 128-x) column of a tile and walks its d-slices with a 3-slice rolling window in shared
+// memory, so every input sample is fetched from L2 once per block column (1.5x halo) instead of 4.6x.
 __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
   extern __shared__ __align__(16) float s_stem[];
+  constexpr int SW = kStemTW + 2, SH = kStemTH + 2;
   float* s_w = s_stem;                 // 27*c0
   float* s_b = s_w + 27 * p.c0;        // c0
-  float* s_in = s_b + p.c0;            // [3][kStemTH+2][kStemTW+2]
+  float* s_in = s_b + p.c0;            // [3 slots][SH][SW]
   const int tid = threadIdx.x;
   for (int i = tid; i < 27 * p.c0; i += blockDim.x) s_w[i] = p.w[i];
   for (int i = tid; i < p.c0; i += blockDim.x) s_b[i] = p.b[i];
@@ -51,7 +54,6 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
   int blk = blockIdx.x;
   const int bx = blk % nbx; blk /= nbx;
   const int by = blk % nby; blk /= nby;
-  const int d = blk % p.td; blk /= p.td;
   const int t = blk;  // tile within batch
   const int tile = p.tile0 + t;
   const int tk = tile % p.gw, tj = (tile / p.gw) % p.gh, ti = tile / (p.gw * p.gh);
@@ -59,65 +61,82 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
   const int oz = ti * p.ed - p.od, oy = tj * p.eh - p.oh, ox = tk * p.ew - p.ow;
   const int x0 = bx * kStemTW, y0 = by * kStemTH;
 
-  constexpr int SW = kStemTW + 2, SH = kStemTH + 2;
-  for (int i = tid; i < 3 * SH * SW; i += blockDim.x) {
-    const int xx = i % SW, yy = (i / SW) % SH, zz = i / (SW * SH);
-    const int lz = d + zz - 1, ly = y0 + yy - 1, lx = x0 + xx - 1;  // tile-local coordinates
-    float v = 0.f;  // conv zero padding at the TILE border
-    if (lz >= 0 && lz < p.td && ly >= 0 && ly < p.th && lx >= 0 && lx < p.tw) {
-      const int gz = reflect_idx(oz + lz, p.VD), gy = reflect_idx(oy + ly, p.VH), gx = reflect_idx(ox + lx, p.VW);
-      v = __ldg(p.vol + (static_cast<size_t>(gz) * p.VH + gy) * p.VW + gx);
+  // slice lz (tile-local; may be -1 or td: conv zero padding at the TILE border) -> slot (lz + 3) % 3
+  auto load_slice = [&](int lz) {
+    float* dst = s_in + ((lz + 3) % 3) * SH * SW;
+    const bool zin = lz >= 0 && lz < p.td;
+    const int gz = zin ? reflect_idx(oz + lz, p.VD) : 0;
+    for (int i = tid; i < SH * SW; i += blockDim.x) {
+      const int xx = i % SW, yy = i / SW;
+      const int ly = y0 + yy - 1, lx = x0 + xx - 1;
+      float v = 0.f;
+      if (zin && ly >= 0 && ly < p.th && lx >= 0 && lx < p.tw) {
+        int gy = oy + ly, gx = ox + lx;
+        if (gy < 0 || gy >= p.VH) gy = reflect_idx(gy, p.VH);
+        if (gx < 0 || gx >= p.VW) gx = reflect_idx(gx, p.VW);
+        v = __ldg(p.vol + (static_cast<size_t>(gz) * p.VH + gy) * p.VW + gx);
+      }
+      dst[i] = v;
     }
-    s_in[i] = v;
-  }
-  __syncthreads();
+  };
+  load_slice(-1);
+  load_slice(0);
 
   const int lx = (tid % (kStemTW / kStemXS)) * kStemXS, ly = tid / (kStemTW / kStemXS);
   const int x = x0 + lx, y = y0 + ly;
-  if (x >= p.tw || y >= p.th) return;
-  float in[9][kStemXS + 2];
+  const bool active = x < p.tw && y < p.th;
+  for (int d = 0; d < p.td; ++d) {
+    load_slice(d + 1);
+    __syncthreads();
+    if (active) {
+      float in[9][kStemXS + 2];
 #pragma unroll
-  for (int kd = 0; kd < 3; ++kd)
+      for (int kd = 0; kd < 3; ++kd) {
+        const float* sl = s_in + ((d + kd + 2) % 3) * SH * SW;  // slice d + kd - 1
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+        for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-      for (int i = 0; i < kStemXS + 2; ++i) in[kd * 3 + kh][i] = s_in[(kd * SH + ly + kh) * SW + lx + i];
-  uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) +
-                  ((((static_cast<size_t>(t) * p.td + d) * p.th + y) * p.tw + x) * p.c0);
-  for (int c8 = 0; c8 < p.c0; c8 += 8) {
-    float acc[kStemXS][8];
-#pragma unroll
-    for (int v = 0; v < kStemXS; ++v)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[v][j] = s_b[c8 + j];
-#pragma unroll
-    for (int r = 0; r < 9; ++r)
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const float4 wa = *reinterpret_cast<const float4*>(s_w + (r * 3 + kw) * p.c0 + c8);
-        const float4 wb = *reinterpret_cast<const float4*>(s_w + (r * 3 + kw) * p.c0 + c8 + 4);
-        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+          for (int i = 0; i < kStemXS + 2; ++i) in[kd * 3 + kh][i] = sl[(ly + kh) * SW + lx + i];
+      }
+      uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) +
+                      ((((static_cast<size_t>(t) * p.td + d) * p.th + y) * p.tw + x) * p.c0);
+      for (int c8 = 0; c8 < p.c0; c8 += 8) {
+        float acc[kStemXS][8];
 #pragma unroll
         for (int v = 0; v < kStemXS; ++v)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[v][j] = fmaf(in[r][v + kw], wv[j], acc[v][j]);
-      }
+          for (int j = 0; j < 8; ++j) acc[v][j] = s_b[c8 + j];
 #pragma unroll
-    for (int v = 0; v < kStemXS; ++v) {
-      if (x + v >= p.tw) break;
-      uint4 o;
-      o.x = pack16(fmaxf(acc[v][0], 0.f), fmaxf(acc[v][1], 0.f), p.fmt);
-      o.y = pack16(fmaxf(acc[v][2], 0.f), fmaxf(acc[v][3], 0.f), p.fmt);
-      o.z = pack16(fmaxf(acc[v][4], 0.f), fmaxf(acc[v][5], 0.f), p.fmt);
-      o.w = pack16(fmaxf(acc[v][6], 0.f), fmaxf(acc[v][7], 0.f), p.fmt);
-      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(v) * p.c0 + c8) = o;
+        for (int r = 0; r < 9; ++r)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float4 wa = *reinterpret_cast<const float4*>(s_w + (r * 3 + kw) * p.c0 + c8);
+            const float4 wb = *reinterpret_cast<const float4*>(s_w + (r * 3 + kw) * p.c0 + c8 + 4);
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int v = 0; v < kStemXS; ++v)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[v][j] = fmaf(in[r][v + kw], wv[j], acc[v][j]);
+          }
+#pragma unroll
+        for (int v = 0; v < kStemXS; ++v) {
+          if (x + v >= p.tw) break;
+          uint4 o;
+          o.x = pack16(fmaxf(acc[v][0], 0.f), fmaxf(acc[v][1], 0.f), p.fmt);
+          o.y = pack16(fmaxf(acc[v][2], 0.f), fmaxf(acc[v][3], 0.f), p.fmt);
+          o.z = pack16(fmaxf(acc[v][4], 0.f), fmaxf(acc[v][5], 0.f), p.fmt);
+          o.w = pack16(fmaxf(acc[v][6], 0.f), fmaxf(acc[v][7], 0.f), p.fmt);
+          *reinterpret_cast<uint4*>(dst + static_cast<size_t>(v) * p.c0 + c8) = o;
+        }
+      }
     }
+    __syncthreads();  // everyone is done with slice d-1 before its slot is overwritten by slice d+2
   }
 }
 
 int stem_launch(const StemParams& p, cudaStream_t st) {
   const int nbx = (p.tw + kStemTW - 1) / kStemTW, nby = (p.th + kStemTH - 1) / kStemTH;
-  const long long blocks = static_cast<long long>(p.ntiles) * p.td * nby * nbx;
+  const long long blocks = static_cast<long long>(p.ntiles) * nby * nbx;
   const size_t smem = (27 * p.c0 + p.c0 + 3 * (kStemTH + 2) * (kStemTW + 2)) * sizeof(float);
   stem_kernel<<<static_cast<unsigned>(blocks), 128, smem, st>>>(p);
   return launched("stem_kernel");

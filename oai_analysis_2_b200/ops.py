@@ -15,7 +15,7 @@ _DT16 = {0: torch.float16, 1: torch.bfloat16}
 
 def conv_plan(D, H, W, c0, c1, cout, pointwise=False, flags=0):
     plan = (c_int * 8)()
-    check(lib.oai_conv3d_igemm_plan(D, H, W, c0, c1, cout, int(pointwise), flags, plan), "conv plan")
+    check(lib.oai_conv3d_igemm_plan(D, H, W, c0, c1, cout, int(pointwise), flags, plan), "conv plan")  # 2 = up2
     keys = ("mode", "kd_per_block", "R", "nhalf", "cout_per_half", "nblk", "wblock_bytes", "nchunks")
     return dict(zip(keys, list(plan)))
 
@@ -202,4 +202,28 @@ def conv3d_igemm_head(src0, wpack, bias, head_w, head_b, out, geom, tile0, crop_
     check(lib.oai_conv3d_igemm_head(ptr(src0), c0, None, 0, NT, D, H, W, ptr(wpack), c_size(wpack.numel()), ptr(bias),
                                     ab_format, ncls, ptr(head_w), ptr(head_b), ptr(out), ptr(dims), ptr(geom), tile0,
                                     ptr(crop), out_mode, flags, stream_ptr()), "conv3d_igemm_head")
+    return out
+
+
+def pack_convt2_weights(w, D, H, W, ab_format=0, device="cuda"):
+    """w: float32 [cout, cin, 2, 2, 2] (conv orientation) of a ConvTranspose3d(k=2, s=2)."""
+    w = np.ascontiguousarray(w.detach().cpu().numpy() if hasattr(w, "detach") else w, dtype=np.float32)
+    cout, cin = w.shape[:2]
+    pl = conv_plan(D, H, W, cin, 0, cout, 2)
+    nbytes = pl["nhalf"] * pl["kd_per_block"] * pl["nblk"] * pl["wblock_bytes"]
+    dst = np.zeros(nbytes, dtype=np.uint8)
+    check(lib.oai_pack_convt2_weights(ptr(w), cout, cin, D, H, W, ab_format, ptr(dst), c_size(nbytes)),
+          "pack convt2 weights")
+    return torch.from_numpy(dst).to(device)
+
+
+def convt2_igemm(src, wpack, bias, cout, relu=True, ab_format=0, region=None, out=None):
+    """ConvTranspose3d(k=2,s=2): src [NT,D,H,W,cin] act16 -> [NT,2D,2H,2W,cout]; region on the input grid."""
+    NT, D, H, W, cin = src.shape
+    assert src.is_contiguous()
+    if out is None:
+        out = torch.empty((NT, 2 * D, 2 * H, 2 * W, cout), dtype=_DT16[ab_format], device=src.device)
+    reg = None if region is None else np.asarray(region, dtype=np.int32)
+    check(lib.oai_convt2_igemm(ptr(src), cin, NT, D, H, W, ptr(wpack), c_size(wpack.numel()), ptr(bias), cout,
+                               int(relu), ab_format, ptr(out), ptr(reg), stream_ptr()), "convt2_igemm")
     return out

@@ -140,13 +140,8 @@ class UNet:
             if name == "ec0":
                 P[name] = dict(w=w.float().reshape(co, 27).t().contiguous().to(dev), b=bias, cout=co)
             elif kind == "t2":
-                taps = []
-                for a in range(2):
-                    for bb in range(2):
-                        for c in range(2):
-                            taps.append(ops.pack_conv_weights(w[:, :, a, bb, c].float(), ci, 0, D, H, W, True, fmt,
-                                                              device=dev))
-                P[name] = dict(taps=taps, b=bias, cout=co, dims=(D, H, W))
+                P[name] = dict(w=ops.pack_convt2_weights(w.float(), D, H, W, fmt, device=dev), b=bias, cout=co,
+                               dims=(D, H, W))
             else:
                 c0 = _SPLIT.get(name, ci)
                 P[name] = dict(w=ops.pack_conv_weights(w.float(), c0, ci - c0, D, H, W, False, fmt, device=dev),
@@ -206,22 +201,10 @@ class UNet:
         return ops.conv3d_igemm(src0, src1, L["w"], L["b"], L["cout"], False, True, self._fmt(), region=region)
 
     def _up(self, P, name, src, box=None):
-        """ConvTranspose3d(k=2, s=2) + ReLU as 8 pointwise GEMMs scattering into the 2x grid."""
+        """ConvTranspose3d(k=2, s=2) + ReLU: one launch, the 8 sub-filters stacked along N, scattered into the 2x grid."""
         L = P[name]
-        NT, D, H, W, _ = src.shape
-        co = L["cout"]
-        out = torch.empty((NT, 2 * D, 2 * H, 2 * W, co), dtype=src.dtype, device=src.device)
-        sW, sH, sD, sN = 2 * co, 4 * W * co, 8 * H * W * co, 8 * D * H * W * co
-        region = None if box is None else self._region_arg(box, L["dims"], co, True)
-        t = 0
-        for a in range(2):
-            for b in range(2):
-                for c in range(2):
-                    base = ((a * 2 * H + b) * 2 * W + c) * co
-                    ops.conv3d_igemm(src, None, L["taps"][t], L["b"], co, True, True, self._fmt(), out=out,
-                                     out_view=(base, sN, sD, sH, sW), region=region)
-                    t += 1
-        return out
+        region = None if box is None else self._region_arg(box, L["dims"], L["cout"], True)
+        return ops.convt2_igemm(src, L["w"], L["b"], L["cout"], True, self._fmt(), region)
 
     def forward_features(self, P, e0, overlap_zyx=(0, 0, 0)):
         """networks.py:110-144 from ec1 to dc2 on act16 tensors; e0 is the stem (ec0) output.  With a non-zero

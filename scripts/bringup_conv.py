@@ -30,6 +30,10 @@ CASES = [
     ("rowshared_bf16", 2, 8, 4, 128, 64, 0, 64, False, 0, 1),
     ("pertap_big_tile_64_64", 4, 32, 128, 128, 64, 0, 64, False, 1, 0),
     ("rowshared_big_tile_64_64", 4, 32, 128, 128, 64, 0, 64, False, 0, 0),
+    ("up2_128_128_w64", 2, 16, 64, 64, 128, 0, 128, 2, 0, 0),
+    ("up2_256_256_w32", 2, 8, 32, 32, 256, 0, 256, 2, 0, 0),
+    ("up2_512_512_w16", 2, 4, 16, 16, 512, 0, 512, 2, 0, 0),
+    ("up2_64_64_w16", 2, 4, 8, 16, 64, 0, 64, 2, 0, 0),
 ]
 
 
@@ -48,6 +52,26 @@ def run_case(i):
     x0 = torch.randn(NT, D, H, W, c0, generator=g, device=dev).to(dt)
     x1 = torch.randn(NT, D, H, W, c1, generator=g, device=dev).to(dt) if c1 else None
     cin = c0 + c1
+    if pw == 2:
+        w = (torch.randn(cout, cin, 2, 2, 2, generator=g, device=dev) / cin ** 0.5).to(dt).float()
+        bias = torch.randn(cout, generator=g, device=dev)
+        wpack = ops.pack_convt2_weights(w, D, H, W, fmt)
+        out = ops.convt2_igemm(x0, wpack, bias, cout, True, fmt)
+        torch.cuda.synchronize()
+        ref = F.relu(F.conv_transpose3d(x0.float().permute(0, 4, 1, 2, 3), w.transpose(0, 1).contiguous(), bias,
+                                        stride=2)).permute(0, 2, 3, 4, 1)
+        err = (out.float() - ref).abs()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.convt2_igemm(x0, wpack, bias, cout, True, fmt, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print("RESULT " + json.dumps(dict(case=name, ok=bool(err.max().item() < 2e-2), max_err=err.max().item(),
+                                          ms=ms, tflops=2.0 * NT * D * H * W * 8 * cout * cin / ms / 1e9,
+                                          plan=ops.conv_plan(D, H, W, cin, 0, cout, 2))), flush=True)
+        return
     if pw:
         w = (torch.randn(cout, cin, generator=g, device=dev) / cin ** 0.5).to(dt).float()
     else:
