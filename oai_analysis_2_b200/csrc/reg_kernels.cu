@@ -218,31 +218,41 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
     for (int ci = ks; ci < nci; ci += KS) {
       const float* plane = in_n + (ci0 + ci) * p.in_cstride;
       const float* wc = s_w + ci * 64 * CO_T;
+      // issue the loads of all four (tz, ty) input rows first (memory-level parallelism), then the FMAs
+      float xin[4][XP + 2];
 #pragma unroll
-      for (int tz = 0; tz < 2; ++tz) {
-        const int z = iz[tz];
-        if (z < 0 || z >= p.Di) continue;
+      for (int tz = 0; tz < 2; ++tz)
 #pragma unroll
         for (int ty = 0; ty < 2; ++ty) {
-          const int y = iy[ty];
-          if (y < 0 || y >= p.Hi) continue;
+          const int z = iz[tz], y = iy[ty];
+          float* xr = xin[tz * 2 + ty];
+          if (z < 0 || z >= p.Di || y < 0 || y >= p.Hi) {
+#pragma unroll
+            for (int i = 0; i < XP + 2; ++i) xr[i] = 0.f;
+            continue;
+          }
           const float* row = plane + (static_cast<size_t>(z) * p.Hi + y) * p.Wi;
-          float xin[XP + 2];
           if (XP == 4 && vec_ok) {
             const float4 m = (j0 < p.Wi) ? __ldg(reinterpret_cast<const float4*>(row + j0))
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-            xin[0] = j0 > 0 ? __ldg(row + j0 - 1) : 0.f;
-            xin[1] = m.x; xin[2] = m.y; xin[3] = m.z; xin[4] = m.w;
-            xin[XP + 1] = (j0 + 4 < p.Wi) ? __ldg(row + j0 + 4) : 0.f;
+            xr[0] = j0 > 0 ? __ldg(row + j0 - 1) : 0.f;
+            xr[1] = m.x; xr[2] = m.y; xr[3] = m.z; xr[4] = m.w;
+            xr[XP + 1] = (j0 + 4 < p.Wi) ? __ldg(row + j0 + 4) : 0.f;
           } else {
 #pragma unroll
             for (int i = 0; i < XP + 2; ++i) {
               const int x = j0 - 1 + i;
-              xin[i] = (x >= 0 && x < p.Wi) ? __ldg(row + x) : 0.f;
+              xr[i] = (x >= 0 && x < p.Wi) ? __ldg(row + x) : 0.f;
             }
           }
+        }
 #pragma unroll
-          for (int i = 0; i < XP + 2; ++i) xin[i] = leaky(xin[i]);
+      for (int tz = 0; tz < 2; ++tz)
+#pragma unroll
+        for (int ty = 0; ty < 2; ++ty) {
+          float* xr = xin[tz * 2 + ty];
+#pragma unroll
+          for (int i = 0; i < XP + 2; ++i) xr[i] = leaky(xr[i]);
           const float* wk = wc + ((kz[tz] * 4 + ky[ty]) * 4) * CO_T;
           float w0[CO_T], w1[CO_T], w2[CO_T], w3[CO_T];
 #pragma unroll
@@ -253,13 +263,12 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
           for (int i = 0; i < XP; ++i)
 #pragma unroll
             for (int c = 0; c < CO_T; ++c) {
-              acc0[i][c] = fmaf(xin[i + 1], w1[c], acc0[i][c]);
-              acc0[i][c] = fmaf(xin[i], w3[c], acc0[i][c]);
-              acc1[i][c] = fmaf(xin[i + 2], w0[c], acc1[i][c]);
-              acc1[i][c] = fmaf(xin[i + 1], w2[c], acc1[i][c]);
+              acc0[i][c] = fmaf(xr[i + 1], w1[c], acc0[i][c]);
+              acc0[i][c] = fmaf(xr[i], w3[c], acc0[i][c]);
+              acc1[i][c] = fmaf(xr[i + 2], w0[c], acc1[i][c]);
+              acc1[i][c] = fmaf(xr[i + 1], w2[c], acc1[i][c]);
             }
         }
-      }
     }
   }
   if (KS > 1) {
@@ -319,6 +328,109 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
         out_n[co * p.out_cstride + ovox] = a * p.bn_scale[co] + p.bn_shift[co];
       }
     }
+  }
+}
+
+// Deep levels of the up path (few voxels, hundreds of channels): one block serves ONE output parity class
+// (zo%2, yo%2, xo%2), which uses only 8 of the 64 taps, so the weight tile staged in shared memory is 8x smaller than
+// in the strip kernel and is amortised over the whole block; the channel loop is split KS ways across thread groups.
+template <int CO_T, int KS>
+__global__ void __launch_bounds__(128) convt4_par_kernel(const ConvT4Params p) {
+  constexpr int CI_CHUNK = 16;
+  constexpr int NV = 128 / KS;
+  __shared__ __align__(16) float s_w[CI_CHUNK * 8 * CO_T];
+  __shared__ float s_red[KS > 1 ? (KS - 1) * NV * CO_T : 1];
+  const int co0 = blockIdx.y * CO_T;
+  const int cls = blockIdx.z & 7, n = blockIdx.z >> 3;
+  const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
+  const int Dq = (p.Do - pz + 1) / 2, Hq = (p.Ho - py + 1) / 2, Wq = (p.Wo - px + 1) / 2;
+  const long long nthr = static_cast<long long>(Dq) * Hq * Wq;
+  const int ks = threadIdx.x / NV, lv = threadIdx.x % NV;
+  const long long v = blockIdx.x * static_cast<long long>(NV) + lv;
+  const bool active = v < nthr;
+  int zo = pz, yo = py, xo = px;
+  if (active) {
+    xo = 2 * static_cast<int>(v % Wq) + px;
+    yo = 2 * static_cast<int>((v / Wq) % Hq) + py;
+    zo = 2 * static_cast<int>(v / (static_cast<long long>(Wq) * Hq)) + pz;
+  }
+  // o = 2 i - 1 + k: taps k = (o+1)%2 + 2t, input i = (o + 1 - k)/2 (block-uniform k, per-thread i)
+  const int kz0 = (pz + 1) & 1, ky0 = (py + 1) & 1, kx0 = (px + 1) & 1;
+  int off[8];
+  bool ok[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int tz = t >> 2, ty = (t >> 1) & 1, tx = t & 1;
+    const int z = (zo + 1 - (kz0 + 2 * tz)) / 2, y = (yo + 1 - (ky0 + 2 * ty)) / 2, x = (xo + 1 - (kx0 + 2 * tx)) / 2;
+    ok[t] = active && z >= 0 && z < p.Di && y >= 0 && y < p.Hi && x >= 0 && x < p.Wi;
+    off[t] = ok[t] ? (z * p.Hi + y) * p.Wi + x : 0;
+  }
+  float acc[CO_T];
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c) acc[c] = 0.f;
+  const float* in_n = p.in + n * p.in_nstride;
+  for (int ci0 = 0; ci0 < p.cin; ci0 += CI_CHUNK) {
+    const int nci = min(CI_CHUNK, p.cin - ci0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nci * 8 * CO_T; i += blockDim.x) {
+      const int c = i % CO_T, t = (i / CO_T) % 8, ci = i / (CO_T * 8);
+      const int k = ((kz0 + 2 * (t >> 2)) * 4 + (ky0 + 2 * ((t >> 1) & 1))) * 4 + (kx0 + 2 * (t & 1));
+      const int co = co0 + c;
+      s_w[i] = co < p.cout ? p.w[(static_cast<size_t>(ci0 + ci) * 64 + k) * p.cout + co] : 0.f;
+    }
+    __syncthreads();
+    for (int ci = ks; ci < nci; ci += KS) {
+      const float* plane = in_n + (ci0 + ci) * p.in_cstride;
+      const float* wc = s_w + ci * 8 * CO_T;
+      float x[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) x[t] = ok[t] ? leaky(__ldg(plane + off[t])) : 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int c = 0; c < CO_T; ++c) acc[c] = fmaf(x[t], wc[t * CO_T + c], acc[c]);
+    }
+  }
+  if (KS > 1) {
+    if (ks > 0) {
+#pragma unroll
+      for (int c = 0; c < CO_T; ++c) s_red[((ks - 1) * NV + lv) * CO_T + c] = acc[c];
+    }
+    __syncthreads();
+    if (ks > 0) return;
+#pragma unroll
+    for (int k = 1; k < KS; ++k)
+#pragma unroll
+      for (int c = 0; c < CO_T; ++c) acc[c] += s_red[((k - 1) * NV + lv) * CO_T + c];
+  }
+  if (!active) return;
+  // residual: F.interpolate(in[:, :cout], scale_factor=2, trilinear, align_corners=False) on the RAW input
+  int i0[3], i1[3];
+  float l[3];
+  {
+    const int o[3] = {zo, yo, xo}, nd[3] = {p.Di, p.Hi, p.Wi};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float s = fmaxf(0.5f * (o[a] + 0.5f) - 0.5f, 0.f);
+      i0[a] = static_cast<int>(s);
+      i1[a] = i0[a] + (i0[a] < nd[a] - 1 ? 1 : 0);
+      l[a] = s - i0[a];
+    }
+  }
+  float* out_n = p.out + n * p.out_nstride;
+  const long long ovox = (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + xo;
+#pragma unroll
+  for (int c = 0; c < CO_T; ++c) {
+    const int co = co0 + c;
+    if (co >= p.cout) break;
+    const float* pl = in_n + co * p.in_cstride;
+    auto at = [&](int z, int y, int x) { return pl[(static_cast<size_t>(z) * p.Hi + y) * p.Wi + x]; };
+    const float lz = l[0], ly = l[1], lx = l[2];
+    const float r = (1.f - lz) * ((1.f - ly) * ((1.f - lx) * at(i0[0], i0[1], i0[2]) + lx * at(i0[0], i0[1], i1[2])) +
+                                  ly * ((1.f - lx) * at(i0[0], i1[1], i0[2]) + lx * at(i0[0], i1[1], i1[2]))) +
+                    lz * ((1.f - ly) * ((1.f - lx) * at(i1[0], i0[1], i0[2]) + lx * at(i1[0], i0[1], i1[2])) +
+                          ly * ((1.f - lx) * at(i1[0], i1[1], i0[2]) + lx * at(i1[0], i1[1], i1[2])));
+    out_n[co * p.out_cstride + ovox] = (acc[c] + p.bias[co] + r) * p.bn_scale[co] + p.bn_shift[co];
   }
 }
 
@@ -580,8 +692,15 @@ static void convt4_dispatch(const ConvT4Params& p, cudaStream_t st) {
 
 int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
   const long long nout = static_cast<long long>(p.Do) * p.Ho * p.Wo;
-  if (nout * ((p.cout + 7) / 8) >= (1 << 17)) convt4_dispatch<8, 4, 1>(p, st);
-  else convt4_dispatch<8, 1, 4>(p, st);                         // deep levels: split the channel loop 4 ways
+  if (nout * ((p.cout + 7) / 8) >= (1 << 17)) {
+    convt4_dispatch<8, 4, 1>(p, st);
+  } else {
+    // deep levels: one block per output parity class, channel loop split 4 ways
+    constexpr int CO_T = 16, KS = 4, NV = 128 / KS;
+    const long long ncls = static_cast<long long>((p.Do + 1) / 2) * ((p.Ho + 1) / 2) * ((p.Wo + 1) / 2);
+    dim3 g(static_cast<unsigned>((ncls + NV - 1) / NV), (p.cout + CO_T - 1) / CO_T, p.N * 8);
+    convt4_par_kernel<CO_T, KS><<<g, 128, 0, st>>>(p);
+  }
   return launched("convt4_kernel");
 }
 

@@ -36,6 +36,9 @@ class UNet:
         self.BN = BN
         self.device = torch.device("cpu")
         self.precision = "fp16"  # fp16 carries TF32's 10-bit mantissa: the reference's own cuDNN default precision
+        # ConvTranspose3d(k2,s2): one stacked-tap launch (True) or 8 pointwise launches (False; measured faster on
+        # B200: the layer is output-bandwidth-bound and the 8 small launches pipeline their epilogues better)
+        self.up2_single_launch = False
         self._sd = self._blank_state_dict()
         self._packed = {}
 
@@ -140,8 +143,13 @@ class UNet:
             if name == "ec0":
                 P[name] = dict(w=w.float().reshape(co, 27).t().contiguous().to(dev), b=bias, cout=co)
             elif kind == "t2":
-                P[name] = dict(w=ops.pack_convt2_weights(w.float(), D, H, W, fmt, device=dev), b=bias, cout=co,
-                               dims=(D, H, W))
+                P[name] = dict(b=bias, cout=co, dims=(D, H, W))
+                if self.up2_single_launch:
+                    P[name]["w"] = ops.pack_convt2_weights(w.float(), D, H, W, fmt, device=dev)
+                else:
+                    P[name]["taps"] = [ops.pack_conv_weights(w[:, :, a, bb, c].float(), ci, 0, D, H, W, True, fmt,
+                                                             device=dev)
+                                       for a in range(2) for bb in range(2) for c in range(2)]
             else:
                 c0 = _SPLIT.get(name, ci)
                 P[name] = dict(w=ops.pack_conv_weights(w.float(), c0, ci - c0, D, H, W, False, fmt, device=dev),
@@ -203,8 +211,18 @@ class UNet:
     def _up(self, P, name, src, box=None):
         """ConvTranspose3d(k=2, s=2) + ReLU: one launch, the 8 sub-filters stacked along N, scattered into the 2x grid."""
         L = P[name]
-        region = None if box is None else self._region_arg(box, L["dims"], L["cout"], True)
-        return ops.convt2_igemm(src, L["w"], L["b"], L["cout"], True, self._fmt(), region)
+        co = L["cout"]
+        region = None if box is None else self._region_arg(box, L["dims"], co, True)
+        if "w" in L:
+            return ops.convt2_igemm(src, L["w"], L["b"], co, True, self._fmt(), region)
+        NT, D, H, W, _ = src.shape
+        out = torch.empty((NT, 2 * D, 2 * H, 2 * W, co), dtype=src.dtype, device=src.device)
+        sW, sH, sD, sN = 2 * co, 4 * W * co, 8 * H * W * co, 8 * D * H * W * co
+        for t in range(8):
+            a, b, c = t >> 2, (t >> 1) & 1, t & 1
+            ops.conv3d_igemm(src, None, L["taps"][t], L["b"], co, True, True, self._fmt(), out=out,
+                             out_view=(((a * 2 * H + b) * 2 * W + c) * co, sN, sD, sH, sW), region=region)
+        return out
 
     def forward_features(self, P, e0, overlap_zyx=(0, 0, 0)):
         """networks.py:110-144 from ec1 to dc2 on act16 tensors; e0 is the stem (ec0) output.  With a non-zero

@@ -122,7 +122,7 @@ def main():
     if a.case is not None:
         run_case(a.case)
         return
-    idx = range(len(CASES)) if a.only is None else [int(s) for s in a.only.split(",")]
+    idx = range(len(CASES)) if a.only is None else [int(s) for s in a.only.split(",") if int(s) < len(CASES)]
     for i in idx:
         t0 = time.time()
         try:

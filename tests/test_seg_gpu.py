@@ -127,12 +127,14 @@ def test_segmenter_matches_reference_golden(name, tmp_path):
     assert np.array_equal(itk_compat.array_from_image(fci), fc)
 
 
-def test_module_forward_matches_oracle_logits():
+@pytest.mark.parametrize("up2_single_launch", [False, True])
+def test_module_forward_matches_oracle_logits(up2_single_launch):
     _cuda()
     from oai_analysis_2_b200.segmentation.networks import UNet
     from oracle.seg_oracle import make_unet_state_dict, unet_forward
     sd = make_unet_state_dict(5, 1, 2, True, True, True)
     net = UNet(1, 2, bias=True, BN=True)
+    net.up2_single_launch = up2_single_launch
     net.load_state_dict(sd, strict=True)
     net.to("cuda").eval()
     x = torch.rand(2, 1, 16, 128, 64, device="cuda")
