@@ -19,6 +19,7 @@ namespace {
 constexpr int kFlagForcePerTap = 1;
 constexpr int kFlagBaseOffFormula = 2;  // debug: descriptor base_offset = (addr>>7)&7 (measured WRONG on B200)
 constexpr int kFlagForceKd1 = 4;
+constexpr int kFlagNoFastPath = 8;
 constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8 - 2112;  // 227 KB minus alignment slack, barriers, fused-head weights
 
 struct Plan {
@@ -327,6 +328,7 @@ static int conv_common(const void* src0, int c0, const void* src1, int c1, int N
   p.astage_bytes = pl.astage_bytes; p.astage_stride = pl.astage_stride;
   p.ab_format = ab_format; p.relu = relu;
   p.base_off_mode = (flags & kFlagBaseOffFormula) ? 1 : 0;
+  p.no_fast_path = (flags & kFlagNoFastPath) ? 1 : 0;
   p.wpack = static_cast<const uint8_t*>(wpack);
   p.bias = bias;
   p.out = out;

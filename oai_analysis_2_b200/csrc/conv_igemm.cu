@@ -246,7 +246,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           const int ti_hi = min(bi.ns - 1, p.R - 1 - a_first);
           const int nt = ti_hi - ti_lo + 1;
           const uint32_t span = ((1u << nt) - 1u) << (a_first + ti_lo);
-          if ((touched & span) == span && !p.base_off_mode) {
+          if ((touched & span) == span && !p.base_off_mode && !p.no_fast_path) {
             // steady state: every accumulator of the stack already holds a partial sum -> MMAs of N = (up to
             // 256/cout taps)*cout per (kw, k16); descriptors differ from the stage base by constants only
             const int per = max(1, 256 / p.cout);

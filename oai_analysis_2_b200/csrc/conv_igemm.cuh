@@ -52,6 +52,7 @@ struct ConvIgemmParams {
   uint32_t astage_stride; // smem stride between A stages (1024-aligned)
   int ab_format;    // 0 fp16, 1 bf16
   int relu;
+  int no_fast_path;   // debug/A-B: always take the general MMA grouping path
   int base_off_mode;  // row-shared mode: 0 (correct on B200: the swizzle XOR uses absolute smem address bits) or
                       // 1 = descriptor base_offset = (addr>>7)&7 (kept for the bring-up test; gives wrong results)
   const uint8_t* wpack;   // [nhalf][nblk][wblock_bytes] pre-swizzled smem images

@@ -9,6 +9,7 @@ from ._lib import c_float, c_int, c_ll, c_size, check, lib, ptr, stream_ptr
 FLAG_FORCE_PER_TAP = 1
 FLAG_BASE_OFF_FORMULA = 2
 FLAG_FORCE_KD1 = 4
+FLAG_NO_FAST_PATH = 8
 
 _DT16 = {0: torch.float16, 1: torch.bfloat16}
 

@@ -33,7 +33,7 @@ LAYERS = {  # name: (D, H, W, c0, c1, cout, pointwise, region)
 }
 
 
-def run(name, NT, iters=5):
+def run(name, NT, iters=5, flags=0):
     D, H, W, c0, c1, cout, pw, region = LAYERS[name]
     dev = "cuda"
     x0 = torch.randn(NT, D, H, W, c0, device=dev).half()
@@ -44,22 +44,26 @@ def run(name, NT, iters=5):
     bias = torch.zeros(cout, device=dev)
     out = torch.empty((NT, D, H, W, cout), dtype=torch.float16, device=dev)
     for _ in range(2):
-        ops.conv3d_igemm(x0, x1, wp, bias, cout, pw, True, 0, out=out, region=region)
+        ops.conv3d_igemm(x0, x1, wp, bias, cout, pw, True, 0, out=out, region=region, flags=flags)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        ops.conv3d_igemm(x0, x1, wp, bias, cout, pw, True, 0, out=out, region=region)
+        ops.conv3d_igemm(x0, x1, wp, bias, cout, pw, True, 0, out=out, region=region, flags=flags)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     frac = 1.0 if region is None else region[1] * region[3] / (D * H)
     fl = 2.0 * NT * D * H * W * cout * cin * (1 if pw else 27)
-    return dict(layer=name, NT=NT, ms=ms, algorithmic_tflops=fl / ms / 1e9, executed_tflops=fl * frac / ms / 1e9,
+    return dict(layer=name, NT=NT, flags=flags, ms=ms, algorithmic_tflops=fl / ms / 1e9, executed_tflops=fl * frac / ms / 1e9,
                 plan=ops.conv_plan(D if region is None else region[1], H, W, c0, c1, cout, pw))
 
 
 if __name__ == "__main__":
     names = sys.argv[1].split(",") if len(sys.argv) > 1 else list(LAYERS)
     NT = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+    flag_list = [int(f) for f in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
     for n in names:
-        print(json.dumps(run(n, NT)), flush=True)
+        for f in flag_list:
+            for rep in range(2):
+                r = run(n, NT, flags=f)
+            print(json.dumps(r)[:150], flush=True)
