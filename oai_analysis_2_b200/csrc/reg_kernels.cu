@@ -467,34 +467,74 @@ __device__ __forceinline__ float tri_sample(const float* __restrict__ v, const T
          tz * ((1.f - ty) * ((1.f - tx) * v100 + tx * v101) + ty * ((1.f - tx) * v110 + tx * v111));
 }
 
-__global__ void __launch_bounds__(256) chain_kernel(const ChainParams p) {
+// A thread carries kChainVX x-adjacent grid points through the whole chain: the independent gather sequences overlap
+// and the map / warped image are written with vector stores.
+constexpr int kChainVX = 4;
+__global__ void __launch_bounds__(256, 2) chain_kernel(const ChainParams p) {
   const long long nvox = static_cast<long long>(p.D) * p.H * p.W;
   const double sz = 1.0 / (p.D - 1), sy = 1.0 / (p.H - 1), sx = 1.0 / (p.W - 1);
-  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvox;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(v % p.W), y = static_cast<int>((v / p.W) % p.H),
-              z = static_cast<int>(v / (static_cast<long long>(p.W) * p.H));
-    float cz = static_cast<float>(z * sz), cy = static_cast<float>(y * sy), cx = static_cast<float>(x * sx);
+  const int nxg = (p.W + kChainVX - 1) / kChainVX;
+  const long long ngroups = static_cast<long long>(p.D) * p.H * nxg;
+  const bool vec = (p.W % kChainVX) == 0 && (!p.phi_out || (reinterpret_cast<uintptr_t>(p.phi_out) & 15) == 0) &&
+                   (!p.img_out || (reinterpret_cast<uintptr_t>(p.img_out) & 15) == 0);
+  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < ngroups;
+       g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x0 = static_cast<int>(g % nxg) * kChainVX;
+    const int y = static_cast<int>((g / nxg) % p.H), z = static_cast<int>(g / (static_cast<long long>(nxg) * p.H));
+    const long long v0 = (static_cast<long long>(z) * p.H + y) * p.W + x0;
+    float cz[kChainVX], cy[kChainVX], cx[kChainVX];
+#pragma unroll
+    for (int i = 0; i < kChainVX; ++i) {
+      cz[i] = static_cast<float>(z * sz);
+      cy[i] = static_cast<float>(y * sy);
+      cx[i] = static_cast<float>(min(x0 + i, p.W - 1) * sx);
+    }
     for (int f = 0; f < p.nfields; ++f) {
       const float* u = p.u[f];
       const size_t plane = static_cast<size_t>(p.ud[f]) * p.uh[f] * p.uw[f];
-      float dz, dy, dx;
       if (f == 0 && p.shortcut_first) {
-        dz = __ldg(u + v); dy = __ldg(u + plane + v); dx = __ldg(u + 2 * plane + v);
+#pragma unroll
+        for (int i = 0; i < kChainVX; ++i) {
+          const long long v = v0 + min(i, p.W - 1 - x0);
+          cz[i] += __ldg(u + v); cy[i] += __ldg(u + plane + v); cx[i] += __ldg(u + 2 * plane + v);
+        }
       } else {
-        const Tri q = tri_setup(cz, cy, cx, p.ud[f], p.uh[f], p.uw[f]);
-        dz = tri_sample(u, q, p.uh[f], p.uw[f]);
-        dy = tri_sample(u + plane, q, p.uh[f], p.uw[f]);
-        dx = tri_sample(u + 2 * plane, q, p.uh[f], p.uw[f]);
+        Tri q[kChainVX];
+#pragma unroll
+        for (int i = 0; i < kChainVX; ++i) q[i] = tri_setup(cz[i], cy[i], cx[i], p.ud[f], p.uh[f], p.uw[f]);
+#pragma unroll
+        for (int i = 0; i < kChainVX; ++i) {
+          const float dz = tri_sample(u, q[i], p.uh[f], p.uw[f]);
+          const float dy = tri_sample(u + plane, q[i], p.uh[f], p.uw[f]);
+          const float dx = tri_sample(u + 2 * plane, q[i], p.uh[f], p.uw[f]);
+          cz[i] += dz; cy[i] += dy; cx[i] += dx;
+        }
       }
-      cz += dz; cy += dy; cx += dx;
     }
-    if (p.phi_out) {
-      p.phi_out[v] = cz; p.phi_out[nvox + v] = cy; p.phi_out[2 * nvox + v] = cx;
-    }
+    float img[kChainVX];
     if (p.img_out) {
-      const Tri q = tri_setup(cz, cy, cx, p.id, p.ih, p.iw);
-      p.img_out[v] = tri_sample(p.img, q, p.ih, p.iw);
+#pragma unroll
+      for (int i = 0; i < kChainVX; ++i) {
+        const Tri q = tri_setup(cz[i], cy[i], cx[i], p.id, p.ih, p.iw);
+        img[i] = tri_sample(p.img, q, p.ih, p.iw);
+      }
+    }
+    if (vec) {
+      if (p.phi_out) {
+        *reinterpret_cast<float4*>(p.phi_out + v0) = make_float4(cz[0], cz[1], cz[2], cz[3]);
+        *reinterpret_cast<float4*>(p.phi_out + nvox + v0) = make_float4(cy[0], cy[1], cy[2], cy[3]);
+        *reinterpret_cast<float4*>(p.phi_out + 2 * nvox + v0) = make_float4(cx[0], cx[1], cx[2], cx[3]);
+      }
+      if (p.img_out) *reinterpret_cast<float4*>(p.img_out + v0) = make_float4(img[0], img[1], img[2], img[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kChainVX; ++i) {
+        if (x0 + i >= p.W) break;
+        if (p.phi_out) {
+          p.phi_out[v0 + i] = cz[i]; p.phi_out[nvox + v0 + i] = cy[i]; p.phi_out[2 * nvox + v0 + i] = cx[i];
+        }
+        if (p.img_out) p.img_out[v0 + i] = img[i];
+      }
     }
   }
 }
@@ -598,45 +638,116 @@ __device__ __forceinline__ void displace(const float* __restrict__ disp, int FD,
   q[0] += d[0]; q[1] += d[1]; q[2] += d[2];
 }
 
+// Trilinear sample set-up for one continuous index (x,y,z) with ITK semantics: clamped neighbours, fp32 weights
+// derived from the fp64 fractional parts.
+struct TriF {
+  int i0[3], i1[3];
+  float t[3];
+};
+__device__ __forceinline__ TriF trif_setup(const double s[3], const int n[3]) {
+  TriF r;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double f = floor(s[a]);
+    r.t[a] = static_cast<float>(s[a] - f);
+    const int b = static_cast<int>(f);
+    r.i0[a] = min(max(b, 0), n[a] - 1);
+    r.i1[a] = min(max(b + 1, 0), n[a] - 1);
+  }
+  return r;
+}
+
+// A thread resamples VX x-adjacent output voxels: the index->lattice affine is evaluated once in fp64 and stepped
+// along x, the VX independent gather chains overlap (memory-level parallelism), and every channel is written with
+// one vector store.  Coordinates stay fp64 (ITK computes in double); interpolation weights / sums are fp32.
+constexpr int kWarpVX = 4;
 __global__ void __launch_bounds__(256) warp_volume_kernel(const WarpVolumeParams p) {
   const long long nvox = static_cast<long long>(p.OD) * p.OH * p.OW;
   const size_t splane = static_cast<size_t>(p.SD) * p.SH * p.SW;
-  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvox;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const double j[3] = {static_cast<double>(v % p.OW), static_cast<double>((v / p.OW) % p.OH),
-                         static_cast<double>(v / (static_cast<long long>(p.OW) * p.OH))};
-    double q[3], s[3];
-    affine_apply(p.out_index_to_net, j, q);
-    displace(p.disp, p.FD, p.FH, p.FW, q);
-    affine_apply(p.net_to_src_index, q, s);
-    const int n[3] = {p.SW, p.SH, p.SD};
-    bool inside = true;
+  const int nxg = (p.OW + kWarpVX - 1) / kWarpVX;
+  const long long ngroups = static_cast<long long>(p.OD) * p.OH * nxg;
+  const int nf[3] = {p.FW, p.FH, p.FD}, ns[3] = {p.SW, p.SH, p.SD};
+  const bool vec_store = (p.OW % kWarpVX) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+  for (long long gidx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; gidx < ngroups;
+       gidx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x0 = static_cast<int>(gidx % nxg) * kWarpVX;
+    const int y = static_cast<int>((gidx / nxg) % p.OH), z = static_cast<int>(gidx / (static_cast<long long>(nxg) * p.OH));
+    const double j0[3] = {static_cast<double>(x0), static_cast<double>(y), static_cast<double>(z)};
+    double qb[3];
+    affine_apply(p.out_index_to_net, j0, qb);
+    // ---- displacement at the VX lattice points
+    double q[kWarpVX][3];
+    TriF tf[kWarpVX];
+    bool fin[kWarpVX];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) inside = inside && s[a] >= -0.5 && s[a] < n[a] - 0.5;
-    if (!inside) {
-      for (int c = 0; c < p.C; ++c) p.out[c * nvox + v] = p.default_value;
-      continue;
-    }
-    int i0[3], i1[3];
-    double t[3];
+    for (int i = 0; i < kWarpVX; ++i) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const double f = floor(s[a]);
-      t[a] = s[a] - f;
-      const int b = static_cast<int>(f);
-      i0[a] = min(max(b, 0), n[a] - 1);
-      i1[a] = min(max(b + 1, 0), n[a] - 1);
+      for (int a = 0; a < 3; ++a) q[i][a] = qb[a] + i * p.out_index_to_net.m[3 * a];
+      fin[i] = true;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) fin[i] = fin[i] && q[i][a] >= -0.5 && q[i][a] < nf[a] - 0.5;
+      tf[i] = trif_setup(q[i], nf);
     }
+    float dsp[kWarpVX][3];
+#pragma unroll
+    for (int i = 0; i < kWarpVX; ++i) {
+      dsp[i][0] = dsp[i][1] = dsp[i][2] = 0.f;
+      if (fin[i]) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int ix = (c & 1) ? tf[i].i1[0] : tf[i].i0[0], iy = (c & 2) ? tf[i].i1[1] : tf[i].i0[1],
+                    iz = (c & 4) ? tf[i].i1[2] : tf[i].i0[2];
+          const float w = ((c & 1) ? tf[i].t[0] : 1.f - tf[i].t[0]) * ((c & 2) ? tf[i].t[1] : 1.f - tf[i].t[1]) *
+                          ((c & 4) ? tf[i].t[2] : 1.f - tf[i].t[2]);
+          const float* e = p.disp + ((static_cast<size_t>(iz) * p.FH + iy) * p.FW + ix) * 3;
+          dsp[i][0] = fmaf(w, __ldg(e), dsp[i][0]);
+          dsp[i][1] = fmaf(w, __ldg(e + 1), dsp[i][1]);
+          dsp[i][2] = fmaf(w, __ldg(e + 2), dsp[i][2]);
+        }
+      }
+    }
+    // ---- source index, inside test, interpolation set-up
+    TriF ts[kWarpVX];
+    bool sin[kWarpVX];
+#pragma unroll
+    for (int i = 0; i < kWarpVX; ++i) {
+      const double qd[3] = {q[i][0] + dsp[i][0], q[i][1] + dsp[i][1], q[i][2] + dsp[i][2]};
+      double sidx[3];
+      affine_apply(p.net_to_src_index, qd, sidx);
+      sin[i] = x0 + i < p.OW;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) sin[i] = sin[i] && sidx[a] >= -0.5 && sidx[a] < ns[a] - 0.5;
+      ts[i] = trif_setup(sidx, ns);
+    }
+    const long long v0 = (static_cast<long long>(z) * p.OH + y) * p.OW + x0;
     for (int c = 0; c < p.C; ++c) {
       const float* src = p.src + c * splane;
-      double acc = 0;
+      float o[kWarpVX];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int ix = (k & 1) ? i1[0] : i0[0], iy = (k & 2) ? i1[1] : i0[1], iz = (k & 4) ? i1[2] : i0[2];
-        const double w = ((k & 1) ? t[0] : 1.0 - t[0]) * ((k & 2) ? t[1] : 1.0 - t[1]) * ((k & 4) ? t[2] : 1.0 - t[2]);
-        acc += w * __ldg(src + (static_cast<size_t>(iz) * p.SH + iy) * p.SW + ix);
+      for (int i = 0; i < kWarpVX; ++i) {
+        float acc = 0.f;
+        if (sin[i]) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int ix = (k & 1) ? ts[i].i1[0] : ts[i].i0[0], iy = (k & 2) ? ts[i].i1[1] : ts[i].i0[1],
+                      iz = (k & 4) ? ts[i].i1[2] : ts[i].i0[2];
+            const float w = ((k & 1) ? ts[i].t[0] : 1.f - ts[i].t[0]) * ((k & 2) ? ts[i].t[1] : 1.f - ts[i].t[1]) *
+                            ((k & 4) ? ts[i].t[2] : 1.f - ts[i].t[2]);
+            acc = fmaf(w, __ldg(src + (static_cast<size_t>(iz) * p.SH + iy) * p.SW + ix), acc);
+          }
+        } else {
+          acc = p.default_value;
+        }
+        o[i] = acc;
       }
-      p.out[c * nvox + v] = static_cast<float>(acc);
+      float* dst = p.out + c * nvox + v0;
+      if (vec_store) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kWarpVX; ++i)
+          if (x0 + i < p.OW) dst[i] = o[i];
+      }
     }
   }
 }
@@ -705,8 +816,8 @@ int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
 }
 
 int chain_launch(const ChainParams& p, cudaStream_t st) {
-  const long long n = static_cast<long long>(p.D) * p.H * p.W;
-  chain_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(p);
+  const long long n = static_cast<long long>(p.D) * p.H * ((p.W + kChainVX - 1) / kChainVX);
+  chain_kernel<<<grid_for(n, 256, 64), 256, 0, st>>>(p);
   return launched("chain_kernel");
 }
 
@@ -730,8 +841,8 @@ int disp_field_launch(const float* phi, int D, int H, int W, float* disp, cudaSt
 }
 
 int warp_volume_launch(const WarpVolumeParams& p, cudaStream_t st) {
-  const long long n = static_cast<long long>(p.OD) * p.OH * p.OW;
-  warp_volume_kernel<<<grid_for(n, 256, 16), 256, 0, st>>>(p);
+  const long long n = static_cast<long long>(p.OD) * p.OH * ((p.OW + kWarpVX - 1) / kWarpVX);
+  warp_volume_kernel<<<grid_for(n, 256, 64), 256, 0, st>>>(p);
   return launched("warp_volume_kernel");
 }
 
