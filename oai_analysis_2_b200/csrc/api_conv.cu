@@ -20,6 +20,7 @@ constexpr int kFlagForcePerTap = 1;
 constexpr int kFlagBaseOffFormula = 2;  // debug: descriptor base_offset = (addr>>7)&7 (measured WRONG on B200)
 constexpr int kFlagForceKd1 = 4;
 constexpr int kFlagNoFastPath = 8;
+constexpr int kFlagWideN = 16;  // A/B: keep 256-wide N tiles for 3x3x3 layers with cout >= 256 (one kd per weight block)
 constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8 - 2112;  // 227 KB minus alignment slack, barriers, fused-head weights
 
 struct Plan {
@@ -34,7 +35,11 @@ int make_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int 
   OAI_REQUIRE(128 % pl->TW == 0 && W % pl->TW == 0, "conv plan: W=%d must divide or be a multiple of 128", W);
   pl->TH = 128 / pl->TW;
   OAI_REQUIRE(H % pl->TH == 0, "conv plan: H=%d not a multiple of the %d-row M tile", H, pl->TH);
-  pl->nhalf = (cout + 255) / 256;
+  // 3x3x3 layers split cout into 128-wide N tiles: each tile then stacks the three kd taps of an input slice (N = 256 +
+  // 128) and keeps R = 4 accumulators, which halves the weight bytes streamed per output compared with a 256-wide
+  // tile limited to R = 2 by the 512 TMEM columns.  Pointwise layers keep 256-wide tiles.
+  const int ntile = (!pointwise && cout > 128 && !(flags & kFlagWideN)) ? 128 : 256;
+  pl->nhalf = (cout + ntile - 1) / ntile;
   OAI_REQUIRE(cout % pl->nhalf == 0, "conv plan: cout=%d not divisible into %d N splits", cout, pl->nhalf);
   pl->cph = cout / pl->nhalf;
   OAI_REQUIRE(pl->cph % 32 == 0, "conv plan: cout per split (%d) must be a multiple of 32", pl->cph);

@@ -10,6 +10,7 @@ FLAG_FORCE_PER_TAP = 1
 FLAG_BASE_OFF_FORMULA = 2
 FLAG_FORCE_KD1 = 4
 FLAG_NO_FAST_PATH = 8
+FLAG_WIDE_N = 16
 
 _DT16 = {0: torch.float16, 1: torch.bfloat16}
 

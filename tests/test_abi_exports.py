@@ -40,6 +40,8 @@ def test_planner_rejects_bad_geometry_with_message():
     pl = ops.conv_plan(32, 128, 128, 128, 64, 64)
     assert pl["mode"] == 0 and pl["R"] == 8 and pl["nblk"] == 9 and pl["wblock_bytes"] == 9 * 64 * 128
     pl = ops.conv_plan(4, 16, 16, 256, 0, 512)
+    assert pl["nhalf"] == 4 and pl["cout_per_half"] == 128 and pl["R"] == 4 and pl["kd_per_block"] == 3
+    pl = ops.conv_plan(4, 16, 16, 256, 0, 512, flags=ops.FLAG_WIDE_N)
     assert pl["nhalf"] == 2 and pl["cout_per_half"] == 256 and pl["R"] == 2 and pl["kd_per_block"] == 1
 
 

@@ -36,8 +36,9 @@ def _case(NT, D, H, W, c0, c1, cout, pointwise, flags=0, seed=0):
     (1, 4, 2, 128, 64, 0, 64, False, 1),     # same geometry forced per-tap
     (2, 4, 4, 64, 64, 0, 128, False, 0),     # per-tap, kd stacked (N=256+128), R=4
     (1, 4, 8, 32, 64, 64, 128, False, 0),    # per-tap two sources
-    (1, 2, 8, 16, 64, 0, 256, False, 0),     # per-tap kd_per_block=1, R=2
-    (1, 2, 8, 16, 64, 0, 512, False, 0),     # two N halves
+    (1, 2, 8, 16, 64, 0, 256, False, 16),    # 256-wide N tile: per-tap kd_per_block=1, R=2
+    (1, 2, 8, 16, 64, 0, 512, False, 16),    # 256-wide, two N halves
+    (1, 4, 8, 16, 64, 0, 256, False, 0),     # default: two 128-wide N tiles, kd stacked, R=4
     (1, 4, 4, 32, 128, 0, 128, True, 0),     # pointwise
     (1, 8, 2, 64, 64, 0, 64, False, 0),      # per-tap cout 64: R=8, N=192 stacks
 ])
