@@ -222,6 +222,9 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_sample(vols_h[0], 1, 0)
         print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm

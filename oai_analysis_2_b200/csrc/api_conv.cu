@@ -21,7 +21,7 @@ constexpr int kFlagBaseOffFormula = 2;  // debug: descriptor base_offset = (addr
 constexpr int kFlagForceKd1 = 4;
 constexpr int kFlagNoFastPath = 8;
 constexpr int kFlagWideN = 16;  // A/B: keep 256-wide N tiles for 3x3x3 layers with cout >= 256 (one kd per weight block)
-constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8 - 2112;  // 227 KB minus alignment slack, barriers, fused-head weights
+constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8 - 2112 - 2048;  // 227 KB minus alignment slack, barriers, head weights, bias
 
 struct Plan {
   int mode, kd_per_block, R, Rd, up_groups, nhalf, cph, nblk, nchunk0, nchunk1, k16, TW, TH, n_wbuf, n_astage;

@@ -132,7 +132,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   uint64_t* acc_full = bars + 24;   // [8]
   uint64_t* acc_empty = bars + 32;  // [8]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
-  float* s_head = reinterpret_cast<float*>(bars + 48);  // [ncls*64 + ncls] when the head is fused
+  float* s_head = reinterpret_cast<float*>(bars + 48);  // [ncls*64 + ncls] when the head is fused (2112 B reserved)
+  float* s_bias = s_head + 528;                          // [nhalf*cout] (<= 512 floats)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,6 +157,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < p.nhalf * p.cout; i += blockDim.x) s_bias[i] = p.bias[i];
   if (p.head.enabled) {
     for (int i = threadIdx.x; i < p.head.ncls * 64; i += blockDim.x) s_head[i] = p.head.w[i];
     for (int i = threadIdx.x; i < p.head.ncls; i += blockDim.x) s_head[p.head.ncls * 64 + i] = p.head.b[i];
@@ -396,26 +398,42 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         } else {
         uint16_t* dst = (p.mode == kModeUp2) ? out + off0 + ui.d0 * p.osD + p.tap_off[ui.tg * p.R + a]
                                              : out + off0 + (ui.d0 + a) * p.osD;
-        for (int j = 0; j < p.cout / 32; ++j) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a * p.cout + j * 32),
-                        v);
+        const float* sb = s_bias + ui.nh * p.cout;
+        const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a * p.cout);
+        const int nb = p.cout / 32;
+        // 64 columns per TMEM round trip; the accumulator is handed back to the MMA warp as soon as its last
+        // columns sit in registers, before the conversion and the global stores of that batch
+        for (int j = 0; j < nb; j += 2) {
+          uint32_t v[2][32];
+          tmem_ld_32x32(t_acc + j * 32, v[0]);
+          if (j + 1 < nb) tmem_ld_32x32(t_acc + (j + 1) * 32, v[1]);
           tmem_ld_wait();
-          uint32_t o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x0 = __uint_as_float(v[2 * i]) + __ldg(bias + j * 32 + 2 * i);
-            float x1 = __uint_as_float(v[2 * i + 1]) + __ldg(bias + j * 32 + 2 * i + 1);
-            if (p.relu) {
-              x0 = fmaxf(x0, 0.f);
-              x1 = fmaxf(x1, 0.f);
-            }
-            o[i] = pack2(x0, x1, p.ab_format);
+          if (j + 2 >= nb) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
           }
-          uint4* d4 = reinterpret_cast<uint4*>(dst + j * 32);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          for (int h = 0; h < 2; ++h) {
+            if (j + h >= nb) break;
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + (j + h) * 32 + 4 * i);
+              float x0 = __uint_as_float(v[h][4 * i]) + b4.x, x1 = __uint_as_float(v[h][4 * i + 1]) + b4.y;
+              float x2 = __uint_as_float(v[h][4 * i + 2]) + b4.z, x3 = __uint_as_float(v[h][4 * i + 3]) + b4.w;
+              if (p.relu) {
+                x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+              }
+              o[2 * i] = pack2(x0, x1, p.ab_format);
+              o[2 * i + 1] = pack2(x2, x3, p.ab_format);
+            }
+            uint4* d4 = reinterpret_cast<uint4*>(dst + (j + h) * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
         }
+        continue;  // accumulator already released
         }
         tc_fence_before();
         __syncwarp();
@@ -436,7 +454,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 
 static size_t conv_igemm_smem_bytes(const ConvIgemmParams& p) {
   const size_t wstride = (p.wblock_bytes + 1023u) & ~size_t(1023);
-  return 1024 + p.n_wbuf * wstride + static_cast<size_t>(p.n_astage) * p.astage_stride + 48 * 8 + 2112;
+  return 1024 + p.n_wbuf * wstride + static_cast<size_t>(p.n_astage) * p.astage_stride + 48 * 8 + 2112 + 2048;
 }
 
 cudaError_t conv_igemm_launch(const ConvIgemmParams& p, const CUtensorMap& tm0, const CUtensorMap& tm1, int num_sms,
