@@ -44,9 +44,9 @@ int make_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int 
   pl->cph = cout / pl->nhalf;
   OAI_REQUIRE(pl->cph % 32 == 0, "conv plan: cout per split (%d) must be a multiple of 32", pl->cph);
   if (d_cnt <= 0) d_cnt = D;
-  int R = 1;
-  for (int r = 1; r <= 8; ++r)
-    if (d_cnt % r == 0 && r * pl->cph <= 512) R = r;
+  // as many accumulators as TMEM holds; the last d-group of a region may be partial
+  int R = 512 / pl->cph < 8 ? 512 / pl->cph : 8;
+  if (R > d_cnt) R = d_cnt;
   pl->R = R;
   pl->Rd = R;
   pl->up_groups = 1;
@@ -340,7 +340,7 @@ static int conv_common(const void* src0, int c0, const void* src1, int c1, int N
   p.obase = obase; p.osN = osN; p.osD = osD; p.osH = osH; p.osW = osW;
   p.d_lo = d_lo; p.d_cnt = d_cnt; p.hp_lo = hp_lo; p.hp_cnt = hp_cnt;
   p.Rd = pl.Rd; p.up_groups = pl.up_groups;
-  p.nunits = NT * (d_cnt / pl.Rd) * (hp_cnt * (W / pl.TW)) * pl.up_groups * pl.nhalf;
+  p.nunits = NT * ((d_cnt + pl.Rd - 1) / pl.Rd) * (hp_cnt * (W / pl.TW)) * pl.up_groups * pl.nhalf;
   if (pl.mode == kModeUp2) {
     for (int t = 0; t < 8; ++t)
       p.tap_off[t] = ((static_cast<long long>(t >> 2) * 2 * H + ((t >> 1) & 1)) * 2 * W + (t & 1)) * cout;

@@ -73,12 +73,14 @@ __device__ __forceinline__ BlockInfo decode_block(const ConvIgemmParams& p, int 
 struct UnitInfo {
   int n, d0, h0, w0, nh;
   int tg;  // kModeUp2: tap group
+  int rd;  // output d-slices of this unit (the last group of a region may be partial)
+  int ra;  // accumulators used by this unit (== rd, or the tap count in kModeUp2)
 };
 
 __device__ __forceinline__ UnitInfo decode_unit(const ConvIgemmParams& p, int u) {
   UnitInfo ui;
   const int npw = p.W / p.TW;
-  const int np = npw * p.hp_cnt, ndg = p.d_cnt / p.Rd;
+  const int np = npw * p.hp_cnt, ndg = (p.d_cnt + p.Rd - 1) / p.Rd;
   ui.nh = u % p.nhalf;
   u /= p.nhalf;
   ui.tg = u % p.up_groups;
@@ -89,6 +91,8 @@ __device__ __forceinline__ UnitInfo decode_unit(const ConvIgemmParams& p, int u)
   ui.n = u / ndg;
   ui.h0 = (p.hp_lo + patch / npw) * p.TH;
   ui.w0 = (patch % npw) * p.TW;
+  ui.rd = min(p.Rd, p.d_lo + p.d_cnt - ui.d0);
+  ui.ra = (p.mode == kModeUp2) ? p.R : ui.rd;
   return ui;
 }
 
@@ -183,7 +187,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           const int cc = (src0 ? bi.c : bi.c - p.nchunk0) * 64;
           const int kdhi = bi.kdlo + bi.nkd - 1;
           const int dlo = max(0, ui.d0 + bi.kdlo - 1);
-          const int dhi = min(p.D - 1, ui.d0 + p.Rd - 1 + kdhi - 1);
+          const int dhi = min(p.D - 1, ui.d0 + ui.rd - 1 + kdhi - 1);
           const int cw = (p.mode == kModeRowShared) ? ui.w0 - 1 : ui.w0 + bi.kw - 1;
           const int ch = ui.h0 + bi.kh - 1;
           for (int dp = dlo; dp <= dhi; ++dp) {
@@ -224,18 +228,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     // elected lane issues tcgen05.mma / tcgen05.commit.  The issue thread is the critical resource of this kernel
     // (one MMA per ~100 tensor-pipe cycles), so the steady state is a fully unrolled sequence of descriptor adds.
     int stage = 0, wb = 0;
-    uint32_t aphase = 0, wphase = 0, it = 0;
+    uint32_t aphase = 0, wphase = 0, use_bits = 0;  // use_bits: per-accumulator mbarrier phase (flips per use)
     const uint32_t cout128 = static_cast<uint32_t>(p.cout) * 128u;
     const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
                              (static_cast<uint64_t>(2) << 61) | (static_cast<uint64_t>(1) << 16);
-    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
       const UnitInfo ui = decode_unit(p, u);
       uint32_t touched = 0, signaled = 0;
       for (int b = 0; b < p.nblk; ++b) {
         const BlockInfo bi = decode_block(p, b);
         const int kdhi = bi.kdlo + bi.nkd - 1;
         const int dlo = max(0, ui.d0 + bi.kdlo - 1);
-        const int dhi = min(p.D - 1, ui.d0 + p.Rd - 1 + kdhi - 1);
+        const int dhi = min(p.D - 1, ui.d0 + ui.rd - 1 + kdhi - 1);
         mbar_wait(&full_w[wb], wphase, 300 + wb);
         const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
         for (int dp = dlo; dp <= dhi; ++dp) {
@@ -245,7 +249,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           // accumulator hit by the first stacked tap (highest kd; tap 0 of the group for kModeUp2)
           const int a_first = (p.mode == kModeUp2) ? 0 : dp - kdhi + 1 - ui.d0;
           const int ti_lo = max(0, -a_first);
-          const int ti_hi = min(bi.ns - 1, p.R - 1 - a_first);
+          const int ti_hi = min(bi.ns - 1, ui.ra - 1 - a_first);
           const int nt = ti_hi - ti_lo + 1;
           const uint32_t span = ((1u << nt) - 1u) << (a_first + ti_lo);
           if ((touched & span) == span && !p.base_off_mode && !p.no_fast_path) {
@@ -285,7 +289,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 int len = 1;
                 while (ti + len <= ti_hi && ((touched >> (a0 + len)) & 1u) == f && (len + 1) * p.cout <= 256) ++len;
                 if (!f) {
-                  for (int j = 0; j < len; ++j) mbar_wait(&acc_empty[a0 + j], (it & 1u) ^ 1u, 500 + a0 + j);
+                  for (int j = 0; j < len; ++j)
+                    mbar_wait(&acc_empty[a0 + j], ((use_bits >> (a0 + j)) & 1u) ^ 1u, 500 + a0 + j);
                   tc_fence_after();
                 }
                 const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * p.cout), p.ab_format);
@@ -309,7 +314,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               }
             }
           }
-          const bool last_block = (b == p.nblk - 1) && a_first >= 0 && a_first < p.R;
+          const bool last_block = (b == p.nblk - 1) && a_first >= 0 && a_first < ui.ra;
           if (elect_one()) {
             umma_commit(&empty_a[stage]);
             if (last_block) umma_commit(&acc_full[a_first]);
@@ -329,25 +334,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         }
       }
       if (elect_one()) {
-        for (int a = 0; a < p.R; ++a)
+        for (int a = 0; a < ui.ra; ++a)
           if (!((signaled >> a) & 1u)) umma_commit(&acc_full[a]);
       }
       __syncwarp();
+      use_bits ^= (1u << ui.ra) - 1u;
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int th = m / p.TW, tw = m % p.TW;
-    uint32_t it = 0;
+    uint32_t use_bits = 0;
     uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
-    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
       const UnitInfo ui = decode_unit(p, u);
       const long long off0 = p.obase + ui.n * p.osN + (ui.h0 + th) * p.osH + (ui.w0 + tw) * p.osW +
                              static_cast<long long>(ui.nh) * p.cout;
       const float* bias = p.bias + ui.nh * p.cout;
-      for (int a = 0; a < p.R; ++a) {
-        mbar_wait(&acc_full[a], it & 1u, 600 + a);
+      for (int a = 0; a < ui.ra; ++a) {
+        mbar_wait(&acc_full[a], (use_bits >> a) & 1u, 600 + a);
         tc_fence_after();
         if (p.head.enabled) {
           // fused dc0 + sigmoid + crop-and-place: only interior voxels of the tile are ever written
@@ -439,6 +445,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[a]);
       }
+      use_bits ^= (1u << ui.ra) - 1u;
     }
   }
 

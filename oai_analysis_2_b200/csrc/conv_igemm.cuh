@@ -31,7 +31,7 @@ struct ConvIgemmParams {
   // activation grid (identical for input and output: stride-1 "same" conv or pointwise)
   int NT, D, H, W;
   int TW, TH;       // M tile = TH x TW voxels in one d-slice (TH*TW == 128)
-  int R;            // accumulators per unit = consecutive output d-slices (R*cout <= 512, d_cnt % R == 0)
+  int R;            // accumulators per unit = consecutive output d-slices (R*cout <= 512; the last group of a region may be partial)
   int Rd;           // d-slices per unit (== R except kModeUp2, where R counts taps and Rd == 1)
   int up_groups;    // kModeUp2: tap groups per M tile (8 / R)
   long long tap_off[8];  // kModeUp2: output element offset of tap (a,b,c) = ((a*2H + b)*2W + c)*cout

@@ -186,21 +186,10 @@ class UNet:
 
     @staticmethod
     def _region_arg(box, dims, cout, pointwise=False):
-        """(d_lo, d_cnt, h_lo, h_cnt) for the C ABI; the d count is padded when that buys a larger accumulator group
-        (a group of r output slices loads r + 2 input slices, so small groups are load-bound)."""
-        (lo, hi), D = box, dims[0]
-        cnt = int(hi[0] - lo[0] + 1)
-        cph = cout if cout <= 256 else cout // 2
-        rmax = max(1, min(8, 512 // cph))
-        best = None
-        for c in range(cnt, min(D, cnt + 3) + 1):
-            r = max(k for k in range(1, rmax + 1) if c % k == 0)
-            cost = c if pointwise else c * (1.0 + 2.0 / r)
-            if best is None or cost < best[0]:
-                best = (cost, c)
-        c = best[1]
-        d_lo = int(max(0, min(lo[0] - (c - cnt) // 2, D - c)))
-        return (d_lo, c, int(lo[1]), int(hi[1] - lo[1] + 1))
+        """(d_lo, d_cnt, h_lo, h_cnt) for the C ABI (the kernel groups d-slices by itself; the last group may be
+        partial)."""
+        lo, hi = box
+        return (int(lo[0]), int(hi[0] - lo[0] + 1), int(lo[1]), int(hi[1] - lo[1] + 1))
 
     # ------------------------------------------------------------------ forward pieces
     def _conv(self, P, name, src0, src1=None, box=None):

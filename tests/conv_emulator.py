@@ -66,6 +66,7 @@ def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", r
         for d0 in range(d_lo, d_lo + d_cnt, R):
             for h0 in range(hp_lo * TH, hp_hi * TH, TH):
                 for w0 in range(0, W, TW):
+                    rv = min(R, d_lo + d_cnt - d0)  # the last d-group of a region may be partial
                     for nh in range(nhalf):
                         acc = np.zeros((R, 128, cph), dtype=np.float32)
                         touched = [False] * R
@@ -84,7 +85,7 @@ def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", r
                             src = xs[0] if c < nchunk0 else xs[1]
                             cc = (c if c < nchunk0 else c - nchunk0) * 64
                             kdhi = kdlo + nkd - 1
-                            dlo, dhi = max(0, d0 + kdlo - 1), min(D - 1, d0 + R - 1 + kdhi - 1)
+                            dlo, dhi = max(0, d0 + kdlo - 1), min(D - 1, d0 + rv - 1 + kdhi - 1)
                             if mode == MODE_ROW_SHARED:
                                 cw, bw, bh = w0 - 1, 130, 1
                             elif mode == MODE_PER_TAP:
@@ -95,7 +96,7 @@ def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", r
                             for dp in range(dlo, dhi + 1):
                                 stage = _swizzled_store(_box(src, n, dp, ch, cw, cc, bh, bw))
                                 a_first = dp - kdhi + 1 - d0
-                                ti_lo, ti_hi = max(0, -a_first), min(nkd - 1, R - 1 - a_first)
+                                ti_lo, ti_hi = max(0, -a_first), min(nkd - 1, rv - 1 - a_first)
                                 for kw in range(nkw):
                                     A = _read_operand(stage, kw * 128, 128).view(f16).astype(np.float32)
                                     A[:, k16_steps * 16:] = 0
@@ -116,7 +117,7 @@ def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", r
                                                 acc[a0 + j] = prod[:, j * cph:(j + 1) * cph]
                                             touched[a0 + j] = True
                                         ti += ln
-                        for a in range(R):
+                        for a in range(rv):
                             v = acc[a] + bias[nh * cph:(nh + 1) * cph][None, :]
                             if relu:
                                 v = np.maximum(v, 0)

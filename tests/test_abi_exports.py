@@ -37,6 +37,7 @@ def test_planner_rejects_bad_geometry_with_message():
         ops.conv_plan(8, 16, 16, 12, 0, 64)
     with pytest.raises(_lib.OaiError, match="W="):
         ops.conv_plan(8, 16, 24, 64, 0, 64)
+    assert ops.conv_plan(6, 32, 32, 64, 0, 128)["R"] == 4      # D need not be a multiple of R any more
     pl = ops.conv_plan(32, 128, 128, 128, 64, 64)
     assert pl["mode"] == 0 and pl["R"] == 8 and pl["nblk"] == 9 and pl["wblock_bytes"] == 9 * 64 * 128
     pl = ops.conv_plan(4, 16, 16, 256, 0, 512)

@@ -55,5 +55,5 @@ def test_production_geometry_regions():
     assert B["dc2"][0].tolist() == [7, 15, 15] and B["dc3"][0].tolist() == [3, 7, 7] and B["dc3"][1].tolist() == [12, 56, 56]
     assert UNet._region_arg(B["dc2"], (32, 128, 128), 64) == (7, 18, 15, 98)
     assert UNet._region_arg(B["dc1"], (32, 128, 128), 64) == (8, 16, 16, 96)
-    assert UNet._region_arg(B["dc4"], (16, 64, 64), 128) == (2, 12, 7, 50)   # 10 slices padded to 12 -> groups of 4
+    assert UNet._region_arg(B["dc4"], (16, 64, 64), 128) == (3, 10, 7, 50)
     assert UNet._region_arg(B["dc3"], (16, 64, 64), 128, True) == (3, 10, 7, 50)
