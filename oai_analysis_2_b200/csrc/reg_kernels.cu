@@ -331,6 +331,153 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
   }
 }
 
+// ---- shared-memory tiled variant for the large levels -----------------------------------------------------------
+// Block = 128 threads = one output tile of 2 (z) x 8 (y) x 64 (x) voxels; per chunk of 8 input channels the
+// 3 x 6 x 34 input neighbourhood and the [8][64][CO_T] weight slice are staged with cp.async (double buffered), so the
+// FMA loop reads shared memory only and the next chunk's global loads are in flight while the current one computes.
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 4 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kTileCI = 8, kTileSX = 36, kTileIn = 3 * 6 * kTileSX;  // input tile floats per channel (x padded 34 -> 36)
+
+template <int CO_T>
+__global__ void __launch_bounds__(128) convt4_tile_kernel(const ConvT4Params p) {
+  constexpr int XP = 4;
+  extern __shared__ __align__(16) float s_tile[];
+  float* s_in = s_tile;                                  // [2][kTileCI][3][6][kTileSX]
+  float* s_w = s_tile + 2 * kTileCI * kTileIn;           // [2][kTileCI][64][CO_T]
+  const int co0 = blockIdx.y * CO_T;
+  const int n = blockIdx.z;
+  const int ntx = ((p.Wo + 1) / 2 + 31) / 32, nty = ((p.Ho + 1) / 2 + 3) / 4;
+  const int x0 = (blockIdx.x % ntx) * 32, y0 = ((blockIdx.x / ntx) % nty) * 4, z0 = blockIdx.x / (ntx * nty);
+  const int tid = threadIdx.x;
+  const int strip = tid & 7, yl = (tid >> 3) & 7, zl = tid >> 6;
+  const int zo = 2 * z0 + zl, yo = 2 * y0 + yl, j0 = x0 + 4 * strip;
+  const float* in_n = p.in + n * p.in_nstride;
+
+  auto stage = [&](int chunk, int buf) {
+    const int ci0 = chunk * kTileCI;
+    float* din = s_in + buf * kTileCI * kTileIn;
+    for (int i = tid; i < kTileCI * 3 * 6 * 34; i += 128) {
+      const int sx = i % 34, sy = (i / 34) % 6, sz = (i / (34 * 6)) % 3, c = i / (34 * 6 * 3);
+      const int x = x0 - 1 + sx, y = y0 - 1 + sy, z = z0 - 1 + sz, ci = ci0 + c;
+      const bool ok = ci < p.cin && x >= 0 && x < p.Wi && y >= 0 && y < p.Hi && z >= 0 && z < p.Di;
+      const float* src = ok ? in_n + ci * p.in_cstride + (static_cast<size_t>(z) * p.Hi + y) * p.Wi + x : in_n;
+      cp_async_4(din + c * kTileIn + (sz * 6 + sy) * kTileSX + sx, src, ok);
+    }
+    float* dw = s_w + buf * kTileCI * 64 * CO_T;
+    for (int i = tid; i < kTileCI * 64 * CO_T / 4; i += 128) {
+      const int q4 = i % (CO_T / 4), k = (i / (CO_T / 4)) % 64, c = i / (64 * CO_T / 4);
+      const int ci = min(ci0 + c, p.cin - 1);  // channels past cin read a valid row; their inputs are zero-filled
+      cp_async_16(dw + (c * 64 + k) * CO_T + 4 * q4, p.w + (static_cast<size_t>(ci) * 64 + k) * p.cout + co0 + 4 * q4);
+    }
+    cp_async_commit();
+  };
+
+  int kz[2], sz[2], ky[2], sy[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    kz[t] = ((zo + 1) & 1) + 2 * t;
+    sz[t] = (zo + 1 - kz[t]) / 2 - (z0 - 1);
+    ky[t] = ((yo + 1) & 1) + 2 * t;
+    sy[t] = (yo + 1 - ky[t]) / 2 - (y0 - 1);
+  }
+  float acc0[XP][CO_T], acc1[XP][CO_T];
+#pragma unroll
+  for (int i = 0; i < XP; ++i)
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) acc0[i][c] = acc1[i][c] = 0.f;
+
+  const int nchunks = (p.cin + kTileCI - 1) / kTileCI;
+  stage(0, 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) {
+      stage(ch + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* tin = s_in + buf * kTileCI * kTileIn;
+    const float* tw = s_w + buf * kTileCI * 64 * CO_T;
+#pragma unroll 2
+    for (int c = 0; c < kTileCI; ++c) {
+#pragma unroll
+      for (int tz = 0; tz < 2; ++tz)
+#pragma unroll
+        for (int ty = 0; ty < 2; ++ty) {
+          const float* row = tin + c * kTileIn + (sz[tz] * 6 + sy[ty]) * kTileSX + 4 * strip;
+          const float4 m = *reinterpret_cast<const float4*>(row);
+          const float2 e = *reinterpret_cast<const float2*>(row + 4);
+          const float xr[XP + 2] = {leaky(m.x), leaky(m.y), leaky(m.z), leaky(m.w), leaky(e.x), leaky(e.y)};
+          const float* wk = tw + (c * 64 + (kz[tz] * 4 + ky[ty]) * 4) * CO_T;
+          float w0[CO_T], w1[CO_T], w2[CO_T], w3[CO_T];
+#pragma unroll
+          for (int k = 0; k < CO_T; ++k) {
+            w0[k] = wk[k]; w1[k] = wk[CO_T + k]; w2[k] = wk[2 * CO_T + k]; w3[k] = wk[3 * CO_T + k];
+          }
+#pragma unroll
+          for (int i = 0; i < XP; ++i)
+#pragma unroll
+            for (int k = 0; k < CO_T; ++k) {
+              acc0[i][k] = fmaf(xr[i + 1], w1[k], acc0[i][k]);
+              acc0[i][k] = fmaf(xr[i], w3[k], acc0[i][k]);
+              acc1[i][k] = fmaf(xr[i + 2], w0[k], acc1[i][k]);
+              acc1[i][k] = fmaf(xr[i + 1], w2[k], acc1[i][k]);
+            }
+        }
+    }
+    __syncthreads();
+  }
+  if (zo >= p.Do || yo >= p.Ho) return;
+  // residual: F.interpolate(in[:, :cout], scale_factor=2, trilinear, align_corners=False) on the RAW input
+  int zz0, zz1, yy0, yy1;
+  float lz, ly;
+  {
+    float sc = fmaxf(0.5f * (zo + 0.5f) - 0.5f, 0.f);
+    zz0 = static_cast<int>(sc); zz1 = zz0 + (zz0 < p.Di - 1 ? 1 : 0); lz = sc - zz0;
+    sc = fmaxf(0.5f * (yo + 0.5f) - 0.5f, 0.f);
+    yy0 = static_cast<int>(sc); yy1 = yy0 + (yy0 < p.Hi - 1 ? 1 : 0); ly = sc - yy0;
+  }
+  float* out_n = p.out + n * p.out_nstride;
+#pragma unroll
+  for (int i = 0; i < XP; ++i) {
+#pragma unroll
+    for (int xx = 0; xx < 2; ++xx) {
+      const int xo = 2 * (j0 + i) + xx;
+      if (xo >= p.Wo) break;
+      const float sc = fmaxf(0.5f * (xo + 0.5f) - 0.5f, 0.f);
+      const int xx0 = static_cast<int>(sc), xx1 = xx0 + (xx0 < p.Wi - 1 ? 1 : 0);
+      const float lx = sc - xx0;
+      const long long ovox = (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + xo;
+#pragma unroll
+      for (int c = 0; c < CO_T; ++c) {
+        const int co = co0 + c;
+        if (co >= p.cout) break;
+        const float* pl = in_n + co * p.in_cstride;
+        auto at = [&](int z, int y, int x) { return __ldg(pl + (static_cast<size_t>(z) * p.Hi + y) * p.Wi + x); };
+        const float r = (1.f - lz) * ((1.f - ly) * ((1.f - lx) * at(zz0, yy0, xx0) + lx * at(zz0, yy0, xx1)) +
+                                      ly * ((1.f - lx) * at(zz0, yy1, xx0) + lx * at(zz0, yy1, xx1))) +
+                        lz * ((1.f - ly) * ((1.f - lx) * at(zz1, yy0, xx0) + lx * at(zz1, yy0, xx1)) +
+                              ly * ((1.f - lx) * at(zz1, yy1, xx0) + lx * at(zz1, yy1, xx1)));
+        const float a = (xx == 0 ? acc0[i][c] : acc1[i][c]) + p.bias[co] + r;
+        out_n[co * p.out_cstride + ovox] = a * p.bn_scale[co] + p.bn_shift[co];
+      }
+    }
+  }
+}
+
 // Deep levels of the up path (few voxels, hundreds of channels): one block serves ONE output parity class
 // (zo%2, yo%2, xo%2), which uses only 8 of the 64 taps, so the weight tile staged in shared memory is 8x smaller than
 // in the strip kernel and is amortised over the whole block; the channel loop is split KS ways across thread groups.
@@ -803,7 +950,20 @@ static void convt4_dispatch(const ConvT4Params& p, cudaStream_t st) {
 
 int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
   const long long nout = static_cast<long long>(p.Do) * p.Ho * p.Wo;
-  if (nout * ((p.cout + 7) / 8) >= (1 << 17)) {
+  if (nout * ((p.cout + 7) / 8) >= (1 << 17) && p.cout % 8 == 0) {
+    // large levels: shared-memory tiled kernel (2 x 8 x 64 output voxels per block)
+    constexpr int CO_T = 8;
+    constexpr size_t smem = (2 * kTileCI * kTileIn + 2 * kTileCI * 64 * CO_T) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(convt4_tile_kernel<CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(smem));
+      configured = true;
+    }
+    const int ntx = ((p.Wo + 1) / 2 + 31) / 32, nty = ((p.Ho + 1) / 2 + 3) / 4, ntz = (p.Do + 1) / 2;
+    dim3 g(static_cast<unsigned>(ntx) * nty * ntz, p.cout / CO_T, p.N);
+    convt4_tile_kernel<CO_T><<<g, 128, smem, st>>>(p);
+  } else if (nout * ((p.cout + 7) / 8) >= (1 << 17)) {
     convt4_dispatch<8, 4, 1>(p, st);
   } else {
     // deep levels: one block per output parity class, channel loop split 4 ways

@@ -6,6 +6,7 @@ over channels-last 16-bit activations.  BatchNorm (eval) is folded into the prec
 convolutions are re-expressed as convolutions / pointwise GEMMs, and the skip concatenations are two-source K loops.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -38,7 +39,7 @@ class UNet:
         self.precision = "fp16"  # fp16 carries TF32's 10-bit mantissa: the reference's own cuDNN default precision
         # ConvTranspose3d(k2,s2): one stacked-tap launch (True) or 8 pointwise launches (False; measured faster on
         # B200: the layer is output-bandwidth-bound and the 8 small launches pipeline their epilogues better)
-        self.up2_single_launch = False
+        self.up2_single_launch = os.environ.get("OAI_B200_UP2_SINGLE", "0") == "1"
         self._sd = self._blank_state_dict()
         self._packed = {}
 
