@@ -85,8 +85,9 @@ OAI_API int oai_conv3d_igemm_head(const void* src0, int c0, const void* src1, in
                                   const int* geom, int tile0, const int* crop_zyx, int out_mode, int flags,
                                   void* stream);
 
-/* Geometry the kernel will use for (D,H,W,cin,cout,pointwise): fills plan[8] =
- * {mode, kd_per_block (tap groups when pointwise == 2), R, nhalf, cout_per_half, nblk, wblock_bytes, nchunks}.
+/* Geometry the kernel will use for (D,H,W,cin,cout,pointwise): fills plan[9] =
+ * {mode, kd_per_block (tap groups when pointwise == 2), R, nhalf, cout_per_half, nblk, wblock_bytes, nchunks,
+ *  row_bytes}.
  * pointwise: 0 = 3x3x3, 1 = 1x1x1, 2 = ConvTranspose3d(k2,s2).  Pure host arithmetic (no GPU). */
 OAI_API int oai_conv3d_igemm_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int flags, int* plan);
 

@@ -20,11 +20,12 @@ constexpr int kFlagForcePerTap = 1;
 constexpr int kFlagBaseOffFormula = 2;  // debug: descriptor base_offset = (addr>>7)&7 (measured WRONG on B200)
 constexpr int kFlagForceKd1 = 4;
 constexpr int kFlagNoFastPath = 8;
-constexpr int kFlagWideN = 16;  // A/B: keep 256-wide N tiles for 3x3x3 layers with cout >= 256 (one kd per weight block)
+constexpr int kFlagWideN = 16;
+constexpr int kFlagWideRows = 32;  // A/B: keep 128-byte rows (zero-filled upper half) for a 32-channel source  // A/B: keep 256-wide N tiles for 3x3x3 layers with cout >= 256 (one kd per weight block)
 constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8 - 2112 - 2048;  // 227 KB minus alignment slack, barriers, head weights, bias
 
 struct Plan {
-  int mode, kd_per_block, R, Rd, up_groups, nhalf, cph, nblk, nchunk0, nchunk1, k16, TW, TH, n_wbuf, n_astage;
+  int mode, kd_per_block, R, Rd, up_groups, nhalf, cph, nblk, nchunk0, nchunk1, k16, row_bytes, TW, TH, n_wbuf, n_astage;
   uint32_t wblock_bytes, astage_bytes, astage_stride;
 };
 
@@ -53,6 +54,9 @@ int make_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int 
   pl->nchunk0 = (c0 + 63) / 64;
   pl->nchunk1 = (c1 + 63) / 64;
   pl->k16 = (c1 == 0 && c0 <= 32) ? (c0 <= 16 ? 1 : 2) : 4;
+  // a single 32-channel source keeps 64-byte rows (SWIZZLE_64B): half the TMA / shared-memory bytes per voxel
+  pl->row_bytes = (c1 == 0 && c0 == 32 && !(flags & kFlagWideRows)) ? 64 : 128;
+  const int rb = pl->row_bytes;
   const int nch = pl->nchunk0 + pl->nchunk1;
   if (pointwise == 2) {
     // ConvTranspose3d(k2,s2): the unit's accumulators are taps of one M tile
@@ -61,35 +65,30 @@ int make_plan(int D, int H, int W, int c0, int c1, int cout, int pointwise, int 
     pl->R = 512 / pl->cph < 8 ? 512 / pl->cph : 8;
     pl->Rd = 1;
     pl->up_groups = 8 / pl->R;
-    pl->wblock_bytes = pl->R * pl->cph * 128;
+    pl->wblock_bytes = pl->R * pl->cph * rb;
     pl->nblk = nch;
     pl->n_wbuf = 2;
   } else if (pointwise) {
     pl->mode = kModePointwise;
     pl->kd_per_block = 1;
-    pl->wblock_bytes = pl->cph * 128;
+    pl->wblock_bytes = pl->cph * rb;
     pl->nblk = nch;
     pl->n_wbuf = 3;
   } else if (pl->TW == 128 && pl->cph <= 64 && !(flags & kFlagForcePerTap)) {
     pl->mode = kModeRowShared;
     pl->kd_per_block = 3;
-    pl->wblock_bytes = 9 * pl->cph * 128;
+    pl->wblock_bytes = 9 * pl->cph * rb;
     pl->nblk = nch * 3;
     pl->n_wbuf = 2;
   } else {
     pl->mode = kModePerTap;
     pl->kd_per_block = (pl->cph <= 128 && !(flags & kFlagForceKd1)) ? 3 : 1;
-    pl->wblock_bytes = pl->kd_per_block * pl->cph * 128;
+    pl->wblock_bytes = pl->kd_per_block * pl->cph * rb;
     pl->nblk = nch * (pl->kd_per_block == 3 ? 9 : 27);
     pl->n_wbuf = pl->kd_per_block == 3 ? 2 : 3;
   }
-  if (pl->mode == kModeRowShared) {
-    pl->astage_bytes = 130 * 128;
-    pl->astage_stride = 17 * 1024;
-  } else {
-    pl->astage_bytes = 128 * 128;
-    pl->astage_stride = 16 * 1024;
-  }
+  pl->astage_bytes = (pl->mode == kModeRowShared ? 130 : 128) * rb;
+  pl->astage_stride = (pl->astage_bytes + 1023u) & ~1023u;
   const size_t wstride = (pl->wblock_bytes + 1023u) & ~size_t(1023);
   const size_t left = kSmemBudget - pl->n_wbuf * wstride;
   int ns = static_cast<int>(left / pl->astage_stride);
@@ -116,17 +115,19 @@ EncodeTiledFn encode_fn() {
 }
 
 // NDHWC 16-bit activation tensor viewed as a rank-5 TMA tensor (C, W, H, D, N); box = (64, bw, bh, 1, 1).
-int make_act_tmap(CUtensorMap* tm, const void* base, int C, int W, int H, int D, int N, int bw, int bh, int fmt) {
+int make_act_tmap(CUtensorMap* tm, const void* base, int C, int W, int H, int D, int N, int bw, int bh, int fmt,
+                  int row_bytes = 128) {
   EncodeTiledFn fn = encode_fn();
   OAI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
                            (cuuint64_t)D * H * W * C * 2};
-  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)(row_bytes / 2), (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(tm, fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   OAI_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (C=%d W=%d H=%d D=%d N=%d box %dx%d)", (int)r,
               C, W, H, D, N, bw, bh);
   return 0;
@@ -143,6 +144,14 @@ inline uint16_t to16(float x, int fmt) {
   uint16_t u;
   memcpy(&u, &h, 2);
   return u;
+}
+
+// byte offset of element j (16-bit) of row r in a K-major swizzled block: 16-byte chunks are XOR-ed with the row index
+// (SWIZZLE_128B: chunk ^= r & 7 over 128-byte rows; SWIZZLE_64B: chunk ^= (r >> 1) & 3 over 64-byte rows)
+inline size_t swz_off(int r, int j, int row_bytes) {
+  const int chunk = j >> 3;
+  const int sw = row_bytes == 128 ? (chunk ^ (r & 7)) : (chunk ^ ((r >> 1) & 3));
+  return static_cast<size_t>(r) * row_bytes + (static_cast<size_t>(sw) << 4) + (j & 7) * 2;
 }
 
 inline float from16(uint16_t u, int fmt) {
@@ -185,6 +194,7 @@ extern "C" int oai_conv3d_igemm_plan(int D, int H, int W, int c0, int c1, int co
   plan[5] = pl.nblk;
   plan[6] = static_cast<int>(pl.wblock_bytes);
   plan[7] = pl.nchunk0 + pl.nchunk1;
+  plan[8] = pl.row_bytes;
   return 0;
 }
 
@@ -241,8 +251,9 @@ extern "C" int oai_pack_conv_weights(const float* w, int cout, int c0, int c1, i
             for (int j = 0; j < 64; ++j) {
               const int ci = cbase + j;
               if (ci >= climit) break;
+              if (j * 2 >= pl.row_bytes) break;
               const uint16_t h = wrow[static_cast<size_t>(ci) * ktaps + tap];
-              const size_t off = static_cast<size_t>(r) * 128 + (((j >> 3) ^ (r & 7)) << 4) + (j & 7) * 2;
+              const size_t off = swz_off(r, j, pl.row_bytes);
               memcpy(blk + off, &h, 2);
             }
           }
@@ -327,7 +338,7 @@ static int conv_common(const void* src0, int c0, const void* src1, int c1, int N
   p.NT = NT; p.D = D; p.H = H; p.W = W;
   p.TW = pl.TW; p.TH = pl.TH; p.R = pl.R;
   p.cout = pl.cph; p.nhalf = pl.nhalf;
-  p.nchunk0 = pl.nchunk0; p.nchunk1 = pl.nchunk1; p.k16_steps = pl.k16;
+  p.nchunk0 = pl.nchunk0; p.nchunk1 = pl.nchunk1; p.k16_steps = pl.k16; p.row_bytes = pl.row_bytes;
   p.mode = pl.mode; p.kd_per_block = pl.kd_per_block; p.nblk = pl.nblk;
   p.wblock_bytes = pl.wblock_bytes; p.n_wbuf = pl.n_wbuf; p.n_astage = pl.n_astage;
   p.astage_bytes = pl.astage_bytes; p.astage_stride = pl.astage_stride;
@@ -351,7 +362,7 @@ static int conv_common(const void* src0, int c0, const void* src1, int c1, int N
   const int bw = pl.mode == kModeRowShared ? 130 : pl.TW;
   const int bh = pl.TH;
   CUtensorMap tm0, tm1;
-  if (make_act_tmap(&tm0, src0, c0, W, H, D, NT, bw, bh, ab_format)) return 1;
+  if (make_act_tmap(&tm0, src0, c0, W, H, D, NT, bw, bh, ab_format, pl.row_bytes)) return 1;
   if (src1) {
     if (make_act_tmap(&tm1, src1, c1, W, H, D, NT, bw, bh, ab_format)) return 1;
   } else {
@@ -426,7 +437,7 @@ extern "C" int oai_pack_convt2_weights(const float* w, int cout, int cin, int D,
               const int ci = b * 64 + j;
               if (ci >= cin) break;
               const uint16_t h = to16(wrow[static_cast<size_t>(ci) * 8 + tap], ab_format);
-              const size_t off = static_cast<size_t>(r) * 128 + (((j >> 3) ^ (r & 7)) << 4) + (j & 7) * 2;
+              const size_t off = swz_off(r, j, 128);
               memcpy(blk + off, &h, 2);
             }
           }

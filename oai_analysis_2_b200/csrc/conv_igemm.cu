@@ -229,9 +229,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     // (one MMA per ~100 tensor-pipe cycles), so the steady state is a fully unrolled sequence of descriptor adds.
     int stage = 0, wb = 0;
     uint32_t aphase = 0, wphase = 0, use_bits = 0;  // use_bits: per-accumulator mbarrier phase (flips per use)
-    const uint32_t cout128 = static_cast<uint32_t>(p.cout) * 128u;
-    const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
-                             (static_cast<uint64_t>(2) << 61) | (static_cast<uint64_t>(1) << 16);
+    // one voxel's K slice is a row of row_bytes (128 B / SWIZZLE_128B or 64 B / SWIZZLE_64B); 8-row swizzle atoms
+    const uint32_t rowb = static_cast<uint32_t>(p.row_bytes), sbo = 8u * rowb, lay = rowb == 128u ? 2u : 4u;
+    const uint32_t cout128 = static_cast<uint32_t>(p.cout) * rowb;  // bytes of one tap's weight rows
+    const uint32_t kw_step = rowb >> 4;                              // descriptor units per one-voxel row shift
+    const uint64_t desc_hi = (static_cast<uint64_t>(sbo >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+                             (static_cast<uint64_t>(lay) << 61) | (static_cast<uint64_t>(1) << 16);
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
       const UnitInfo ui = decode_unit(p, u);
       uint32_t touched = 0, signaled = 0;
@@ -270,7 +273,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 #pragma unroll
                     for (int k16 = 0; k16 < 4; ++k16) {
                       if (k16 < p.k16_steps)
-                        umma_f16_ss(d_addr, desc_hi | (a_lo + kw * 8 + k16 * 2),
+                        umma_f16_ss(d_addr, desc_hi | (a_lo + kw * kw_step + k16 * 2),
                                     desc_hi | (b_lo + kw * b_kw + k16 * 2), idesc, 1u);
                     }
                   }
@@ -294,7 +297,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                   tc_fence_after();
                 }
                 const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * p.cout), p.ab_format);
-                const uint32_t a_addr = a_base + static_cast<uint32_t>(kw) * 128u;
+                const uint32_t a_addr = a_base + static_cast<uint32_t>(kw) * rowb;
                 const uint32_t b_addr = w_base + static_cast<uint32_t>(kw * bi.ns + ti) * cout128;
                 const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
                 const uint32_t d_addr = tmem_base + static_cast<uint32_t>(a0 * p.cout);
@@ -302,8 +305,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 #pragma unroll
                   for (int k16 = 0; k16 < 4; ++k16) {
                     if (k16 < p.k16_steps) {
-                      const uint64_t adesc = umma_desc_sw128(a_addr + k16 * 32, 1024, boff);
-                      const uint64_t bdesc = umma_desc_sw128(b_addr + k16 * 32, 1024, 0);
+                      const uint64_t adesc = umma_desc_kmajor(a_addr + k16 * 32, sbo, boff, lay);
+                      const uint64_t bdesc = umma_desc_kmajor(b_addr + k16 * 32, sbo, 0, lay);
                       umma_f16_ss(d_addr, adesc, bdesc, idesc, (f | (k16 > 0)) ? 1u : 0u);
                     }
                   }

@@ -41,7 +41,8 @@ struct ConvIgemmParams {
   int nhalf;        // N splits (cout_total = nhalf*cout)
   int nchunk0;      // 64-channel K chunks read from source 0
   int nchunk1;      // ... then from source 1 (skip connection); 0 if single source
-  int k16_steps;    // K=16 MMA steps per chunk: 4 (64 channels) or 2 (a 32-channel source, upper half TMA zero-filled)
+  int k16_steps;    // K=16 MMA steps per chunk: 4 (64 channels) or 2 (32 channels)
+  int row_bytes;    // shared-memory row pitch of one voxel's K slice: 128 (64 ch, SWIZZLE_128B) or 64 (32 ch, SWIZZLE_64B)
   int mode;         // ConvMode
   int kd_per_block; // 3: weights block stacks kd=2,1,0 ; 1: one kd per block
   int nblk;         // weight blocks per (unit, nhalf)

@@ -150,15 +150,20 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor, K-major, 128-byte swizzle (rows of 128 B, 8-row groups `sbo_bytes` apart).
 // Field layout follows the sm_100 UMMA descriptor: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4,
 // [46,48) version=1, [49,52) base offset, [61,64) layout type (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+// layout_type: 2 = SWIZZLE_128B (rows of 128 B, sbo 1024), 4 = SWIZZLE_64B (rows of 64 B, sbo 512).
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset,
+                                                     uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;  // LBO (unused for swizzled K-major)
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(base_offset & 7) << 49;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type & 7) << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+  return umma_desc_kmajor(smem_addr, sbo_bytes, base_offset, 2);
 }
 
 // Instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major.

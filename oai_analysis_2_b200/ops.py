@@ -16,9 +16,9 @@ _DT16 = {0: torch.float16, 1: torch.bfloat16}
 
 
 def conv_plan(D, H, W, c0, c1, cout, pointwise=False, flags=0):
-    plan = (c_int * 8)()
+    plan = (c_int * 9)()
     check(lib.oai_conv3d_igemm_plan(D, H, W, c0, c1, cout, int(pointwise), flags, plan), "conv plan")  # 2 = up2
-    keys = ("mode", "kd_per_block", "R", "nhalf", "cout_per_half", "nblk", "wblock_bytes", "nchunks")
+    keys = ("mode", "kd_per_block", "R", "nhalf", "cout_per_half", "nblk", "wblock_bytes", "nchunks", "row_bytes")
     return dict(zip(keys, list(plan)))
 
 

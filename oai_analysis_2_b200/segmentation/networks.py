@@ -37,9 +37,8 @@ class UNet:
         self.BN = BN
         self.device = torch.device("cpu")
         self.precision = "fp16"  # fp16 carries TF32's 10-bit mantissa: the reference's own cuDNN default precision
-        # ConvTranspose3d(k2,s2): one stacked-tap launch (True) or 8 pointwise launches (False; measured faster on
-        # B200: the layer is output-bandwidth-bound and the 8 small launches pipeline their epilogues better)
-        self.up2_single_launch = os.environ.get("OAI_B200_UP2_SINGLE", "0") == "1"
+        # ConvTranspose3d(k2,s2): one stacked-tap launch (default; reads the input once) or 8 pointwise launches
+        self.up2_single_launch = os.environ.get("OAI_B200_UP2_SINGLE", "1") == "1"
         self._sd = self._blank_state_dict()
         self._packed = {}
 

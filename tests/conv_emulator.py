@@ -8,42 +8,50 @@ import numpy as np
 MODE_ROW_SHARED, MODE_PER_TAP, MODE_POINTWISE = 0, 1, 2
 
 
+def _xor(r, nchunks):
+    """16-byte chunk XOR pattern of a row: SWIZZLE_128B (8 chunks): r % 8; SWIZZLE_64B (4 chunks): (r // 2) % 4."""
+    return r % 8 if nchunks == 8 else (r // 2) % 4
+
+
 def _swizzled_store(rows16):
-    """rows16: [nrows, 64] uint16 -> smem image bytes (uint16 view) with chunk ^= row%8."""
-    n = rows16.shape[0]
-    out = np.zeros((n, 8, 8), dtype=np.uint16)
+    """rows16: [nrows, 64 | 32] uint16 -> smem image (uint16 view), chunks XOR-swizzled by the row index."""
+    n, elems = rows16.shape
+    nch = elems // 8
+    out = np.zeros((n, nch, 8), dtype=np.uint16)
     r = np.arange(n)
-    src = rows16.reshape(n, 8, 8)
-    for j in range(8):
-        out[r, j ^ (r % 8), :] = src[:, j, :]
-    return out.reshape(n * 64)
+    src = rows16.reshape(n, nch, 8)
+    for j in range(nch):
+        out[r, j ^ _xor(r, nch), :] = src[:, j, :]
+    return out.reshape(n * elems)
 
 
-def _read_operand(img16, start_byte, nrows):
-    """UMMA K-major SW128 read: row i at start+i*128, XOR pattern from the absolute row index."""
-    assert start_byte % 128 == 0
-    r_abs = start_byte // 128 + np.arange(nrows)
-    img = img16.reshape(-1, 8, 8)
-    out = np.zeros((nrows, 8, 8), dtype=np.uint16)
-    for j in range(8):
-        out[:, j, :] = img[r_abs, j ^ (r_abs % 8), :]
-    return out.reshape(nrows, 64)
+def _read_operand(img16, start_byte, nrows, elems=64):
+    """UMMA K-major swizzled read: row i at start + i*row_bytes, XOR pattern from the absolute row index."""
+    rb = elems * 2
+    assert start_byte % rb == 0
+    nch = elems // 8
+    r_abs = start_byte // rb + np.arange(nrows)
+    img = img16.reshape(-1, nch, 8)
+    out = np.zeros((nrows, nch, 8), dtype=np.uint16)
+    for j in range(nch):
+        out[:, j, :] = img[r_abs, j ^ _xor(r_abs, nch), :]
+    return out.reshape(nrows, elems)
 
 
-def _box(src, n, dp, ch, cw, cc, bh, bw):
-    """TMA tiled load with zero fill: src [NT,D,H,W,C] uint16 -> [bh*bw, 64]."""
+def _box(src, n, dp, ch, cw, cc, bh, bw, elems=64):
+    """TMA tiled load with zero fill: src [NT,D,H,W,C] uint16 -> [bh*bw, elems]."""
     NT, D, H, W, C = src.shape
-    out = np.zeros((bh, bw, 64), dtype=np.uint16)
+    out = np.zeros((bh, bw, elems), dtype=np.uint16)
     if 0 <= dp < D:
         for i in range(bh):
             h = ch + i
             if not 0 <= h < H:
                 continue
             w_lo, w_hi = max(cw, 0), min(cw + bw, W)
-            c_hi = min(cc + 64, C)
+            c_hi = min(cc + elems, C)
             if w_lo < w_hi and cc < c_hi:
                 out[i, w_lo - cw:w_hi - cw, :c_hi - cc] = src[n, dp, h, w_lo:w_hi, cc:c_hi]
-    return out.reshape(bh * bw, 64)
+    return out.reshape(bh * bw, elems)
 
 
 def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", region=None):
@@ -55,6 +63,8 @@ def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", r
                                                                   "cout_per_half", "nblk", "wblock_bytes"))
     TW = min(W, 128)
     TH = 128 // TW
+    elems = plan.get("row_bytes", 128) // 2
+    rb = elems * 2
     nchunk0 = (c0 + 63) // 64
     xs = (x0.view(np.uint16), None if x1 is None else x1.view(np.uint16))
     w16 = np.frombuffer(wpack.tobytes(), dtype=np.uint16)
@@ -94,11 +104,11 @@ def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", r
                                 cw, bw, bh = w0, TW, TH
                             ch = h0 + kh - 1
                             for dp in range(dlo, dhi + 1):
-                                stage = _swizzled_store(_box(src, n, dp, ch, cw, cc, bh, bw))
+                                stage = _swizzled_store(_box(src, n, dp, ch, cw, cc, bh, bw, elems))
                                 a_first = dp - kdhi + 1 - d0
                                 ti_lo, ti_hi = max(0, -a_first), min(nkd - 1, rv - 1 - a_first)
                                 for kw in range(nkw):
-                                    A = _read_operand(stage, kw * 128, 128).view(f16).astype(np.float32)
+                                    A = _read_operand(stage, kw * rb, 128, elems).view(f16).astype(np.float32)
                                     A[:, k16_steps * 16:] = 0
                                     ti = ti_lo
                                     while ti <= ti_hi:
@@ -107,7 +117,7 @@ def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", r
                                         ln = 1
                                         while ti + ln <= ti_hi and touched[a0 + ln] == f and (ln + 1) * cph <= 256:
                                             ln += 1
-                                        Bm = _read_operand(blk, (kw * nkd + ti) * cph * 128, ln * cph)
+                                        Bm = _read_operand(blk, (kw * nkd + ti) * cph * rb, ln * cph, elems)
                                         Bm = Bm.view(f16).astype(np.float32)
                                         prod = A @ Bm.T  # [128, ln*cph]
                                         for j in range(ln):

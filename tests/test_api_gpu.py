@@ -7,6 +7,7 @@ import torch
 from helpers import write_seg_config
 
 pytestmark = pytest.mark.gpu
+NET = (40, 48, 44)  # network lattice: every pyramid level keeps >= 2 samples per axis (torch's avg_pool3d needs it)
 
 
 def _cuda():
@@ -24,7 +25,7 @@ def _small_setup(tmp_path):
     cfg = write_seg_config(tmp_path, sd, [64, 128, 16], True, True, (8, 16, 4))
     rsd = reg_oracle.make_gradicon_state_dict(77)
     model = pretrained_models.OAI_knees_gradICON_model(pretrained=False)
-    model.assign_identity_map([1, 1, 24, 40, 36])
+    model.assign_identity_map([1, 1, *NET])
     model.load_state_dict(rsd, strict=True)
     img = itk_compat.Image(seg_oracle.synthetic_knee(shape, 3), spacing=(0.4, 0.35, 0.8), origin=(-5, 2, 1))
     atlas = itk_compat.Image(seg_oracle.synthetic_knee(shape, 4), spacing=(0.4, 0.35, 0.8), origin=(-4, 3, 0))
@@ -46,12 +47,12 @@ def test_analysis_object_segment_register_and_deform(tmp_path, capsys):
     phi = ao.register(img)                                    # analysis_object.py:47-49 -> registration.py:22-27
     assert "fixed range" in capsys.readouterr().out           # the reference prints the intensity ranges
     # transform parity: same points through the oracle's composite transform built from the oracle's own maps
-    ref_AB, _ = reg_oracle.register_pair_maps(rsd, img.array, atlas.array, (24, 40, 36))
+    ref_AB, _ = reg_oracle.register_pair_maps(rsd, img.array, atlas.array, NET)
     gA = warp_oracle.Geometry(shape[::-1], img.spacing, img.origin)
     gB = warp_oracle.Geometry(shape[::-1], atlas.spacing, atlas.origin)
-    tr_ref = warp_oracle.CompositeTransform(reg_oracle.displacement_field_xyz(ref_AB, (24, 40, 36)), gA, gB)
+    tr_ref = warp_oracle.CompositeTransform(reg_oracle.displacement_field_xyz(ref_AB, NET), gA, gB)
     rng = np.random.default_rng(0)
-    pts = gB.index_to_physical(rng.uniform(2, 20, (2000, 3)) * np.array([3.0, 6.0, 1.0]))
+    pts = gB.index_to_physical(rng.uniform(2, 20, (2000, 3)) * np.array([3.0, 6.0, 1.0]))  # x<72, y<136, z<24
     d = np.abs(phi.transform_points(pts) - tr_ref.transform_points(pts)).max()
     assert d < 1e-3, f"warped points differ by {d} mm"
     # deform_probmap (dask_processing.py:95-111) against the ITK-semantics oracle
