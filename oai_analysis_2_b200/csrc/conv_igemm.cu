@@ -255,24 +255,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           const int ti_hi = min(bi.ns - 1, ui.ra - 1 - a_first);
           const int nt = ti_hi - ti_lo + 1;
           const uint32_t span = ((1u << nt) - 1u) << (a_first + ti_lo);
-          if ((touched & span) == span && !p.base_off_mode && !p.no_fast_path) {
-            // steady state: every accumulator of the stack already holds a partial sum -> MMAs of N = (up to
-            // 256/cout taps)*cout per (kw, k16); descriptors differ from the stage base by constants only
+          if (!p.base_off_mode && !p.no_fast_path) {
+            // MMAs of N = (up to 256/cout taps)*cout per (kw, k16); descriptors differ from the stage base by
+            // constants only.  Accumulators seeing their first MMA of the unit (overwrite instead of accumulate)
+            // only change the very first (kw = 0, k16 = 0) issue of their group, which is split per run.
+            const uint32_t fresh = span & ~touched;
+            if (fresh) {
+              for (int a = a_first + ti_lo; a <= a_first + ti_hi; ++a)
+                if ((fresh >> a) & 1u) mbar_wait(&acc_empty[a], ((use_bits >> a) & 1u) ^ 1u, 500 + a);
+              tc_fence_after();
+            }
             const int per = max(1, 256 / p.cout);
             const uint32_t a_lo = (a_base & 0x3FFFF) >> 4;
             const uint32_t b_kw = (static_cast<uint32_t>(bi.ns) * cout128) >> 4;
             const bool leader = elect_one();
             for (int g0 = 0; g0 < nt; g0 += per) {
-              const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(min(per, nt - g0) * p.cout), p.ab_format);
-              const uint32_t d_addr = tmem_base + static_cast<uint32_t>((a_first + ti_lo + g0) * p.cout);
+              const int ng = min(per, nt - g0), ga = a_first + ti_lo + g0;
+              const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(ng * p.cout), p.ab_format);
+              const uint32_t d_addr = tmem_base + static_cast<uint32_t>(ga * p.cout);
               const uint32_t b_lo = ((w_base + static_cast<uint32_t>(ti_lo + g0) * cout128) & 0x3FFFF) >> 4;
+              const uint32_t gfresh = (fresh >> ga) & ((1u << ng) - 1u);
               if (leader) {
+                if (gfresh) {
+                  // first issue, split into runs of equal state
+                  int j = 0;
+                  while (j < ng) {
+                    const uint32_t f = (gfresh >> j) & 1u;
+                    int len = 1;
+                    while (j + len < ng && ((gfresh >> (j + len)) & 1u) == f) ++len;
+                    umma_f16_ss(d_addr + static_cast<uint32_t>(j * p.cout), desc_hi | a_lo,
+                                desc_hi | (b_lo + ((static_cast<uint32_t>(j) * cout128) >> 4)),
+                                umma_idesc_f16(128, static_cast<uint32_t>(len * p.cout), p.ab_format), f ? 0u : 1u);
+                    j += len;
+                  }
+                }
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
                   if (kw < nkw) {
 #pragma unroll
                     for (int k16 = 0; k16 < 4; ++k16) {
-                      if (k16 < p.k16_steps)
+                      if (k16 < p.k16_steps && !(gfresh && kw == 0 && k16 == 0))
                         umma_f16_ss(d_addr, desc_hi | (a_lo + kw * kw_step + k16 * 2),
                                     desc_hi | (b_lo + kw * b_kw + k16 * 2), idesc, 1u);
                     }
@@ -281,6 +303,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               }
             }
             __syncwarp();
+            touched |= span;
           } else {
             // first touch of an accumulator (overwrite instead of accumulate), N > 256 stacks, or the debug
             // base-offset mode: general grouping
