@@ -224,68 +224,79 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------ MMA issuer
-    // The whole warp walks the (warp-uniform) schedule so the compiler keeps descriptors in uniform registers; one
-    // elected lane issues tcgen05.mma / tcgen05.commit.  The issue thread is the critical resource of this kernel
-    // (one MMA per ~100 tensor-pipe cycles), so the steady state is a fully unrolled sequence of descriptor adds.
+    // The whole warp walks the (warp-uniform) schedule so the compiler keeps everything in uniform registers; one
+    // elected lane issues tcgen05.mma / tcgen05.commit.  This thread is the critical resource of the kernel: the
+    // tensor pipe retires an N=192 MMA every 96 clocks, so the per-stage bookkeeping below is kept to a handful of
+    // integer ops (block indices are counters, descriptors are "stage base + constant", no divisions, no re-reads
+    // of kernel parameters).
+    const int mode = p.mode, R_acc = p.R, cout = p.cout, nblk = p.nblk, k16n = p.k16_steps, nst = p.n_astage,
+              nwb = p.n_wbuf, Dm1 = p.D - 1, kpb = p.kd_per_block;
+    const bool general = p.base_off_mode || p.no_fast_path;
+    const uint32_t rowb = static_cast<uint32_t>(p.row_bytes), sbo = 8u * rowb, lay = rowb == 128u ? 2u : 4u;
+    const uint32_t cout128 = static_cast<uint32_t>(cout) * rowb;    // bytes of one tap's weight rows
+    const uint32_t tap16 = cout128 >> 4;                             // ... in descriptor units
+    const uint32_t kw_step = rowb >> 4;                              // descriptor units per one-voxel row shift
+    const uint32_t desc_hi32 = (sbo >> 4) | (1u << 14) | (lay << 29);  // SBO, version = 1, swizzle mode
+    const uint32_t a_lo0 = ((smem_u32(abuf) & 0x3FFFF) >> 4) | (1u << 16), a_step = p.astage_stride >> 4;
+    const uint32_t w_lo0 = ((smem_u32(wbuf) & 0x3FFFF) >> 4) | (1u << 16), w_step = wstride >> 4;
+    const int per = max(1, 256 / cout);
+    const uint32_t idesc_1 = umma_idesc_f16(128, static_cast<uint32_t>(cout), p.ab_format);
+    const uint32_t idesc_step = static_cast<uint32_t>(cout >> 3) << 17;  // +1 tap in the N field
     int stage = 0, wb = 0;
     uint32_t aphase = 0, wphase = 0, use_bits = 0;  // use_bits: per-accumulator mbarrier phase (flips per use)
-    // one voxel's K slice is a row of row_bytes (128 B / SWIZZLE_128B or 64 B / SWIZZLE_64B); 8-row swizzle atoms
-    const uint32_t rowb = static_cast<uint32_t>(p.row_bytes), sbo = 8u * rowb, lay = rowb == 128u ? 2u : 4u;
-    const uint32_t cout128 = static_cast<uint32_t>(p.cout) * rowb;  // bytes of one tap's weight rows
-    const uint32_t kw_step = rowb >> 4;                              // descriptor units per one-voxel row shift
-    const uint64_t desc_hi = (static_cast<uint64_t>(sbo >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
-                             (static_cast<uint64_t>(lay) << 61) | (static_cast<uint64_t>(1) << 16);
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
       const UnitInfo ui = decode_unit(p, u);
+      const int d0 = ui.d0, ra = ui.ra, rd = ui.rd;
       uint32_t touched = 0, signaled = 0;
-      for (int b = 0; b < p.nblk; ++b) {
-        const BlockInfo bi = decode_block(p, b);
-        const int kdhi = bi.kdlo + bi.nkd - 1;
-        const int dlo = max(0, ui.d0 + bi.kdlo - 1);
-        const int dhi = min(p.D - 1, ui.d0 + ui.rd - 1 + kdhi - 1);
+      int kd_it = 0;  // kd counter of the one-kd-per-block schedule (fastest block index there)
+      for (int b = 0; b < nblk; ++b) {
+        // taps stacked in this block and the input slices it walks (same arithmetic as decode_block, by counters)
+        int kdlo = 0, nkd = 3;
+        if (mode == kModePointwise || mode == kModeUp2) { kdlo = 1; nkd = 1; }
+        else if (mode == kModePerTap && kpb == 1) { kdlo = kd_it; nkd = 1; kd_it = kd_it == 2 ? 0 : kd_it + 1; }
+        const int ns = (mode == kModeUp2) ? R_acc : nkd;
+        const int kdhi = kdlo + nkd - 1;
+        const int dlo = max(0, d0 + kdlo - 1);
+        const int dhi = min(Dm1, d0 + rd - 1 + kdhi - 1);
         mbar_wait(&full_w[wb], wphase, 300 + wb);
-        const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
-        for (int dp = dlo; dp <= dhi; ++dp) {
+        const uint32_t w_lo = w_lo0 + static_cast<uint32_t>(wb) * w_step;
+        const uint32_t b_kw = static_cast<uint32_t>(ns) * tap16;
+        int a_first = (mode == kModeUp2) ? 0 : dlo - kdhi + 1 - d0;  // accumulator hit by the first stacked tap
+        for (int dp = dlo; dp <= dhi; ++dp, a_first += (mode == kModeUp2 ? 0 : 1)) {
           mbar_wait(&full_a[stage], aphase, 400 + stage);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
-          // accumulator hit by the first stacked tap (highest kd; tap 0 of the group for kModeUp2)
-          const int a_first = (p.mode == kModeUp2) ? 0 : dp - kdhi + 1 - ui.d0;
-          const int ti_lo = max(0, -a_first);
-          const int ti_hi = min(bi.ns - 1, ui.ra - 1 - a_first);
+          const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step;
+          const int ti_lo = a_first < 0 ? -a_first : 0;
+          const int ti_hi = min(ns - 1, ra - 1 - a_first);
           const int nt = ti_hi - ti_lo + 1;
-          const uint32_t span = ((1u << nt) - 1u) << (a_first + ti_lo);
-          if (!p.base_off_mode && !p.no_fast_path) {
-            // MMAs of N = (up to 256/cout taps)*cout per (kw, k16); descriptors differ from the stage base by
-            // constants only.  Accumulators seeing their first MMA of the unit (overwrite instead of accumulate)
-            // only change the very first (kw = 0, k16 = 0) issue of their group, which is split per run.
-            const uint32_t fresh = span & ~touched;
+          const int acc0 = a_first + ti_lo;
+          const uint32_t span = ((1u << nt) - 1u) << acc0;
+          const uint32_t fresh = span & ~touched;
+          if (!general) {
             if (fresh) {
-              for (int a = a_first + ti_lo; a <= a_first + ti_hi; ++a)
+              // accumulators seeing their first MMA of the unit: wait until the epilogue has drained their previous
+              // contents; their very first issue (kw = 0, k16 = 0) overwrites instead of accumulating
+              for (int a = acc0; a < acc0 + nt; ++a)
                 if ((fresh >> a) & 1u) mbar_wait(&acc_empty[a], ((use_bits >> a) & 1u) ^ 1u, 500 + a);
               tc_fence_after();
             }
-            const int per = max(1, 256 / p.cout);
-            const uint32_t a_lo = (a_base & 0x3FFFF) >> 4;
-            const uint32_t b_kw = (static_cast<uint32_t>(bi.ns) * cout128) >> 4;
             const bool leader = elect_one();
             for (int g0 = 0; g0 < nt; g0 += per) {
-              const int ng = min(per, nt - g0), ga = a_first + ti_lo + g0;
-              const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(ng * p.cout), p.ab_format);
-              const uint32_t d_addr = tmem_base + static_cast<uint32_t>(ga * p.cout);
-              const uint32_t b_lo = ((w_base + static_cast<uint32_t>(ti_lo + g0) * cout128) & 0x3FFFF) >> 4;
-              const uint32_t gfresh = (fresh >> ga) & ((1u << ng) - 1u);
+              const int ng = min(per, nt - g0);
+              const uint32_t idesc = idesc_1 + static_cast<uint32_t>(ng - 1) * idesc_step;
+              const uint32_t d_addr = tmem_base + static_cast<uint32_t>((acc0 + g0) * cout);
+              const uint32_t b_lo = w_lo + static_cast<uint32_t>(ti_lo + g0) * tap16;
+              const uint32_t gfresh = (fresh >> (acc0 + g0)) & ((1u << ng) - 1u);
               if (leader) {
                 if (gfresh) {
-                  // first issue, split into runs of equal state
-                  int j = 0;
+                  int j = 0;  // first issue of the group, split into runs of equal state
                   while (j < ng) {
                     const uint32_t f = (gfresh >> j) & 1u;
                     int len = 1;
                     while (j + len < ng && ((gfresh >> (j + len)) & 1u) == f) ++len;
-                    umma_f16_ss(d_addr + static_cast<uint32_t>(j * p.cout), desc_hi | a_lo,
-                                desc_hi | (b_lo + ((static_cast<uint32_t>(j) * cout128) >> 4)),
-                                umma_idesc_f16(128, static_cast<uint32_t>(len * p.cout), p.ab_format), f ? 0u : 1u);
+                    umma_f16_ss_lohi(d_addr + static_cast<uint32_t>(j * cout), a_lo,
+                                     b_lo + static_cast<uint32_t>(j) * tap16, desc_hi32,
+                                     idesc_1 + static_cast<uint32_t>(len - 1) * idesc_step, f ? 0u : 1u);
                     j += len;
                   }
                 }
@@ -294,9 +305,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                   if (kw < nkw) {
 #pragma unroll
                     for (int k16 = 0; k16 < 4; ++k16) {
-                      if (k16 < p.k16_steps && !(gfresh && kw == 0 && k16 == 0))
-                        umma_f16_ss(d_addr, desc_hi | (a_lo + kw * kw_step + k16 * 2),
-                                    desc_hi | (b_lo + kw * b_kw + k16 * 2), idesc, 1u);
+                      if (k16 < k16n && !(gfresh && kw == 0 && k16 == 0))
+                        umma_f16_ss_lohi(d_addr, a_lo + kw * kw_step + k16 * 2, b_lo + kw * b_kw + k16 * 2,
+                                         desc_hi32, idesc, 1u);
                     }
                   }
                 }
@@ -305,29 +316,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             __syncwarp();
             touched |= span;
           } else {
-            // first touch of an accumulator (overwrite instead of accumulate), N > 256 stacks, or the debug
-            // base-offset mode: general grouping
+            // debug / A-B path: one group per run of equal accumulator state, descriptors rebuilt per MMA
+            const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
+            const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
             for (int kw = 0; kw < nkw; ++kw) {
               int ti = ti_lo;
               while (ti <= ti_hi) {
                 const int a0 = a_first + ti;
                 const uint32_t f = (touched >> a0) & 1u;
                 int len = 1;
-                while (ti + len <= ti_hi && ((touched >> (a0 + len)) & 1u) == f && (len + 1) * p.cout <= 256) ++len;
+                while (ti + len <= ti_hi && ((touched >> (a0 + len)) & 1u) == f && (len + 1) * cout <= 256) ++len;
                 if (!f) {
                   for (int j = 0; j < len; ++j)
                     mbar_wait(&acc_empty[a0 + j], ((use_bits >> (a0 + j)) & 1u) ^ 1u, 500 + a0 + j);
                   tc_fence_after();
                 }
-                const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * p.cout), p.ab_format);
+                const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * cout), p.ab_format);
                 const uint32_t a_addr = a_base + static_cast<uint32_t>(kw) * rowb;
-                const uint32_t b_addr = w_base + static_cast<uint32_t>(kw * bi.ns + ti) * cout128;
+                const uint32_t b_addr = w_base + static_cast<uint32_t>(kw * ns + ti) * cout128;
                 const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
-                const uint32_t d_addr = tmem_base + static_cast<uint32_t>(a0 * p.cout);
+                const uint32_t d_addr = tmem_base + static_cast<uint32_t>(a0 * cout);
                 if (elect_one()) {
 #pragma unroll
                   for (int k16 = 0; k16 < 4; ++k16) {
-                    if (k16 < p.k16_steps) {
+                    if (k16 < k16n) {
                       const uint64_t adesc = umma_desc_kmajor(a_addr + k16 * 32, sbo, boff, lay);
                       const uint64_t bdesc = umma_desc_kmajor(b_addr + k16 * 32, sbo, 0, lay);
                       umma_f16_ss(d_addr, adesc, bdesc, idesc, (f | (k16 > 0)) ? 1u : 0u);
@@ -340,31 +352,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               }
             }
           }
-          const bool last_block = (b == p.nblk - 1) && a_first >= 0 && a_first < ui.ra;
+          const bool last_block = (b == nblk - 1) && a_first >= 0 && a_first < ra;
           if (elect_one()) {
             umma_commit(&empty_a[stage]);
             if (last_block) umma_commit(&acc_full[a_first]);
           }
           __syncwarp();
           if (last_block) signaled |= 1u << a_first;
-          if (++stage == p.n_astage) {
+          if (++stage == nst) {
             stage = 0;
             aphase ^= 1u;
           }
         }
         if (elect_one()) umma_commit(&empty_w[wb]);
         __syncwarp();
-        if (++wb == p.n_wbuf) {
+        if (++wb == nwb) {
           wb = 0;
           wphase ^= 1u;
         }
       }
       if (elect_one()) {
-        for (int a = 0; a < ui.ra; ++a)
+        for (int a = 0; a < ra; ++a)
           if (!((signaled >> a) & 1u)) umma_commit(&acc_full[a]);
       }
       __syncwarp();
-      use_bits ^= (1u << ui.ra) - 1u;
+      use_bits ^= (1u << ra) - 1u;
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
