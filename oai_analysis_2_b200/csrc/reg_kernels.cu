@@ -614,43 +614,46 @@ __device__ __forceinline__ float tri_sample(const float* __restrict__ v, const T
          tz * ((1.f - ty) * ((1.f - tx) * v100 + tx * v101) + ty * ((1.f - tx) * v110 + tx * v111));
 }
 
-// A thread carries kChainVX x-adjacent grid points through the whole chain: the independent gather sequences overlap
-// and the map / warped image are written with vector stores.
-constexpr int kChainVX = 4;
-__global__ void __launch_bounds__(256, 2) chain_kernel(const ChainParams p) {
+// Thread mapping: a warp owns 32 x-adjacent grid points of one row, so every gather and every store of the warp
+// touches a few 128-byte lines; a block owns 8 consecutive rows; a thread carries kChainVZ z-adjacent points through
+// the whole chain (independent gather sequences in flight; the z+1 plane of point i is the z plane of point i+1).
+template <int kChainVZ, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) chain_kernel(const ChainParams p) {
   const long long nvox = static_cast<long long>(p.D) * p.H * p.W;
   const double sz = 1.0 / (p.D - 1), sy = 1.0 / (p.H - 1), sx = 1.0 / (p.W - 1);
-  const int nxg = (p.W + kChainVX - 1) / kChainVX;
-  const long long ngroups = static_cast<long long>(p.D) * p.H * nxg;
-  const bool vec = (p.W % kChainVX) == 0 && (!p.phi_out || (reinterpret_cast<uintptr_t>(p.phi_out) & 15) == 0) &&
-                   (!p.img_out || (reinterpret_cast<uintptr_t>(p.img_out) & 15) == 0);
-  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < ngroups;
-       g += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x0 = static_cast<int>(g % nxg) * kChainVX;
-    const int y = static_cast<int>((g / nxg) % p.H), z = static_cast<int>(g / (static_cast<long long>(nxg) * p.H));
-    const long long v0 = (static_cast<long long>(z) * p.H + y) * p.W + x0;
-    float cz[kChainVX], cy[kChainVX], cx[kChainVX];
+  const int nbx = (p.W + 31) / 32, nby = (p.H + 7) / 8, nbz = (p.D + kChainVZ - 1) / kChainVZ;
+  const long long ntiles = static_cast<long long>(nbx) * nby * nbz;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int x = static_cast<int>(tile % nbx) * 32 + lane;
+    const int y = static_cast<int>((tile / nbx) % nby) * 8 + wrp;
+    const int z0 = static_cast<int>(tile / (static_cast<long long>(nbx) * nby)) * kChainVZ;
+    if (x >= p.W || y >= p.H) continue;
+    float cz[kChainVZ], cy[kChainVZ], cx[kChainVZ];
+    const long long v0 = (static_cast<long long>(z0) * p.H + y) * p.W + x, zs = static_cast<long long>(p.H) * p.W;
+    auto vof = [&](int i) { return v0 + min(i, p.D - 1 - z0) * zs; };
 #pragma unroll
-    for (int i = 0; i < kChainVX; ++i) {
+    for (int i = 0; i < kChainVZ; ++i) {
+      const int z = min(z0 + i, p.D - 1);
       cz[i] = static_cast<float>(z * sz);
       cy[i] = static_cast<float>(y * sy);
-      cx[i] = static_cast<float>(min(x0 + i, p.W - 1) * sx);
+      cx[i] = static_cast<float>(x * sx);
     }
     for (int f = 0; f < p.nfields; ++f) {
       const float* u = p.u[f];
       const size_t plane = static_cast<size_t>(p.ud[f]) * p.uh[f] * p.uw[f];
       if (f == 0 && p.shortcut_first) {
 #pragma unroll
-        for (int i = 0; i < kChainVX; ++i) {
-          const long long v = v0 + min(i, p.W - 1 - x0);
+        for (int i = 0; i < kChainVZ; ++i) {
+          const long long v = vof(i);
           cz[i] += __ldg(u + v); cy[i] += __ldg(u + plane + v); cx[i] += __ldg(u + 2 * plane + v);
         }
       } else {
-        Tri q[kChainVX];
+        Tri q[kChainVZ];
 #pragma unroll
-        for (int i = 0; i < kChainVX; ++i) q[i] = tri_setup(cz[i], cy[i], cx[i], p.ud[f], p.uh[f], p.uw[f]);
+        for (int i = 0; i < kChainVZ; ++i) q[i] = tri_setup(cz[i], cy[i], cx[i], p.ud[f], p.uh[f], p.uw[f]);
 #pragma unroll
-        for (int i = 0; i < kChainVX; ++i) {
+        for (int i = 0; i < kChainVZ; ++i) {
           const float dz = tri_sample(u, q[i], p.uh[f], p.uw[f]);
           const float dy = tri_sample(u + plane, q[i], p.uh[f], p.uw[f]);
           const float dx = tri_sample(u + 2 * plane, q[i], p.uh[f], p.uw[f]);
@@ -658,30 +661,22 @@ __global__ void __launch_bounds__(256, 2) chain_kernel(const ChainParams p) {
         }
       }
     }
-    float img[kChainVX];
+    float img[kChainVZ];
     if (p.img_out) {
 #pragma unroll
-      for (int i = 0; i < kChainVX; ++i) {
+      for (int i = 0; i < kChainVZ; ++i) {
         const Tri q = tri_setup(cz[i], cy[i], cx[i], p.id, p.ih, p.iw);
         img[i] = tri_sample(p.img, q, p.ih, p.iw);
       }
     }
-    if (vec) {
-      if (p.phi_out) {
-        *reinterpret_cast<float4*>(p.phi_out + v0) = make_float4(cz[0], cz[1], cz[2], cz[3]);
-        *reinterpret_cast<float4*>(p.phi_out + nvox + v0) = make_float4(cy[0], cy[1], cy[2], cy[3]);
-        *reinterpret_cast<float4*>(p.phi_out + 2 * nvox + v0) = make_float4(cx[0], cx[1], cx[2], cx[3]);
-      }
-      if (p.img_out) *reinterpret_cast<float4*>(p.img_out + v0) = make_float4(img[0], img[1], img[2], img[3]);
-    } else {
 #pragma unroll
-      for (int i = 0; i < kChainVX; ++i) {
-        if (x0 + i >= p.W) break;
-        if (p.phi_out) {
-          p.phi_out[v0 + i] = cz[i]; p.phi_out[nvox + v0 + i] = cy[i]; p.phi_out[2 * nvox + v0 + i] = cx[i];
-        }
-        if (p.img_out) p.img_out[v0 + i] = img[i];
+    for (int i = 0; i < kChainVZ; ++i) {
+      if (z0 + i >= p.D) break;
+      const long long v = v0 + i * zs;
+      if (p.phi_out) {
+        p.phi_out[v] = cz[i]; p.phi_out[nvox + v] = cy[i]; p.phi_out[2 * nvox + v] = cx[i];
       }
+      if (p.img_out) p.img_out[v] = img[i];
     }
   }
 }
@@ -791,61 +786,63 @@ struct TriF {
   int i0[3], i1[3];
   float t[3];
 };
+// floor / fractional split of a lattice coordinate without the slow fp64 conversion instructions (FRND, F2I, I2F):
+// adding 1.5 * 2^52 leaves round-to-nearest(s) in the low mantissa word (|s| < 2^31); the remainder s - rn(s) is exact
+// in fp64, lies in [-0.5, 0.5] and is folded back to [0, 1) in fp32.
 __device__ __forceinline__ TriF trif_setup(const double s[3], const int n[3]) {
   TriF r;
+  const double magic = 6755399441055744.0;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const double f = floor(s[a]);
-    r.t[a] = static_cast<float>(s[a] - f);
-    const int b = static_cast<int>(f);
+    const double m = s[a] + magic;
+    int b = __double2loint(m);
+    float d = static_cast<float>(s[a] - (m - magic));
+    if (d < 0.f) { d += 1.f; b -= 1; }
+    r.t[a] = d;
     r.i0[a] = min(max(b, 0), n[a] - 1);
     r.i1[a] = min(max(b + 1, 0), n[a] - 1);
   }
   return r;
 }
 
-// A thread resamples VX x-adjacent output voxels: the index->lattice affine is evaluated once in fp64 and stepped
-// along x, the VX independent gather chains overlap (memory-level parallelism), and every channel is written with
-// one vector store.  Coordinates stay fp64 (ITK computes in double); interpolation weights / sums are fp32.
-constexpr int kWarpVX = 4;
-__global__ void __launch_bounds__(256) warp_volume_kernel(const WarpVolumeParams p) {
+// Tile = 32 (x) x 8 (y) x kWarpVZ (z) output voxels per block; lane <-> x, so the gathers and stores of a warp fall
+// in a few 128-byte lines and neighbouring warps (rows) share them through L1.  A thread carries kWarpVZ z-adjacent
+// voxels (1 in the shipped instantiation: at 40 registers 6 blocks / SM are resident, which beat carrying 2 or 4
+// voxels per thread at lower occupancy, and staging the tile's field box in shared memory was slower than L1;
+// profiles/r01_warp_variants.txt).  The kernel is issue-bound on the fp64 coordinate math and address arithmetic.  Coordinates stay fp64 (ITK computes in double); interpolation weights and
+// sums are fp32.
+template <int kWarpVZ, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) warp_volume_kernel(const WarpVolumeParams p) {
   const long long nvox = static_cast<long long>(p.OD) * p.OH * p.OW;
   const size_t splane = static_cast<size_t>(p.SD) * p.SH * p.SW;
-  const int nxg = (p.OW + kWarpVX - 1) / kWarpVX;
-  const long long ngroups = static_cast<long long>(p.OD) * p.OH * nxg;
   const int nf[3] = {p.FW, p.FH, p.FD}, ns[3] = {p.SW, p.SH, p.SD};
-  const bool vec_store = (p.OW % kWarpVX) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
-  for (long long gidx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; gidx < ngroups;
-       gidx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x0 = static_cast<int>(gidx % nxg) * kWarpVX;
-    const int y = static_cast<int>((gidx / nxg) % p.OH), z = static_cast<int>(gidx / (static_cast<long long>(nxg) * p.OH));
-    const double j0[3] = {static_cast<double>(x0), static_cast<double>(y), static_cast<double>(z)};
-    double qb[3];
-    affine_apply(p.out_index_to_net, j0, qb);
-    // ---- displacement at the VX lattice points
-    double q[kWarpVX][3];
-    TriF tf[kWarpVX];
-    bool fin[kWarpVX];
+  const int nbx = (p.OW + 31) / 32, nby = (p.OH + 7) / 8;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int tx0 = static_cast<int>(blockIdx.x % nbx) * 32, ty0 = static_cast<int>((blockIdx.x / nbx) % nby) * 8;
+  const int tz0 = static_cast<int>(blockIdx.x / (nbx * nby)) * kWarpVZ;
+  const int x = tx0 + lane, y = ty0 + wrp;
+  if (x >= p.OW || y >= p.OH) return;
+  // ---- displacement at the kWarpVZ lattice points
+  double q[kWarpVZ][3];
+  float dsp[kWarpVZ][3];
 #pragma unroll
-    for (int i = 0; i < kWarpVX; ++i) {
+  for (int i = 0; i < kWarpVZ; ++i) {
+    const double j[3] = {static_cast<double>(x), static_cast<double>(y),
+                         static_cast<double>(min(tz0 + i, p.OD - 1))};
+    affine_apply(p.out_index_to_net, j, q[i]);
+    bool fin = true;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) q[i][a] = qb[a] + i * p.out_index_to_net.m[3 * a];
-      fin[i] = true;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) fin[i] = fin[i] && q[i][a] >= -0.5 && q[i][a] < nf[a] - 0.5;
-      tf[i] = trif_setup(q[i], nf);
-    }
-    float dsp[kWarpVX][3];
-#pragma unroll
-    for (int i = 0; i < kWarpVX; ++i) {
-      dsp[i][0] = dsp[i][1] = dsp[i][2] = 0.f;
-      if (fin[i]) {
+    for (int a = 0; a < 3; ++a) fin = fin && q[i][a] >= -0.5 && q[i][a] < p.fhi[a];
+    dsp[i][0] = dsp[i][1] = dsp[i][2] = 0.f;
+    if (fin) {
+      const TriF tf = trif_setup(q[i], nf);
+      {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const int ix = (c & 1) ? tf[i].i1[0] : tf[i].i0[0], iy = (c & 2) ? tf[i].i1[1] : tf[i].i0[1],
-                    iz = (c & 4) ? tf[i].i1[2] : tf[i].i0[2];
-          const float w = ((c & 1) ? tf[i].t[0] : 1.f - tf[i].t[0]) * ((c & 2) ? tf[i].t[1] : 1.f - tf[i].t[1]) *
-                          ((c & 4) ? tf[i].t[2] : 1.f - tf[i].t[2]);
+          const int ix = (c & 1) ? tf.i1[0] : tf.i0[0], iy = (c & 2) ? tf.i1[1] : tf.i0[1],
+                    iz = (c & 4) ? tf.i1[2] : tf.i0[2];
+          const float w = ((c & 1) ? tf.t[0] : 1.f - tf.t[0]) * ((c & 2) ? tf.t[1] : 1.f - tf.t[1]) *
+                          ((c & 4) ? tf.t[2] : 1.f - tf.t[2]);
           const float* e = p.disp + ((static_cast<size_t>(iz) * p.FH + iy) * p.FW + ix) * 3;
           dsp[i][0] = fmaf(w, __ldg(e), dsp[i][0]);
           dsp[i][1] = fmaf(w, __ldg(e + 1), dsp[i][1]);
@@ -853,49 +850,46 @@ __global__ void __launch_bounds__(256) warp_volume_kernel(const WarpVolumeParams
         }
       }
     }
-    // ---- source index, inside test, interpolation set-up
-    TriF ts[kWarpVX];
-    bool sin[kWarpVX];
+  }
+  // ---- source index, inside test, interpolation set-up
+  TriF ts[kWarpVZ];
+  bool sin[kWarpVZ];
 #pragma unroll
-    for (int i = 0; i < kWarpVX; ++i) {
-      const double qd[3] = {q[i][0] + dsp[i][0], q[i][1] + dsp[i][1], q[i][2] + dsp[i][2]};
-      double sidx[3];
-      affine_apply(p.net_to_src_index, qd, sidx);
-      sin[i] = x0 + i < p.OW;
+  for (int i = 0; i < kWarpVZ; ++i) {
+    const double qd[3] = {q[i][0] + dsp[i][0], q[i][1] + dsp[i][1], q[i][2] + dsp[i][2]};
+    double sidx[3];
+    affine_apply(p.net_to_src_index, qd, sidx);
+    sin[i] = true;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) sin[i] = sin[i] && sidx[a] >= -0.5 && sidx[a] < ns[a] - 0.5;
-      ts[i] = trif_setup(sidx, ns);
-    }
-    const long long v0 = (static_cast<long long>(z) * p.OH + y) * p.OW + x0;
-    for (int c = 0; c < p.C; ++c) {
-      const float* src = p.src + c * splane;
-      float o[kWarpVX];
+    for (int a = 0; a < 3; ++a) sin[i] = sin[i] && sidx[a] >= -0.5 && sidx[a] < p.shi[a];
+    ts[i] = trif_setup(sidx, ns);
+  }
+  const long long v0 = (static_cast<long long>(tz0) * p.OH + y) * p.OW + x;
+  const long long zstride = static_cast<long long>(p.OH) * p.OW;
+  for (int c = 0; c < p.C; ++c) {
+    const float* src = p.src + c * splane;
+    float o[kWarpVZ];
 #pragma unroll
-      for (int i = 0; i < kWarpVX; ++i) {
-        float acc = 0.f;
-        if (sin[i]) {
+    for (int i = 0; i < kWarpVZ; ++i) {
+      float acc = 0.f;
+      if (sin[i]) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int ix = (k & 1) ? ts[i].i1[0] : ts[i].i0[0], iy = (k & 2) ? ts[i].i1[1] : ts[i].i0[1],
-                      iz = (k & 4) ? ts[i].i1[2] : ts[i].i0[2];
-            const float w = ((k & 1) ? ts[i].t[0] : 1.f - ts[i].t[0]) * ((k & 2) ? ts[i].t[1] : 1.f - ts[i].t[1]) *
-                            ((k & 4) ? ts[i].t[2] : 1.f - ts[i].t[2]);
-            acc = fmaf(w, __ldg(src + (static_cast<size_t>(iz) * p.SH + iy) * p.SW + ix), acc);
-          }
-        } else {
-          acc = p.default_value;
+        for (int k = 0; k < 8; ++k) {
+          const int ix = (k & 1) ? ts[i].i1[0] : ts[i].i0[0], iy = (k & 2) ? ts[i].i1[1] : ts[i].i0[1],
+                    iz = (k & 4) ? ts[i].i1[2] : ts[i].i0[2];
+          const float w = ((k & 1) ? ts[i].t[0] : 1.f - ts[i].t[0]) * ((k & 2) ? ts[i].t[1] : 1.f - ts[i].t[1]) *
+                          ((k & 4) ? ts[i].t[2] : 1.f - ts[i].t[2]);
+          acc = fmaf(w, __ldg(src + (static_cast<size_t>(iz) * p.SH + iy) * p.SW + ix), acc);
         }
-        o[i] = acc;
-      }
-      float* dst = p.out + c * nvox + v0;
-      if (vec_store) {
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
       } else {
-#pragma unroll
-        for (int i = 0; i < kWarpVX; ++i)
-          if (x0 + i < p.OW) dst[i] = o[i];
+        acc = p.default_value;
       }
+      o[i] = acc;
     }
+    float* dst = p.out + c * nvox + v0;
+#pragma unroll
+    for (int i = 0; i < kWarpVZ; ++i)
+      if (tz0 + i < p.OD) dst[i * zstride] = o[i];
   }
 }
 
@@ -976,8 +970,9 @@ int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
 }
 
 int chain_launch(const ChainParams& p, cudaStream_t st) {
-  const long long n = static_cast<long long>(p.D) * p.H * ((p.W + kChainVX - 1) / kChainVX);
-  chain_kernel<<<grid_for(n, 256, 64), 256, 0, st>>>(p);
+  constexpr int vz = 2;
+  const long long tiles = static_cast<long long>((p.W + 31) / 32) * ((p.H + 7) / 8) * ((p.D + vz - 1) / vz);
+  chain_kernel<vz, 4><<<grid_for(tiles * 256, 256, 64), 256, 0, st>>>(p);
   return launched("chain_kernel");
 }
 
@@ -1001,8 +996,13 @@ int disp_field_launch(const float* phi, int D, int H, int W, float* disp, cudaSt
 }
 
 int warp_volume_launch(const WarpVolumeParams& p, cudaStream_t st) {
-  const long long n = static_cast<long long>(p.OD) * p.OH * ((p.OW + kWarpVX - 1) / kWarpVX);
-  warp_volume_kernel<<<grid_for(n, 256, 64), 256, 0, st>>>(p);
+  constexpr int vz = 1;
+  const long long tiles = static_cast<long long>((p.OW + 31) / 32) * ((p.OH + 7) / 8) * ((p.OD + vz - 1) / vz);
+  if (tiles <= 0 || tiles > 0x7fffffffLL) return fail("warp_volume: output too large");
+  WarpVolumeParams q = p;
+  const int nf[3] = {p.FW, p.FH, p.FD}, ns[3] = {p.SW, p.SH, p.SD};
+  for (int a = 0; a < 3; ++a) { q.fhi[a] = nf[a] - 0.5; q.shi[a] = ns[a] - 0.5; }
+  warp_volume_kernel<vz, 6><<<static_cast<unsigned>(tiles), 256, 0, st>>>(q);
   return launched("warp_volume_kernel");
 }
 

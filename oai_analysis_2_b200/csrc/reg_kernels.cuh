@@ -62,6 +62,7 @@ struct WarpVolumeParams {
   float* out;        // [C][OD][OH][OW]
   int OD, OH, OW;
   float default_value;
+  double fhi[3], shi[3];  // filled by warp_volume_launch: upper inside bounds n - 0.5 of the field / source lattices (x,y,z)
 };
 
 struct WarpPointsParams {

@@ -44,7 +44,8 @@ def main():
         pass
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > L2, rewritten between cases
     eye = (np.eye(3), np.zeros(3))
-    for n in (64, 96, 128, 192, 256, 384):
+    sizes = [int(v) for v in sys.argv[1:]] or [64, 96, 128, 192, 256, 384]
+    for n in sizes:
         disp = smooth_disp(n)                                   # [3,n,n,n] voxels
         field = disp.permute(1, 2, 3, 0).flip(-1).contiguous()  # [n,n,n,3] x,y,z components
         for C in (1, 2, 3, 4, 8):
