@@ -147,6 +147,20 @@ OAI_API int oai_reg_convt4(const float* in, long long in_nstride, long long in_c
                            long long out_nstride, long long out_cstride, int cout, const int* out_dims, int N,
                            void* stream);
 
+/* Split-fp16 weights for oai_reg_convt4_mma: w [cin][64][cout] fp32 (device) -> wpk (device, cin*64*cout*4 bytes,
+ * 16-byte aligned): mma.sync.m16n8k16 B fragments [cout/16][cin/16][64 taps][2 n-tiles][32 lanes] x (hi k0-7, hi k8-15,
+ * lo k0-7, lo k8-15), each weight scaled by 2^wexp before the hi/lo fp16 split (choose wexp so that
+ * max|w| * 2^wexp is in [2^13, 2^14): lo then stays clear of fp16 subnormals).  cin, cout multiples of 16. */
+OAI_API int oai_reg_pack_convt4(const float* w, int cin, int cout, int wexp, void* wpk, void* stream);
+
+/* Same operator as oai_reg_convt4 (icon networks.UNet2 up step) on the tensor path: implicit GEMM with
+ * mma.sync.m16n8k16, operands split into fp16 hi + lo pairs (hi*hi + lo*hi + hi*lo, fp32 accumulate: fp32-level
+ * accuracy).  w (the fp32 packing of oai_reg_convt4) is kept for shapes the MMA tiling does not cover. */
+OAI_API int oai_reg_convt4_mma(const float* in, long long in_nstride, long long in_cstride, int cin,
+                               const int* in_dims, const float* w, const void* wpk, int wexp, const float* bias,
+                               const float* bn_scale, const float* bn_shift, float* out, long long out_nstride,
+                               long long out_cstride, int cout, const int* out_dims, int N, void* stream);
+
 /* Composition of displacement maps and image warp, fused (icon network_wrappers.TwoStepRegistration /
  * FunctionFromVectorField closures; mermaidlite.compute_warped_image_multiNC == F.grid_sample(bilinear, border,
  * align_corners=True) at 2c-1).  Starting from the identity map of grid_dims (coordinates in [0,1], channel order

@@ -47,6 +47,37 @@ extern "C" int oai_reg_convt4(const float* in, long long in_nstride, long long i
   p.w = w; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
   p.out = out; p.out_nstride = out_nstride; p.out_cstride = out_cstride; p.cout = cout;
   p.Do = out_dims[0]; p.Ho = out_dims[1]; p.Wo = out_dims[2]; p.N = N;
+  p.wpk = nullptr; p.wexp = 0;
+  return convt4_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int oai_reg_pack_convt4(const float* w, int cin, int cout, int wexp, void* wpk, void* stream) {
+  OAI_REQUIRE(w && wpk, "reg_pack_convt4: null pointer");
+  OAI_REQUIRE(cin > 0 && cout > 0 && cin % 16 == 0 && cout % 16 == 0,
+              "reg_pack_convt4: cin and cout must be multiples of 16 (got %d, %d)", cin, cout);
+  OAI_REQUIRE(wexp >= -14 && wexp <= 30, "reg_pack_convt4: scale exponent %d out of range", wexp);
+  return reg_pack_convt4_launch(w, cin, cout, wexp, static_cast<uint4*>(wpk), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int oai_reg_convt4_mma(const float* in, long long in_nstride, long long in_cstride, int cin,
+                                  const int* in_dims, const float* w, const void* wpk, int wexp, const float* bias,
+                                  const float* bn_scale, const float* bn_shift, float* out, long long out_nstride,
+                                  long long out_cstride, int cout, const int* out_dims, int N, void* stream) {
+  OAI_REQUIRE(in && in_dims && w && wpk && bias && bn_scale && bn_shift && out && out_dims,
+              "reg_convt4_mma: null pointer");
+  OAI_REQUIRE(cout <= cin, "reg_convt4_mma: the residual keeps the first cout of cin channels (cout=%d cin=%d)", cout,
+              cin);
+  OAI_REQUIRE(cin % 16 == 0 && cout % 16 == 0, "reg_convt4_mma: cin and cout must be multiples of 16");
+  OAI_REQUIRE((reinterpret_cast<uintptr_t>(wpk) & 15) == 0, "reg_convt4_mma: packed weights must be 16-byte aligned");
+  for (int a = 0; a < 3; ++a)
+    OAI_REQUIRE(out_dims[a] >= 1 && out_dims[a] <= 2 * in_dims[a], "reg_convt4_mma: output dim %d exceeds 2x input", a);
+  ConvT4Params p;
+  p.in = in; p.in_nstride = in_nstride; p.in_cstride = in_cstride; p.cin = cin;
+  p.Di = in_dims[0]; p.Hi = in_dims[1]; p.Wi = in_dims[2];
+  p.w = w; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
+  p.out = out; p.out_nstride = out_nstride; p.out_cstride = out_cstride; p.cout = cout;
+  p.Do = out_dims[0]; p.Ho = out_dims[1]; p.Wo = out_dims[2]; p.N = N;
+  p.wpk = static_cast<const uint4*>(wpk); p.wexp = wexp;
   return convt4_launch(p, static_cast<cudaStream_t>(stream));
 }
 

@@ -9,6 +9,8 @@
 //   * disp_field          : itk_wrapper.create_itk_transform's (phi - id) * (N - 1), components reversed to x,y,z
 //   * warp_volume/points  : itk.resample_image_filter / TransformPoint through R_A o DisplacementField o R_B^-1
 //                           (oai_analysis/dask_processing.py:100-109), float64 coordinate arithmetic
+#include <cuda_fp16.h>
+
 #include "api_common.h"
 #include "reg_kernels.cuh"
 
@@ -581,6 +583,234 @@ __global__ void __launch_bounds__(128) convt4_par_kernel(const ConvT4Params p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ convT k4 s2 p1, MMA
+// The up path of tallUNet2 holds 79 % of the registration FLOPs with 48..512 input channels: it runs as an implicit
+// GEMM on the warp-level tensor path (mma.sync m16n8k16, fp16 operands, fp32 accumulate) with fp32-level accuracy:
+// every operand is split x = hi + lo into two fp16 values (22 mantissa bits) and hi*hi + lo*hi + hi*lo is accumulated
+// (the dropped lo*lo term is ~2^-22 relative; products of two fp16 values are exact in fp32).  Weights are pre-split,
+// pre-scaled by 2^wexp (so lo never falls into fp16 subnormals) and stored in B-fragment order by
+// reg_pack_convt4_kernel.
+//   GEMM view per output parity class (pz,py,px): M = input lattice points q, K = 8 taps x Cin, N = Cout.
+//   o = 2 i - 1 + k: class p = 0 uses (k = 1, i = q), (k = 3, i = q - 1); p = 1 uses (k = 2, i = q), (k = 0, i = q + 1).
+// A block owns TX x TY x 1 lattice points (all 8 classes = 2TX x 2TY x 2 outputs) and 16 output channels; per chunk of
+// 16 input channels the 3 x (TY+2) x (TX+2) input neighbourhood is leaky-ReLU'd, split and stored as fp16 channel pairs
+// (one 32-bit word = one A-fragment register).  Each of the 27 neighbour shifts loads its A fragments once and feeds
+// every (class, tap) pair that maps to it: 64 weight taps x 2 m-tiles x 2 n-tiles x 3 split terms = 768 MMAs per warp
+// per chunk against 432 shared-memory loads.  The residual (2x trilinear upsample of the raw input channels, fixed
+// 0.25 / 0.75 weights), bias and BatchNorm are applied in the epilogue from a raw fp32 copy of the 16 residual
+// channels kept in shared memory (staged with replicate-clamped coordinates = the interpolation's border rule).
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_pack(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// (class parity, tap) pairs served by neighbour shift s in {0,1,2} (input i = q + s - 1) along one axis
+__host__ __device__ constexpr int sh_ncomb(int s) { return s == 1 ? 2 : 1; }
+__host__ __device__ constexpr int sh_par(int s, int i) { return s == 0 ? 0 : (s == 2 ? 1 : i); }
+__host__ __device__ constexpr int sh_tap(int s, int i) { return s == 0 ? 3 : (s == 2 ? 0 : (i == 0 ? 1 : 2)); }
+
+template <int TX>
+struct ConvT4MmaCfg {
+  static constexpr int TY = 128 / TX;             // 4 / 8 / 16 lattice rows per block for TX = 32 / 16 / 8
+  static constexpr int SX = TX + 4, SY = TY + 2;  // shared-memory row length (TX + 2 used) and rows per z
+  static constexpr int PS = 3 * SY * SX;          // words per channel pair: 648 / 600 / 648 = 8 * odd (mod 32)
+  static constexpr int RS = PS + 4;               // floats per raw residual channel: 12 / 28 (mod 32)
+  static constexpr size_t smem_bytes = (16 * PS + 16 * RS) * 4;
+};
+
+template <int TX>
+__global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p) {
+  using Cfg = ConvT4MmaCfg<TX>;
+  constexpr int TY = Cfg::TY, SX = Cfg::SX, SY = Cfg::SY, PS = Cfg::PS, RS = Cfg::RS;
+  extern __shared__ __align__(16) uint32_t s_mma[];
+  uint32_t* sHi = s_mma;                                     // [8 pairs][PS]
+  uint32_t* sLo = s_mma + 8 * PS;                            // [8 pairs][PS]
+  float* sRes = reinterpret_cast<float*>(s_mma + 16 * PS);   // [16][RS] raw residual channels co0 .. co0+15
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int ntx = (p.Wi + TX - 1) / TX, nty = (p.Hi + TY - 1) / TY;
+  const int qx0 = static_cast<int>(blockIdx.x % ntx) * TX, qy0 = static_cast<int>((blockIdx.x / ntx) % nty) * TY;
+  const int qz = static_cast<int>(blockIdx.x / (ntx * nty));
+  const int coblk = blockIdx.y, co0 = coblk * 16, n = blockIdx.z;
+  const float* in_n = p.in + n * p.in_nstride;
+  const int nchunks = p.cin / 16;
+  // rows g and g + 8 (h = 0, 1) of m-tile j of this warp <-> lattice point (ty[j][h], tx[j][h]) of the block tile:
+  // an m-tile is 16 x-adjacent points (TX >= 16) or 8 x-adjacent points of two rows (TX = 8)
+  int ty[2][2], tx[2][2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      ty[j][h] = TX == 32 ? wrp : (TX == 16 ? 2 * wrp + j : 4 * wrp + 2 * j + h);
+      tx[j][h] = TX == 32 ? 16 * j + g + 8 * h : (TX == 16 ? g + 8 * h : g);
+    }
+  float acc[8][2][2][4];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) acc[c][j][nt][0] = acc[c][j][nt][1] = acc[c][j][nt][2] = acc[c][j][nt][3] = 0.f;
+
+  for (int ch = 0; ch < nchunks; ++ch) {
+    // ---- stage: global fp32 -> leaky -> hi/lo fp16 channel pairs (and the raw residual channels of this block)
+    const bool res_chunk = ch == coblk;
+    constexpr int NE = 8 * 3 * SY * (TX + 2);
+#pragma unroll 4
+    for (int e = tid; e < NE; e += 128) {
+      const int sx = e % (TX + 2);
+      int r = e / (TX + 2);
+      const int sy = r % SY;
+      r /= SY;
+      const int sz = r % 3, pair = r / 3;
+      const int z = qz - 1 + sz, y = qy0 - 1 + sy, x = qx0 - 1 + sx;
+      const bool ok = z >= 0 && z < p.Di && y >= 0 && y < p.Hi && x >= 0 && x < p.Wi;
+      const int zc = min(max(z, 0), p.Di - 1), yc = min(max(y, 0), p.Hi - 1), xc = min(max(x, 0), p.Wi - 1);
+      const float* src = in_n + (ch * 16 + 2 * pair) * p.in_cstride + (static_cast<size_t>(zc) * p.Hi + yc) * p.Wi + xc;
+      const float r0 = __ldg(src), r1 = __ldg(src + p.in_cstride);
+      const int so = (sz * SY + sy) * SX + sx;
+      if (res_chunk) {
+        sRes[(2 * pair) * RS + so] = r0;
+        sRes[(2 * pair + 1) * RS + so] = r1;
+      }
+      uint32_t hi, lo;
+      split_pack(ok ? leaky(r0) : 0.f, ok ? leaky(r1) : 0.f, hi, lo);
+      sHi[pair * PS + so] = hi;
+      sLo[pair * PS + so] = lo;
+    }
+    __syncthreads();
+    // ---- MMAs: 27 neighbour shifts, A fragments loaded once per shift
+    const uint4* wq = p.wpk + (static_cast<size_t>(coblk) * nchunks + ch) * (64 * 2 * 32) + lane;
+#pragma unroll
+    for (int sz = 0; sz < 3; ++sz)
+#pragma unroll
+      for (int sy = 0; sy < 3; ++sy)
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx) {
+          uint32_t ah[2][4], al[2][4];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int b0 = (sz * SY + ty[j][0] + sy) * SX + tx[j][0] + sx;
+            const int b1 = (sz * SY + ty[j][1] + sy) * SX + tx[j][1] + sx;
+            ah[j][0] = sHi[t * PS + b0];       ah[j][1] = sHi[t * PS + b1];
+            ah[j][2] = sHi[(t + 4) * PS + b0]; ah[j][3] = sHi[(t + 4) * PS + b1];
+            al[j][0] = sLo[t * PS + b0];       al[j][1] = sLo[t * PS + b1];
+            al[j][2] = sLo[(t + 4) * PS + b0]; al[j][3] = sLo[(t + 4) * PS + b1];
+          }
+#pragma unroll
+          for (int iz = 0; iz < sh_ncomb(sz); ++iz)
+#pragma unroll
+            for (int iy = 0; iy < sh_ncomb(sy); ++iy)
+#pragma unroll
+              for (int ix = 0; ix < sh_ncomb(sx); ++ix) {
+                const int cls = sh_par(sz, iz) * 4 + sh_par(sy, iy) * 2 + sh_par(sx, ix);
+                const int k = (sh_tap(sz, iz) * 4 + sh_tap(sy, iy)) * 4 + sh_tap(sx, ix);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                  const uint4 b = __ldg(wq + (k * 2 + nt) * 32);
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    mma16816(acc[cls][j][nt], ah[j], b.x, b.y);
+                    mma16816(acc[cls][j][nt], al[j], b.x, b.y);
+                    mma16816(acc[cls][j][nt], ah[j], b.z, b.w);
+                  }
+                }
+              }
+        }
+    __syncthreads();
+  }
+
+  // ---- epilogue: out = BN( acc * 2^-wexp + bias + upsample2x(raw in[co]) ), cropped to (Do, Ho, Wo)
+  const float inv = exp2f(static_cast<float>(-p.wexp));
+  float* out_n = p.out + n * p.out_nstride;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      const int cl = 8 * nt + 2 * t + cb, co = co0 + cl;
+      const float bias = __ldg(p.bias + co), bs = __ldg(p.bn_scale + co), bt = __ldg(p.bn_shift + co);
+      float* out_c = out_n + co * p.out_cstride;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int xl = tx[j][h], yl = ty[j][h];
+          const int qx = qx0 + xl, qy = qy0 + yl;
+          if (qx >= p.Wi || qy >= p.Hi) continue;
+          // separable 0.25 / 0.75 interpolation of the 3x3x3 raw neighbourhood -> the 8 class values
+          float ax[3][3][2];
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const float* row = sRes + cl * RS + (dz * SY + yl + dy) * SX + xl;
+              const float v0 = row[0], v1 = row[1], v2 = row[2];
+              ax[dz][dy][0] = 0.25f * v0 + 0.75f * v1;
+              ax[dz][dy][1] = 0.75f * v1 + 0.25f * v2;
+            }
+          float ay[3][2][2];
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+              ay[dz][0][px] = 0.25f * ax[dz][0][px] + 0.75f * ax[dz][1][px];
+              ay[dz][1][px] = 0.75f * ax[dz][1][px] + 0.25f * ax[dz][2][px];
+            }
+#pragma unroll
+          for (int pz = 0; pz < 2; ++pz)
+#pragma unroll
+            for (int py = 0; py < 2; ++py) {
+              const int zo = 2 * qz + pz, yo = 2 * qy + py, xo = 2 * qx;
+              if (zo >= p.Do || yo >= p.Ho || xo >= p.Wo) continue;
+              float v[2];
+#pragma unroll
+              for (int px = 0; px < 2; ++px) {
+                const float r = pz == 0 ? 0.25f * ay[0][py][px] + 0.75f * ay[1][py][px]
+                                        : 0.75f * ay[1][py][px] + 0.25f * ay[2][py][px];
+                v[px] = (acc[pz * 4 + py * 2 + px][j][nt][2 * h + cb] * inv + bias + r) * bs + bt;
+              }
+              float* dst = out_c + (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + xo;
+              if (xo + 1 < p.Wo && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+              } else {
+                dst[0] = v[0];
+                if (xo + 1 < p.Wo) dst[1] = v[1];
+              }
+            }
+        }
+    }
+}
+
+// w [cin][64][cout] fp32 -> B fragments of mma.sync.m16n8k16 (col-major B: k = input channel within the chunk,
+// n = output channel within the 8-wide n-tile), split into hi / lo fp16 after scaling by 2^wexp.
+__global__ void reg_pack_convt4_kernel(const float* __restrict__ w, int cin, int cout, int wexp, uint4* __restrict__ wpk) {
+  const long long total = static_cast<long long>(cout / 16) * (cin / 16) * 64 * 2 * 32;
+  const float sc = exp2f(static_cast<float>(wexp));
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int lane = r % 32; r /= 32;
+    const int nt = r % 2; r /= 2;
+    const int k = r % 64; r /= 64;
+    const int ch = r % (cin / 16);
+    const int coblk = static_cast<int>(r / (cin / 16));
+    const int g = lane >> 2, t = lane & 3;
+    const int co = coblk * 16 + nt * 8 + g;
+    auto at = [&](int ci) { return w[(static_cast<size_t>(ch * 16 + ci) * 64 + k) * cout + co] * sc; };
+    uint4 o;
+    split_pack(at(2 * t), at(2 * t + 1), o.x, o.z);
+    split_pack(at(2 * t + 8), at(2 * t + 9), o.y, o.w);
+    wpk[i] = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ sampling helpers
 // F.grid_sample(bilinear, border, align_corners=True) at normalised coordinate g = 2c-1 along each axis.
 struct Tri {
@@ -942,8 +1172,34 @@ static void convt4_dispatch(const ConvT4Params& p, cudaStream_t st) {
   convt4_kernel<CO_T, XP, KS><<<g, 128, 0, st>>>(p);
 }
 
+template <int TX>
+static void convt4_mma_dispatch(const ConvT4Params& p, cudaStream_t st) {
+  using Cfg = ConvT4MmaCfg<TX>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(convt4_mma_kernel<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(Cfg::smem_bytes));
+    configured = true;
+  }
+  const int ntx = (p.Wi + TX - 1) / TX, nty = (p.Hi + Cfg::TY - 1) / Cfg::TY;
+  dim3 g(static_cast<unsigned>(ntx) * nty * p.Di, p.cout / 16, p.N);
+  convt4_mma_kernel<TX><<<g, 128, Cfg::smem_bytes, st>>>(p);
+}
+
+int reg_pack_convt4_launch(const float* w, int cin, int cout, int wexp, uint4* wpk, cudaStream_t st) {
+  const long long total = static_cast<long long>(cout / 16) * (cin / 16) * 64 * 2 * 32;
+  reg_pack_convt4_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(w, cin, cout, wexp, wpk);
+  return launched("reg_pack_convt4_kernel");
+}
+
 int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
   const long long nout = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+  if (p.wpk && p.cin % 16 == 0 && p.cout % 16 == 0) {
+    if (p.Wi > 16) convt4_mma_dispatch<32>(p, st);
+    else if (p.Wi > 8) convt4_mma_dispatch<16>(p, st);
+    else convt4_mma_dispatch<8>(p, st);
+    return launched("convt4_mma_kernel");
+  }
   if (nout * ((p.cout + 7) / 8) >= (1 << 17) && p.cout % 8 == 0) {
     // large levels: shared-memory tiled kernel (2 x 8 x 64 output voxels per block)
     constexpr int CO_T = 8;

@@ -33,6 +33,10 @@ struct ConvT4Params {
   long long out_nstride, out_cstride;
   int cout, Do, Ho, Wo;  // Do <= 2*Di etc. (crop)
   int N;
+  // optional split-fp16 weights for the mma.sync path (reg_pack_convt4_launch): [cout/16][cin/16][64][2][32] uint4 of
+  // B fragments (hi k0-7, hi k8-15, lo k0-7, lo k8-15), scaled by 2^wexp
+  const uint4* wpk;
+  int wexp;
 };
 
 struct ChainParams {
@@ -76,6 +80,7 @@ struct WarpPointsParams {
 
 int conv3_launch(const Conv3Params& p, cudaStream_t st);
 int convt4_launch(const ConvT4Params& p, cudaStream_t st);
+int reg_pack_convt4_launch(const float* w, int cin, int cout, int wexp, uint4* wpk, cudaStream_t st);
 int chain_launch(const ChainParams& p, cudaStream_t st);
 int resize_trilinear_launch(const float* in, int Di, int Hi, int Wi, float* out, int Do, int Ho, int Wo,
                             cudaStream_t st);

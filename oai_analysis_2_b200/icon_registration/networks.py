@@ -47,6 +47,7 @@ class TallUNet2:
         self.device = torch.device("cpu")
         self._packed = None
         self._bufs = {}
+        self.use_mma = True  # False: every layer on the fp32 CUDA-core kernels (A/B switch for tests / profiling)
 
     def state_dict(self, prefix=""):
         return {prefix + k: v for k, v in self._sd.items()}
@@ -84,6 +85,8 @@ class TallUNet2:
             w = sd[f"upConvs.{d}.weight"]
             P[f"uw{d}"] = w.permute(0, 2, 3, 4, 1).reshape(UP_IN[d], 64, UP_OUT[d]).contiguous().to(dev)
             P[f"ub{d}"] = sd[f"upConvs.{d}.bias"].to(dev)
+            # split-fp16 B fragments for the mma.sync path (levels too small for it fall back to the fp32 kernels)
+            P[f"uq{d}"] = ops.reg_pack_convt4(P[f"uw{d}"], UP_IN[d], UP_OUT[d]) if self.use_mma else (None, 0)
             s = sd[f"batchNorms.{d}.weight"].double() / torch.sqrt(sd[f"batchNorms.{d}.running_var"].double() + 1e-5)
             P[f"bs{d}"] = s.float().to(dev)
             P[f"bt{d}"] = (sd[f"batchNorms.{d}.bias"].double() - sd[f"batchNorms.{d}.running_mean"].double() * s
@@ -121,8 +124,9 @@ class TallUNet2:
             ops.reg_conv3(src, DOWN[d], P[f"dw{d}"], P[f"db{d}"], dst, DOWN[d + 1], 2, True, True)
         for d in reversed(range(5)):
             src = x5 if d == 4 else cat[d + 1]
+            wpk, wexp = P[f"uq{d}"]
             ops.reg_convt4(src, UP_IN[d], P[f"uw{d}"], P[f"ub{d}"], P[f"bs{d}"], P[f"bt{d}"], cat[d][:, :UP_OUT[d]],
-                           UP_OUT[d])
+                           UP_OUT[d], wpk, wexp)
         if out is None:
             out = torch.empty((N, 3) + dims, dtype=torch.float32, device=self.device)
         ops.reg_conv3(cat[0], 18, P["lw"], P["lb"], out, 3, 1, False, False, 0.1)

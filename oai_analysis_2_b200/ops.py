@@ -1,5 +1,6 @@
 """Thin Python wrappers over the C-ABI ops (torch tensors in, torch tensors out; torch is only the allocator)."""
 import ctypes
+import math
 
 import numpy as np
 import torch
@@ -112,13 +113,29 @@ def reg_conv3(x, cin, w, bias, out, cout, stride, leaky_in, residual, out_scale=
     return out
 
 
-def reg_convt4(x, cin, w, bias, bn_scale, bn_shift, out, cout):
+def reg_convt4(x, cin, w, bias, bn_scale, bn_shift, out, cout, wpk=None, wexp=0):
     N, _, D, H, W = x.shape
     od = _dims(*out.shape[2:])
+    if wpk is not None:
+        check(lib.oai_reg_convt4_mma(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(_dims(D, H, W)), ptr(w),
+                                     ptr(wpk), wexp, ptr(bias), ptr(bn_scale), ptr(bn_shift), ptr(out),
+                                     c_ll(out.stride(0)), c_ll(out.stride(1)), cout, ptr(od), N, stream_ptr()),
+              "reg_convt4_mma")
+        return out
     check(lib.oai_reg_convt4(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(_dims(D, H, W)), ptr(w),
                              ptr(bias), ptr(bn_scale), ptr(bn_shift), ptr(out), c_ll(out.stride(0)),
                              c_ll(out.stride(1)), cout, ptr(od), N, stream_ptr()), "reg_convt4")
     return out
+
+
+def reg_pack_convt4(w, cin, cout):
+    """w: [cin, 64, cout] float32 cuda -> (wpk uint8 tensor, wexp) for reg_convt4(..., wpk=...)."""
+    wmax = float(w.abs().max())
+    wexp = 0 if wmax == 0.0 else int(13 - math.floor(math.log2(wmax)))
+    wexp = max(-14, min(30, wexp))
+    wpk = torch.empty(cin * 64 * cout * 4, dtype=torch.uint8, device=w.device)
+    check(lib.oai_reg_pack_convt4(ptr(w), cin, cout, wexp, ptr(wpk), stream_ptr()), "reg_pack_convt4")
+    return wpk, wexp
 
 
 def compose(grid_dims, fields, shortcut_first=False, img=None, want_phi=True, phi_out=None, img_out=None):

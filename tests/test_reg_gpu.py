@@ -72,6 +72,45 @@ def test_unet2_layers_match_torch():
     assert (out.cpu() - ref).abs().max() < 3e-5
 
 
+@pytest.mark.parametrize("cin,cout,dims,crop", [
+    (48, 16, (3, 9, 40), (6, 17, 79)),      # TX=32 tiles, ragged x/y, odd crops
+    (96, 32, (2, 12, 14), (4, 24, 28)),     # TX=16 tiles, two output-channel blocks (residual chunk 1)
+    (32, 32, (2, 5, 33), (3, 10, 66)),      # cin == cout, partial tiles in both axes
+    (64, 48, (3, 6, 6), (5, 12, 12)),       # TX=8 tiles (deep levels), three output-channel blocks
+    (32, 16, (2, 3, 3), (3, 5, 6)),         # deepest level of the quarter-resolution nets
+])
+def test_convt4_mma_matches_torch(cin, cout, dims, crop):
+    """Split-fp16 mma.sync path of the up step (oai_reg_convt4_mma) against torch fp32 and against the fp32 kernels."""
+    _cuda()
+    from oai_analysis_2_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    N = 2
+    buf = torch.randn(N, cin + 3, *dims, generator=g) * 2.0
+    x = buf[:, 3:]
+    w, b = torch.randn(cin, cout, 4, 4, 4, generator=g) * 0.05, torch.randn(cout, generator=g) * 0.1
+    gam, bet = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    mean, var = torch.randn(cout, generator=g) * 0.1, torch.rand(cout, generator=g) + 0.5
+    y = F.conv_transpose3d(F.leaky_relu(x).double(), w.double(), b.double(), stride=2, padding=1)
+    ref = y + F.interpolate(x[:, :cout].double(), scale_factor=2, mode="trilinear", align_corners=False)
+    ref = F.batch_norm(ref, mean.double(), var.double(), gam.double(), bet.double(), training=False, eps=1e-5)
+    ref = ref[:, :, :crop[0], :crop[1], :crop[2]]
+    s = (gam.double() / torch.sqrt(var.double() + 1e-5)).float().cuda()
+    t = (bet.double() - mean.double() * s.cpu().double()).float().cuda()
+    wp = w.permute(0, 2, 3, 4, 1).reshape(cin, 64, cout).contiguous().cuda()
+    wpk, wexp = ops.reg_pack_convt4(wp, cin, cout)
+    xc = buf.cuda()[:, 3:]
+    out_buf = torch.zeros(N, cout + 2, *crop).cuda()
+    ops.reg_convt4(xc, cin, wp, b.cuda(), s, t, out_buf[:, 2:], cout, wpk, wexp)
+    fp32 = torch.zeros(N, cout, *crop).cuda()
+    ops.reg_convt4(xc, cin, wp, b.cuda(), s, t, fp32, cout)
+    e_mma = (out_buf[:, 2:].cpu().double() - ref).abs().max().item()
+    e_f32 = (fp32.cpu().double() - ref).abs().max().item()
+    print(f"convt4 {cin}->{cout} {dims}: max-abs error vs fp64 torch: mma(split fp16) {e_mma:.2e}, fp32 kernels {e_f32:.2e}")
+    scale = max(1.0, ref.abs().max().item())
+    assert e_mma < 4e-6 * scale, (e_mma, e_f32, scale)   # fp32-level: a few ulp of the largest output
+    assert out_buf[:, :2].abs().max() == 0
+
+
 def test_tallunet2_matches_oracle():
     _cuda()
     from oai_analysis_2_b200.icon_registration.networks import TallUNet2
