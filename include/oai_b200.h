@@ -148,18 +148,24 @@ OAI_API int oai_reg_convt4(const float* in, long long in_nstride, long long in_c
                            void* stream);
 
 /* Split-fp16 weights for oai_reg_convt4_mma: w [cin][64][cout] fp32 (device) -> wpk (device, cin*64*cout*4 bytes,
- * 16-byte aligned): mma.sync.m16n8k16 B fragments [cout/16][cin/16][64 taps][2 n-tiles][32 lanes] x (hi k0-7, hi k8-15,
+ * 16-byte aligned): mma.sync.m16n8k16 B fragments [cout/16][cin/16][64 taps, kernel visit order][2 n-tiles][32 lanes] x (hi k0-7, hi k8-15,
  * lo k0-7, lo k8-15), each weight scaled by 2^wexp before the hi/lo fp16 split (choose wexp so that
  * max|w| * 2^wexp is in [2^13, 2^14): lo then stays clear of fp16 subnormals).  cin, cout multiples of 16. */
 OAI_API int oai_reg_pack_convt4(const float* w, int cin, int cout, int wexp, void* wpk, void* stream);
 
 /* Same operator as oai_reg_convt4 (icon networks.UNet2 up step) on the tensor path: implicit GEMM with
  * mma.sync.m16n8k16, operands split into fp16 hi + lo pairs (hi*hi + lo*hi + hi*lo, fp32 accumulate: fp32-level
- * accuracy).  w (the fp32 packing of oai_reg_convt4) is kept for shapes the MMA tiling does not cover. */
+ * accuracy).  Levels narrower than 12 input points run the fp32 kernels of oai_reg_convt4 on w; workspace: see
+ * oai_reg_convt4_mma_workspace (16-byte aligned). */
 OAI_API int oai_reg_convt4_mma(const float* in, long long in_nstride, long long in_cstride, int cin,
                                const int* in_dims, const float* w, const void* wpk, int wexp, const float* bias,
                                const float* bn_scale, const float* bn_shift, float* out, long long out_nstride,
-                               long long out_cstride, int cout, const int* out_dims, int N, void* stream);
+                               long long out_cstride, int cout, const int* out_dims, int N, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
+/* Bytes of caller-owned device scratch oai_reg_convt4_mma needs (the layer input rewritten once as leaky-ReLU'd
+ * hi / lo fp16 channel pairs): N * cin * D * H * W * 4. */
+OAI_API size_t oai_reg_convt4_mma_workspace(int cin, const int* in_dims, int N);
 
 /* Composition of displacement maps and image warp, fused (icon network_wrappers.TwoStepRegistration /
  * FunctionFromVectorField closures; mermaidlite.compute_warped_image_multiNC == F.grid_sample(bilinear, border,

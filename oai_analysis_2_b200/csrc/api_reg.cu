@@ -47,7 +47,7 @@ extern "C" int oai_reg_convt4(const float* in, long long in_nstride, long long i
   p.w = w; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
   p.out = out; p.out_nstride = out_nstride; p.out_cstride = out_cstride; p.cout = cout;
   p.Do = out_dims[0]; p.Ho = out_dims[1]; p.Wo = out_dims[2]; p.N = N;
-  p.wpk = nullptr; p.wexp = 0;
+  p.wpk = nullptr; p.wexp = 0; p.xsplit = nullptr;
   return convt4_launch(p, static_cast<cudaStream_t>(stream));
 }
 
@@ -59,12 +59,22 @@ extern "C" int oai_reg_pack_convt4(const float* w, int cin, int cout, int wexp, 
   return reg_pack_convt4_launch(w, cin, cout, wexp, static_cast<uint4*>(wpk), static_cast<cudaStream_t>(stream));
 }
 
+extern "C" size_t oai_reg_convt4_mma_workspace(int cin, const int* in_dims, int N) {
+  if (!in_dims || cin <= 0 || N <= 0) return 0;
+  return static_cast<size_t>(N) * cin * in_dims[0] * in_dims[1] * in_dims[2] * 4;
+}
+
 extern "C" int oai_reg_convt4_mma(const float* in, long long in_nstride, long long in_cstride, int cin,
                                   const int* in_dims, const float* w, const void* wpk, int wexp, const float* bias,
                                   const float* bn_scale, const float* bn_shift, float* out, long long out_nstride,
-                                  long long out_cstride, int cout, const int* out_dims, int N, void* stream) {
-  OAI_REQUIRE(in && in_dims && w && wpk && bias && bn_scale && bn_shift && out && out_dims,
+                                  long long out_cstride, int cout, const int* out_dims, int N, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  OAI_REQUIRE(in && in_dims && w && wpk && bias && bn_scale && bn_shift && out && out_dims && workspace,
               "reg_convt4_mma: null pointer");
+  OAI_REQUIRE(workspace_bytes >= oai_reg_convt4_mma_workspace(cin, in_dims, N) &&
+                  (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+              "reg_convt4_mma: workspace of %zu bytes, 16-byte aligned, required",
+              oai_reg_convt4_mma_workspace(cin, in_dims, N));
   OAI_REQUIRE(cout <= cin, "reg_convt4_mma: the residual keeps the first cout of cin channels (cout=%d cin=%d)", cout,
               cin);
   OAI_REQUIRE(cin % 16 == 0 && cout % 16 == 0, "reg_convt4_mma: cin and cout must be multiples of 16");
@@ -77,7 +87,7 @@ extern "C" int oai_reg_convt4_mma(const float* in, long long in_nstride, long lo
   p.w = w; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
   p.out = out; p.out_nstride = out_nstride; p.out_cstride = out_cstride; p.cout = cout;
   p.Do = out_dims[0]; p.Ho = out_dims[1]; p.Wo = out_dims[2]; p.N = N;
-  p.wpk = static_cast<const uint4*>(wpk); p.wexp = wexp;
+  p.wpk = static_cast<const uint4*>(wpk); p.wexp = wexp; p.xsplit = static_cast<uint32_t*>(workspace);
   return convt4_launch(p, static_cast<cudaStream_t>(stream));
 }
 

@@ -20,6 +20,25 @@ namespace {
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.01f * v; }
 
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 4 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16z(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+
 // ------------------------------------------------------------------------------------------------ conv k3
 // Register-tiled direct convolution: a thread produces XS x-adjacent outputs for CO_T output channels, so every
 // weight vector read from shared memory feeds XS FMAs per channel and every input value feeds up to 3*CO_T.
@@ -337,19 +356,6 @@ __global__ void __launch_bounds__(128) convt4_kernel(const ConvT4Params p) {
 // Block = 128 threads = one output tile of 2 (z) x 8 (y) x 64 (x) voxels; per chunk of 8 input channels the
 // 3 x 6 x 34 input neighbourhood and the [8][64][CO_T] weight slice are staged with cp.async (double buffered), so the
 // FMA loop reads shared memory only and the next chunk's global loads are in flight while the current one computes.
-__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc, bool valid) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  const int sz = valid ? 4 : 0;  // src-size 0 -> zero fill
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 constexpr int kTileCI = 8, kTileSX = 36, kTileIn = 3 * 6 * kTileSX;  // input tile floats per channel (x padded 34 -> 36)
 
 template <int CO_T>
@@ -592,13 +598,14 @@ __global__ void __launch_bounds__(128) convt4_par_kernel(const ConvT4Params p) {
 // reg_pack_convt4_kernel.
 //   GEMM view per output parity class (pz,py,px): M = input lattice points q, K = 8 taps x Cin, N = Cout.
 //   o = 2 i - 1 + k: class p = 0 uses (k = 1, i = q), (k = 3, i = q - 1); p = 1 uses (k = 2, i = q), (k = 0, i = q + 1).
-// A block owns TX x TY x 1 lattice points (all 8 classes = 2TX x 2TY x 2 outputs) and 16 output channels; per chunk of
-// 16 input channels the 3 x (TY+2) x (TX+2) input neighbourhood is leaky-ReLU'd, split and stored as fp16 channel pairs
-// (one 32-bit word = one A-fragment register).  Each of the 27 neighbour shifts loads its A fragments once and feeds
+// reg_split_kernel first rewrites the layer input once as leaky-ReLU'd hi / lo fp16 channel pairs (one 32-bit word =
+// one A-fragment register).  A block owns TX x TY x 1 lattice points (all 8 classes = 2TX x 2TY x 2 outputs) and 16
+// output channels; per chunk of 16 input channels the 3 x (TY+2) x (TX+2) neighbourhood of both arrays is copied to
+// shared memory by cp.async (double buffered: chunk c+1 flies while chunk c computes).  Each of the 27 neighbour shifts loads its A fragments once and feeds
 // every (class, tap) pair that maps to it: 64 weight taps x 2 m-tiles x 2 n-tiles x 3 split terms = 768 MMAs per warp
 // per chunk against 432 shared-memory loads.  The residual (2x trilinear upsample of the raw input channels, fixed
-// 0.25 / 0.75 weights), bias and BatchNorm are applied in the epilogue from a raw fp32 copy of the 16 residual
-// channels kept in shared memory (staged with replicate-clamped coordinates = the interpolation's border rule).
+// 0.25 / 0.75 weights), bias and BatchNorm are applied in the epilogue from the 16 raw residual channels, fetched
+// into the free buffer (replicate-clamped coordinates = the interpolation's border rule) during the last chunk's MMAs.
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -617,23 +624,40 @@ __host__ __device__ constexpr int sh_ncomb(int s) { return s == 1 ? 2 : 1; }
 __host__ __device__ constexpr int sh_par(int s, int i) { return s == 0 ? 0 : (s == 2 ? 1 : i); }
 __host__ __device__ constexpr int sh_tap(int s, int i) { return s == 0 ? 3 : (s == 2 ? 0 : (i == 0 ? 1 : 2)); }
 
+// The kernel visits the 64 weight taps in the order of its shift loops; the packed weights are stored in that order so
+// the B-fragment stream of a chunk is read front to back (register double buffering + L1 prefetch a few visits ahead).
+__host__ __device__ constexpr int visit_tap(int v) {
+  int c = 0;
+  for (int sz = 0; sz < 3; ++sz)
+    for (int sy = 0; sy < 3; ++sy)
+      for (int sx = 0; sx < 3; ++sx)
+        for (int iz = 0; iz < sh_ncomb(sz); ++iz)
+          for (int iy = 0; iy < sh_ncomb(sy); ++iy)
+            for (int ix = 0; ix < sh_ncomb(sx); ++ix) {
+              if (c == v) return (sh_tap(sz, iz) * 4 + sh_tap(sy, iy)) * 4 + sh_tap(sx, ix);
+              ++c;
+            }
+  return -1;
+}
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 template <int TX>
 struct ConvT4MmaCfg {
-  static constexpr int TY = 128 / TX;             // 4 / 8 / 16 lattice rows per block for TX = 32 / 16 / 8
-  static constexpr int SX = TX + 4, SY = TY + 2;  // shared-memory row length (TX + 2 used) and rows per z
-  static constexpr int PS = 3 * SY * SX;          // words per channel pair: 648 / 600 / 648 = 8 * odd (mod 32)
-  static constexpr int RS = PS + 4;               // floats per raw residual channel: 12 / 28 (mod 32)
-  static constexpr size_t smem_bytes = (16 * PS + 16 * RS) * 4;
+  static constexpr int TY = 128 / TX;             // 4 / 8 lattice rows per block for TX = 32 / 16
+  // shared-memory row: col 3 = left halo, cols 4 .. TX+3 = the tile (16-byte aligned for cp.async), col TX+4 = right halo
+  static constexpr int SX = TX + 8, SY = TY + 2;
+  static constexpr int PS0 = 3 * SY * SX;
+  // words per channel pair, padded to 8 (mod 16): A-fragment loads (pair = lane % 4, point = lane / 4) conflict-free
+  static constexpr int PS = PS0 + ((8 - PS0 % 16) + 16) % 16;
+  static constexpr size_t smem_bytes = 2 * 16 * PS * 4;  // two buffers of (hi, lo) x 8 pairs
 };
 
 template <int TX>
 __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p) {
   using Cfg = ConvT4MmaCfg<TX>;
-  constexpr int TY = Cfg::TY, SX = Cfg::SX, SY = Cfg::SY, PS = Cfg::PS, RS = Cfg::RS;
-  extern __shared__ __align__(16) uint32_t s_mma[];
-  uint32_t* sHi = s_mma;                                     // [8 pairs][PS]
-  uint32_t* sLo = s_mma + 8 * PS;                            // [8 pairs][PS]
-  float* sRes = reinterpret_cast<float*>(s_mma + 16 * PS);   // [16][RS] raw residual channels co0 .. co0+15
+  constexpr int TY = Cfg::TY, SX = Cfg::SX, SY = Cfg::SY, PS = Cfg::PS;
+  extern __shared__ __align__(16) uint32_t s_mma[];  // [2 buffers][hi, lo][8 pairs][PS]
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int ntx = (p.Wi + TX - 1) / TX, nty = (p.Hi + TY - 1) / TY;
   const int qx0 = static_cast<int>(blockIdx.x % ntx) * TX, qy0 = static_cast<int>((blockIdx.x / ntx) % nty) * TY;
@@ -641,15 +665,16 @@ __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p
   const int coblk = blockIdx.y, co0 = coblk * 16, n = blockIdx.z;
   const float* in_n = p.in + n * p.in_nstride;
   const int nchunks = p.cin / 16;
-  // rows g and g + 8 (h = 0, 1) of m-tile j of this warp <-> lattice point (ty[j][h], tx[j][h]) of the block tile:
-  // an m-tile is 16 x-adjacent points (TX >= 16) or 8 x-adjacent points of two rows (TX = 8)
+  const long long vol = static_cast<long long>(p.Di) * p.Hi * p.Wi;
+  // rows g and g + 8 (h = 0, 1) of m-tile j of this warp <-> lattice point (ty[j][h], tx[j][h]) of the block tile
+  // (an m-tile is 16 x-adjacent points)
   int ty[2][2], tx[2][2];
 #pragma unroll
   for (int j = 0; j < 2; ++j)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      ty[j][h] = TX == 32 ? wrp : (TX == 16 ? 2 * wrp + j : 4 * wrp + 2 * j + h);
-      tx[j][h] = TX == 32 ? 16 * j + g + 8 * h : (TX == 16 ? g + 8 * h : g);
+      ty[j][h] = TX == 32 ? wrp : 2 * wrp + j;
+      tx[j][h] = TX == 32 ? 16 * j + g + 8 * h : g + 8 * h;
     }
   float acc[8][2][2][4];
 #pragma unroll
@@ -659,35 +684,91 @@ __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) acc[c][j][nt][0] = acc[c][j][nt][1] = acc[c][j][nt][2] = acc[c][j][nt][3] = 0.f;
 
-  for (int ch = 0; ch < nchunks; ++ch) {
-    // ---- stage: global fp32 -> leaky -> hi/lo fp16 channel pairs (and the raw residual channels of this block)
-    const bool res_chunk = ch == coblk;
-    constexpr int NE = 8 * 3 * SY * (TX + 2);
-#pragma unroll 4
-    for (int e = tid; e < NE; e += 128) {
-      const int sx = e % (TX + 2);
-      int r = e / (TX + 2);
-      const int sy = r % SY;
-      r /= SY;
-      const int sz = r % 3, pair = r / 3;
-      const int z = qz - 1 + sz, y = qy0 - 1 + sy, x = qx0 - 1 + sx;
-      const bool ok = z >= 0 && z < p.Di && y >= 0 && y < p.Hi && x >= 0 && x < p.Wi;
-      const int zc = min(max(z, 0), p.Di - 1), yc = min(max(y, 0), p.Hi - 1), xc = min(max(x, 0), p.Wi - 1);
-      const float* src = in_n + (ch * 16 + 2 * pair) * p.in_cstride + (static_cast<size_t>(zc) * p.Hi + yc) * p.Wi + xc;
-      const float r0 = __ldg(src), r1 = __ldg(src + p.in_cstride);
-      const int so = (sz * SY + sy) * SX + sx;
-      if (res_chunk) {
-        sRes[(2 * pair) * RS + so] = r0;
-        sRes[(2 * pair + 1) * RS + so] = r1;
+  // ---- cp.async of one chunk: (hi, lo) x 8 channel pairs x 3 x SY rows of the pre-split input (reg_split_kernel),
+  // zero-filled outside the volume (the transposed conv's implicit padding).  Per row: TX/4 16-byte pieces + 2 halo
+  // words when rows are 16-byte aligned, TX + 2 words otherwise.
+  const bool vec = (p.Wi & 3) == 0;
+  const int items = vec ? TX / 4 + 2 : TX + 2;
+  const uint32_t* xs_n = p.xsplit + static_cast<long long>(n) * (p.cin / 2) * vol;
+  const long long arr_stride = static_cast<long long>(p.N) * (p.cin / 2) * vol;
+  auto fetch_chunk = [&](int ch, int b) {
+    uint32_t* dbuf = s_mma + b * 16 * PS;
+    const int total = 2 * 8 * 3 * SY * items;
+    for (int e = tid; e < total; e += 128) {
+      const int r = e / items, it = e - r * items;
+      const int sy = r % SY, sz = (r / SY) % 3, pair = (r / (3 * SY)) & 7, arr = r / (24 * SY);
+      const int z = qz - 1 + sz, y = qy0 - 1 + sy;
+      const bool rowok = z >= 0 && z < p.Di && y >= 0 && y < p.Hi;
+      const uint32_t* src = xs_n + arr * arr_stride + (ch * 8 + pair) * vol +
+                            (rowok ? (static_cast<long long>(z) * p.Hi + y) * p.Wi : 0);
+      uint32_t* dst = dbuf + (arr * 8 + pair) * PS + (sz * SY + sy) * SX;
+      if (vec && it < TX / 4) {
+        const int x = qx0 + 4 * it;
+        const bool ok = rowok && x < p.Wi;
+        cp_async_16z(dst + 4 + 4 * it, ok ? src + x : xs_n, ok);
+      } else {
+        const int sx = vec ? (it == TX / 4 ? 0 : TX + 1) : it;  // tile-relative column incl. halo (0 .. TX+1)
+        const int x = qx0 - 1 + sx;
+        const bool ok = rowok && x >= 0 && x < p.Wi;
+        cp_async_4(reinterpret_cast<float*>(dst + 3 + sx), reinterpret_cast<const float*>(ok ? src + x : xs_n), ok);
       }
-      uint32_t hi, lo;
-      split_pack(ok ? leaky(r0) : 0.f, ok ? leaky(r1) : 0.f, hi, lo);
-      sHi[pair * PS + so] = hi;
-      sLo[pair * PS + so] = lo;
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+  // ---- cp.async of the 16 raw residual channels (fp32, replicate-clamped = the upsample's border rule)
+  const bool vec_in = vec && (p.in_cstride & 3) == 0 && (p.in_nstride & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
+  auto fetch_res = [&](int b) {
+    float* dbuf = reinterpret_cast<float*>(s_mma + b * 16 * PS);
+    constexpr int IT = TX / 4 + 2;
+    const int total = 16 * 3 * SY * IT;
+    for (int e = tid; e < total; e += 128) {
+      const int r = e / IT, it = e - r * IT;
+      const int sy = r % SY, sz = (r / SY) % 3, c = r / (3 * SY);
+      const int zc = min(max(qz - 1 + sz, 0), p.Di - 1), yc = min(max(qy0 - 1 + sy, 0), p.Hi - 1);
+      const float* src = in_n + (co0 + c) * p.in_cstride + (static_cast<long long>(zc) * p.Hi + yc) * p.Wi;
+      float* dst = dbuf + c * PS + (sz * SY + sy) * SX;
+      if (it < TX / 4) {
+        const int x = qx0 + 4 * it;
+        if (vec_in && x + 3 < p.Wi) {
+          cp_async_16(dst + 4 + 4 * it, src + x);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cp_async_4(dst + 4 + 4 * it + i, src + min(x + i, p.Wi - 1), true);
+        }
+      } else {
+        const int sx = it == TX / 4 ? 0 : TX + 1;
+        cp_async_4(dst + 3 + sx, src + min(max(qx0 - 1 + sx, 0), p.Wi - 1), true);
+      }
+    }
+    cp_async_commit();
+  };
+
+  const int rb = nchunks & 1;  // buffer the last chunk does not use: the residual channels land there
+  fetch_chunk(0, 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    cp_async_wait<0>();
+    __syncthreads();  // chunk ch has landed; every warp is done with chunk ch - 1, whose buffer is refilled now
+    if (!(p.debug & 4)) {
+      if (ch + 1 < nchunks) fetch_chunk(ch + 1, (ch + 1) & 1);
+      else fetch_res(rb);
+    }
+    const uint32_t* sHi = s_mma + (ch & 1) * 16 * PS;
+    const uint32_t* sLo = sHi + 8 * PS;
     // ---- MMAs: 27 neighbour shifts, A fragments loaded once per shift
     const uint4* wq = p.wpk + (static_cast<size_t>(coblk) * nchunks + ch) * (64 * 2 * 32) + lane;
+    if (ch + 1 < nchunks) {
+      // next chunk's weights (64 KB) towards L2 while this chunk computes
+      const char* wn = reinterpret_cast<const char*>(wq - lane + 64 * 2 * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) prefetch_l2(wn + (tid + 128 * i) * 128);
+    }
+    constexpr int kAhead = 8;  // L1 prefetch distance in B-fragment visits (one visit = 512 B = 6 MMAs)
+#pragma unroll
+    for (int i = 0; i < kAhead; ++i) prefetch_l1(wq + i * 32);
+    if (p.debug & 2) continue;
+    uint4 bnext[2] = {__ldg(wq), __ldg(wq + 32)};
+    int v = 0;  // visit counter (tap): compile-time after unrolling
 #pragma unroll
     for (int sz = 0; sz < 3; ++sz)
 #pragma unroll
@@ -697,8 +778,8 @@ __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p
           uint32_t ah[2][4], al[2][4];
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const int b0 = (sz * SY + ty[j][0] + sy) * SX + tx[j][0] + sx;
-            const int b1 = (sz * SY + ty[j][1] + sy) * SX + tx[j][1] + sx;
+            const int b0 = (sz * SY + ty[j][0] + sy) * SX + tx[j][0] + sx + 3;
+            const int b1 = (sz * SY + ty[j][1] + sy) * SX + tx[j][1] + sx + 3;
             ah[j][0] = sHi[t * PS + b0];       ah[j][1] = sHi[t * PS + b1];
             ah[j][2] = sHi[(t + 4) * PS + b0]; ah[j][3] = sHi[(t + 4) * PS + b1];
             al[j][0] = sLo[t * PS + b0];       al[j][1] = sLo[t * PS + b1];
@@ -711,21 +792,32 @@ __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p
 #pragma unroll
               for (int ix = 0; ix < sh_ncomb(sx); ++ix) {
                 const int cls = sh_par(sz, iz) * 4 + sh_par(sy, iy) * 2 + sh_par(sx, ix);
-                const int k = (sh_tap(sz, iz) * 4 + sh_tap(sy, iy)) * 4 + sh_tap(sx, ix);
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                  const uint4 b = __ldg(wq + (k * 2 + nt) * 32);
-#pragma unroll
-                  for (int j = 0; j < 2; ++j) {
-                    mma16816(acc[cls][j][nt], ah[j], b.x, b.y);
-                    mma16816(acc[cls][j][nt], al[j], b.x, b.y);
-                    mma16816(acc[cls][j][nt], ah[j], b.z, b.w);
-                  }
+                const uint4 b[2] = {bnext[0], bnext[1]};
+                if (v + 1 < 64) {
+                  bnext[0] = __ldg(wq + (2 * v + 2) * 32);
+                  bnext[1] = __ldg(wq + (2 * v + 3) * 32);
                 }
+                if (2 * v + kAhead < 128) {
+                  prefetch_l1(wq + (2 * v + kAhead) * 32);
+                  prefetch_l1(wq + (2 * v + kAhead + 1) * 32);
+                }
+                ++v;
+                // term-major order: the three split terms of one accumulator are 4 MMAs apart (mma.sync on the same
+                // accumulator serialises on the previous result)
+#pragma unroll
+                for (int term = 0; term < 3; ++term)
+#pragma unroll
+                  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                      mma16816(acc[cls][j][nt], term == 1 ? al[j] : ah[j], term == 2 ? b[nt].z : b[nt].x,
+                               term == 2 ? b[nt].w : b[nt].y);
               }
         }
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();  // raw residual channels co0 .. co0+15 (replicate-clamped) have landed in buffer rb
+  const float* sRaw = reinterpret_cast<const float*>(s_mma + rb * 16 * PS);
 
   // ---- epilogue: out = BN( acc * 2^-wexp + bias + upsample2x(raw in[co]) ), cropped to (Do, Ho, Wo)
   const float inv = exp2f(static_cast<float>(-p.wexp));
@@ -743,15 +835,15 @@ __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p
         for (int h = 0; h < 2; ++h) {
           const int xl = tx[j][h], yl = ty[j][h];
           const int qx = qx0 + xl, qy = qy0 + yl;
-          if (qx >= p.Wi || qy >= p.Hi) continue;
+          if (qx >= p.Wi || qy >= p.Hi || (p.debug & 8)) continue;
           // separable 0.25 / 0.75 interpolation of the 3x3x3 raw neighbourhood -> the 8 class values
           float ax[3][3][2];
 #pragma unroll
           for (int dz = 0; dz < 3; ++dz)
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-              const float* row = sRes + cl * RS + (dz * SY + yl + dy) * SX + xl;
-              const float v0 = row[0], v1 = row[1], v2 = row[2];
+              const float* row = sRaw + cl * PS + (dz * SY + yl + dy) * SX + xl + 3;
+              const float v0 = (p.debug & 1) ? 0.f : row[0], v1 = (p.debug & 1) ? 0.f : row[1], v2 = (p.debug & 1) ? 0.f : row[2];
               ax[dz][dy][0] = 0.25f * v0 + 0.75f * v1;
               ax[dz][dy][1] = 0.75f * v1 + 0.25f * v2;
             }
@@ -788,8 +880,27 @@ __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p
     }
 }
 
+// Layer input [N][cin] planes (explicit strides) -> xsplit [2 (hi, lo)][N][cin/2][vol] words: leaky_relu, then the
+// hi / lo fp16 split of channels (2c, 2c+1) packed into one word each.
+__global__ void __launch_bounds__(256) reg_split_kernel(const float* __restrict__ in, long long in_nstride,
+                                                        long long in_cstride, int N, int cin, long long vol,
+                                                        uint32_t* __restrict__ xs) {
+  const long long per_n = static_cast<long long>(cin / 2) * vol, total = N * per_n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / per_n, r = i - n * per_n;
+    const long long c = r / vol, v = r - c * vol;
+    const float* src = in + n * in_nstride + 2 * c * in_cstride + v;
+    uint32_t hi, lo;
+    split_pack(leaky(__ldg(src)), leaky(__ldg(src + in_cstride)), hi, lo);
+    xs[i] = hi;
+    xs[total + i] = lo;
+  }
+}
+
 // w [cin][64][cout] fp32 -> B fragments of mma.sync.m16n8k16 (col-major B: k = input channel within the chunk,
-// n = output channel within the 8-wide n-tile), split into hi / lo fp16 after scaling by 2^wexp.
+// n = output channel within the 8-wide n-tile), split into hi / lo fp16 after scaling by 2^wexp; taps in the
+// kernel's visit order (visit_tap).
 __global__ void reg_pack_convt4_kernel(const float* __restrict__ w, int cin, int cout, int wexp, uint4* __restrict__ wpk) {
   const long long total = static_cast<long long>(cout / 16) * (cin / 16) * 64 * 2 * 32;
   const float sc = exp2f(static_cast<float>(wexp));
@@ -798,7 +909,7 @@ __global__ void reg_pack_convt4_kernel(const float* __restrict__ w, int cin, int
     long long r = i;
     const int lane = r % 32; r /= 32;
     const int nt = r % 2; r /= 2;
-    const int k = r % 64; r /= 64;
+    const int k = visit_tap(static_cast<int>(r % 64)); r /= 64;
     const int ch = r % (cin / 16);
     const int coblk = static_cast<int>(r / (cin / 16));
     const int g = lane >> 2, t = lane & 3;
@@ -1181,9 +1292,15 @@ static void convt4_mma_dispatch(const ConvT4Params& p, cudaStream_t st) {
                          static_cast<int>(Cfg::smem_bytes));
     configured = true;
   }
+  const long long vol = static_cast<long long>(p.Di) * p.Hi * p.Wi;
+  reg_split_kernel<<<grid_for(p.N * (p.cin / 2) * vol, 256, 16), 256, 0, st>>>(p.in, p.in_nstride, p.in_cstride, p.N,
+                                                                              p.cin, vol, p.xsplit);
   const int ntx = (p.Wi + TX - 1) / TX, nty = (p.Hi + Cfg::TY - 1) / Cfg::TY;
   dim3 g(static_cast<unsigned>(ntx) * nty * p.Di, p.cout / 16, p.N);
-  convt4_mma_kernel<TX><<<g, 128, Cfg::smem_bytes, st>>>(p);
+  static const int dbg = getenv("OAI_CONVT4_DEBUG") ? atoi(getenv("OAI_CONVT4_DEBUG")) : 0;
+  ConvT4Params q = p;
+  q.debug = dbg;
+  convt4_mma_kernel<TX><<<g, 128, Cfg::smem_bytes, st>>>(q);
 }
 
 int reg_pack_convt4_launch(const float* w, int cin, int cout, int wexp, uint4* wpk, cudaStream_t st) {
@@ -1194,10 +1311,11 @@ int reg_pack_convt4_launch(const float* w, int cin, int cout, int wexp, uint4* w
 
 int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
   const long long nout = static_cast<long long>(p.Do) * p.Ho * p.Wo;
-  if (p.wpk && p.cin % 16 == 0 && p.cout % 16 == 0) {
+  // levels narrower than 12 lattice points (the two deepest) stay on the fp32 parity-class kernel: their 3x3 / 6x6
+  // planes fill too little of an MMA tile (measured 0.57 ms vs 0.35 ms for 512 -> 256 at 3x6x6)
+  if (p.wpk && p.xsplit && p.cin % 16 == 0 && p.cout % 16 == 0 && p.Wi >= 12) {
     if (p.Wi > 16) convt4_mma_dispatch<32>(p, st);
-    else if (p.Wi > 8) convt4_mma_dispatch<16>(p, st);
-    else convt4_mma_dispatch<8>(p, st);
+    else convt4_mma_dispatch<16>(p, st);
     return launched("convt4_mma_kernel");
   }
   if (nout * ((p.cout + 7) / 8) >= (1 << 17) && p.cout % 8 == 0) {

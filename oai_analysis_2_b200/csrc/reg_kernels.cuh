@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdint>
+
 namespace oai {
 
 // Direct fp32 convolution, kernel 3, pad 1, stride 1 or 2, planar NCDHW tensors with explicit channel strides so a
@@ -33,10 +35,12 @@ struct ConvT4Params {
   long long out_nstride, out_cstride;
   int cout, Do, Ho, Wo;  // Do <= 2*Di etc. (crop)
   int N;
-  // optional split-fp16 weights for the mma.sync path (reg_pack_convt4_launch): [cout/16][cin/16][64][2][32] uint4 of
+  // optional split-fp16 weights for the mma.sync path (reg_pack_convt4_launch): [cout/16][cin/16][64 taps in visit order][2][32] uint4 of
   // B fragments (hi k0-7, hi k8-15, lo k0-7, lo k8-15), scaled by 2^wexp
   const uint4* wpk;
   int wexp;
+  int debug;         // development switches (OAI_CONVT4_DEBUG): 1 no residual, 2 no MMAs, 4 no staging, 8 no stores
+  uint32_t* xsplit;  // workspace of N*cin*Di*Hi*Wi words for the mma.sync path: the layer input as hi / lo fp16 pairs
 };
 
 struct ChainParams {

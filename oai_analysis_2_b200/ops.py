@@ -113,14 +113,23 @@ def reg_conv3(x, cin, w, bias, out, cout, stride, leaky_in, residual, out_scale=
     return out
 
 
-def reg_convt4(x, cin, w, bias, bn_scale, bn_shift, out, cout, wpk=None, wexp=0):
+_scratch = {}
+
+
+def reg_convt4(x, cin, w, bias, bn_scale, bn_shift, out, cout, wpk=None, wexp=0, workspace=None):
     N, _, D, H, W = x.shape
     od = _dims(*out.shape[2:])
     if wpk is not None:
+        need = N * cin * D * H * W * 4
+        if workspace is None or workspace.numel() < need:
+            key = (x.device, "convt4")
+            if key not in _scratch or _scratch[key].numel() < need:
+                _scratch[key] = torch.empty(need, dtype=torch.uint8, device=x.device)
+            workspace = _scratch[key]
         check(lib.oai_reg_convt4_mma(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(_dims(D, H, W)), ptr(w),
                                      ptr(wpk), wexp, ptr(bias), ptr(bn_scale), ptr(bn_shift), ptr(out),
-                                     c_ll(out.stride(0)), c_ll(out.stride(1)), cout, ptr(od), N, stream_ptr()),
-              "reg_convt4_mma")
+                                     c_ll(out.stride(0)), c_ll(out.stride(1)), cout, ptr(od), N, ptr(workspace),
+                                     c_size(workspace.numel()), stream_ptr()), "reg_convt4_mma")
         return out
     check(lib.oai_reg_convt4(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(_dims(D, H, W)), ptr(w),
                              ptr(bias), ptr(bn_scale), ptr(bn_shift), ptr(out), c_ll(out.stride(0)),

@@ -1,0 +1,35 @@
+"""Time single tallUNet2 up-path layers (oai_reg_convt4 / oai_reg_convt4_mma) at the GradICON shapes."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oai_analysis_2_b200 import ops  # noqa: E402
+
+SHAPES = [(48, 16, (40, 96, 96)), (96, 32, (20, 48, 48)), (192, 64, (10, 24, 24)), (512, 128, (5, 12, 12)),
+          (512, 256, (3, 6, 6))]
+which = [int(v) for v in sys.argv[1:]] or range(len(SHAPES))
+for i in which:
+    cin, cout, dims = SHAPES[i]
+    N = 2
+    x = torch.randn(N, cin, *dims, device="cuda")
+    w = (torch.randn(cin, 64, cout, device="cuda") * 0.05).contiguous()
+    b, s, t = torch.randn(cout, device="cuda"), torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda")
+    out = torch.empty(N, cout, *[2 * d for d in dims], device="cuda")
+    wpk, wexp = ops.reg_pack_convt4(w, cin, cout)
+    res = {}
+    for name, kw in (("mma", dict(wpk=wpk, wexp=wexp)), ("fp32", {})):
+        for _ in range(3):
+            ops.reg_convt4(x, cin, w, b, s, t, out, cout, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.reg_convt4(x, cin, w, b, s, t, out, cout, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / 10
+    gmac = N * cin * cout * 64 * dims[0] * dims[1] * dims[2] / 1e9
+    print(json.dumps(dict(cin=cin, cout=cout, dims=dims, gmac=gmac, ms_mma=res["mma"], ms_fp32=res["fp32"],
+                          tflops_mma=2 * gmac / res["mma"], tflops_fp32=2 * gmac / res["fp32"])), flush=True)
