@@ -147,8 +147,23 @@ def run_b200(args):
     vols_pin = [torch.from_numpy(v).pin_memory() for v in vols_h]
     verts_pin = torch.from_numpy(verts_h).pin_memory()
 
+    import ctypes
+    launches_per_step = None
+    if not args.no_graph:
+        # the whole per-knee path is one CUDA graph; the conv profiling events are recorded inside it
+        mark = {}
+
+        def on_record():
+            _lib.lib.oai_profile_begin()
+            mark["n0"] = _lib.launch_count()
+
+        pipe.capture(vols_d[0].shape, geom, verts_d.shape[0], on_record)
+        launches_per_step = _lib.launch_count() - mark["n0"]   # kernels recorded into the graph = launches per replay
+
     def step_device(i):
-        return pipe.run_device(vols_d[i % len(vols_d)], geom, verts_d)
+        if args.no_graph:
+            return pipe.run_device(vols_d[i % len(vols_d)], geom, verts_d)
+        return pipe.run_device_graph(vols_d[i % len(vols_d)], geom, verts_d)
 
     for i in range(args.warmup):
         step_device(i)
@@ -160,18 +175,23 @@ def run_b200(args):
         sampler.start()
     torch.cuda.synchronize()
     n0 = _lib.launch_count()
-    _lib.lib.oai_profile_begin()
+    if args.no_graph:
+        _lib.lib.oai_profile_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         step_device(i)
     e1.record()
     torch.cuda.synchronize()
-    import ctypes
     conv_ms, conv_n, conv_fl, conv_xfl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_double()
     _lib.check(_lib.lib.oai_profile_end(ctypes.byref(conv_ms), ctypes.byref(conv_n), ctypes.byref(conv_fl),
                                         ctypes.byref(conv_xfl)), "profile")
-    launches = _lib.launch_count() - n0
+    if args.no_graph:
+        launches = _lib.launch_count() - n0
+        prof_steps = args.steps
+    else:  # the events inside the graph hold the timings of the last replay: one step's worth of conv launches
+        launches = launches_per_step * args.steps
+        prof_steps = 1
     sharding.barrier(world)
     clocks = sampler.stop() if rank == 0 else None
     ms = sharding.max_over_ranks(e0.elapsed_time(e1), world)
@@ -192,15 +212,23 @@ def run_b200(args):
                d2h_bytes_per_step=int(res["d2h_bytes"]), ms_per_step=1e3 * e2e_s / args.steps)
 
     peaks = load_peaks()
+    traffic, traffic_src = None, None
+    try:   # per-launch DRAM bytes of the conv kernel from the committed ncu capture of this same command
+        with open(os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")) as f:
+            t = json.load(f)
+        traffic, traffic_src = float(t["dram_bytes_per_launch"]), "profiles/r01_conv_dram_traffic.json"
+    except Exception:  # noqa: BLE001
+        pass
     conv_tflops = conv_fl.value / (conv_ms.value * 1e-3) / 1e12 if conv_ms.value > 0 else 0.0
     exec_tflops = conv_xfl.value / (conv_ms.value * 1e-3) / 1e12 if conv_ms.value > 0 else 0.0
     roofline = dict(bound="tensor", kernel="conv_igemm_kernel (tcgen05 implicit-GEMM conv3d)",
                     achieved=conv_tflops, peak=peaks["tflops"], unit="TFLOP/s", frac=conv_tflops / peaks["tflops"],
                     peak_source=peaks["source"] + " cuBLAS bf16 (fp16 runs at the same tcgen05 kind::f16 rate)",
-                    traffic=None, launches_per_step=conv_n.value / args.steps,
-                    kernel_ms_per_step=conv_ms.value / args.steps, share_of_step=conv_ms.value / (ms / 1.0) if ms else None,
-                    algorithmic_flops_per_step=conv_fl.value / args.steps,
-                    executed_flops_per_step=conv_xfl.value / args.steps, executed_tflops=exec_tflops,
+                    traffic=traffic, traffic_source=traffic_src, launches_per_step=conv_n.value / prof_steps,
+                    kernel_ms_per_step=conv_ms.value / prof_steps,
+                    share_of_step=(conv_ms.value / prof_steps) / ms_per_step if ms else None,
+                    algorithmic_flops_per_step=conv_fl.value / prof_steps,
+                    executed_flops_per_step=conv_xfl.value / prof_steps, executed_tflops=exec_tflops,
                     executed_frac=exec_tflops / peaks["tflops"],
                     note="achieved = algorithmic FLOPs (every MAC the reference executes on its tile grid) / kernel "
                          "time; executed_* counts only the MACs issued after dead-halo elimination (decoder outputs "
@@ -311,6 +339,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--tiles-per-batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

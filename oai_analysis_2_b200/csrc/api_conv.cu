@@ -177,6 +177,14 @@ struct ProfEntry {
   double flops;       // algorithmic: every MAC the reference executes for this layer
   double exec_flops;  // MACs actually issued (dead-halo rows skipped)
 };
+
+// Inside a stream capture (the per-knee CUDA graph) the profiling events become external event-record nodes: every
+// replay re-records them, so oai_profile_end reports the conv launches of the most recent replay.
+inline void prof_record(cudaEvent_t ev, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  cudaEventRecordWithFlags(ev, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
 std::vector<ProfEntry> g_prof;
 size_t g_prof_used = 0;
 bool g_prof_on = false;
@@ -380,10 +388,10 @@ static int conv_common(const void* src0, int c0, const void* src1, int c1, int N
     pe = &g_prof[g_prof_used++];
     pe->flops = 2.0 * NT * D * H * W * static_cast<double>(cout) * (c0 + c1) * (pointwise ? 1 : 27);
     pe->exec_flops = pe->flops * (static_cast<double>(d_cnt) * hp_cnt * pl.TH) / (static_cast<double>(D) * H);
-    cudaEventRecord(pe->a, st);
+    prof_record(pe->a, st);
   }
   cudaError_t e = conv_igemm_launch(p, tm0, tm1, num_sms(), st);
-  if (pe) cudaEventRecord(pe->b, st);
+  if (pe) prof_record(pe->b, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_cuda(e, "conv_igemm launch");
 }

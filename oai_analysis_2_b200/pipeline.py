@@ -38,6 +38,45 @@ class KneePipeline:
                                               tr_BA.to_network_space)
         return out
 
+    # -- CUDA graph of the whole per-knee path (about a hundred launches; replaying one graph removes the launch gaps)
+    def capture(self, vol_shape, geom, n_vertices=None, on_record=None):
+        """Record run_device for volumes of `vol_shape` (and `n_vertices` mesh vertices) into a CUDA graph with static
+        input / output buffers.  Afterwards run_device_graph / run replay it."""
+        dev = self.device
+        self._g_vol = torch.zeros(tuple(vol_shape), dtype=torch.float32, device=dev)
+        self._g_verts = None if not n_vertices else torch.zeros((int(n_vertices), 3), dtype=torch.float64, device=dev)
+        self._g_geom = geom
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # eager pass: packs weights, sizes the kernels' static buffers
+            self.run_device(self._g_vol, geom, self._g_verts)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        torch.cuda.empty_cache()
+        self._graph = torch.cuda.CUDAGraph()
+        if on_record is not None:
+            on_record()   # e.g. switch the library's per-launch profiling events on for the recorded pass only
+        with torch.cuda.graph(self._graph):
+            self._g_out = self.run_device(self._g_vol, geom, self._g_verts)
+        return self
+
+    def _graph_matches(self, vol, geom, vertices):
+        return (getattr(self, "_graph", None) is not None and tuple(vol.shape) == tuple(self._g_vol.shape)
+                and geom is self._g_geom
+                and ((vertices is None) == (self._g_verts is None))
+                and (vertices is None or tuple(vertices.shape) == tuple(self._g_verts.shape)))
+
+    def run_device_graph(self, vol, geom, vertices=None):
+        """Same contract as run_device; the returned tensors are the graph's static outputs (overwritten by the next
+        replay)."""
+        if not self._graph_matches(vol, geom, vertices):
+            return self.run_device(vol, geom, vertices)
+        self._g_vol.copy_(vol, non_blocking=True)
+        if vertices is not None:
+            self._g_verts.copy_(vertices, non_blocking=True)
+        self._graph.replay()
+        return self._g_out
+
     def _pin(self, name, shape, dtype):
         key = (name, tuple(shape), dtype)
         if key not in self._pinned:
@@ -49,11 +88,14 @@ class KneePipeline:
         (views of reused pinned buffers) + the two transforms."""
         vol_h = torch.as_tensor(volume)
         geom = geom or Geometry(tuple(vol_h.shape)[::-1])
-        vol = vol_h.to(self.device, non_blocking=True)
-        verts = None
-        if vertices is not None:
-            verts = torch.as_tensor(vertices, dtype=torch.float64).to(self.device, non_blocking=True)
-        r = self.run_device(vol, geom, verts)
+        verts_h = None if vertices is None else torch.as_tensor(vertices, dtype=torch.float64)
+        if self._graph_matches(vol_h, geom, verts_h):
+            r = self.run_device_graph(vol_h, geom, verts_h)   # H2D straight into the graph's static inputs
+            verts = verts_h
+        else:
+            vol = vol_h.to(self.device, non_blocking=True)
+            verts = None if verts_h is None else verts_h.to(self.device, non_blocking=True)
+            r = self.run_device(vol, geom, verts)
         res = {}
         w = self._pin("warped", r["warped"].shape, torch.float32)
         w.copy_(r["warped"], non_blocking=True)
