@@ -204,6 +204,21 @@ OAI_API int oai_warp_volume(const float* src, int C, const int* src_dims, const 
 OAI_API int oai_warp_points(const double* pts, long long n, const float* disp, const int* field_dims,
                             const double* phys_to_net, const double* net_to_phys, double* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Intensity pre-normalisation (oai_analysis/dask_processing.py:10-26 image_normalize, called at :75 and
+ * :177 right before registration and segmentation):
+ *   wmin, wmax = np.percentile(volume, perc_lo), np.percentile(volume, perc_hi)      (numpy "linear" method)
+ *   out = itk.IntensityWindowingImageFilter(window [wmin, wmax] -> [out_min, out_max])
+ * in / out: n float32 voxels on the device (in 16-byte aligned; out may alias in).  The order statistics come from an
+ * exact three-pass radix select on the device, no host synchronisation.  workspace: oai_intensity_window_workspace()
+ * bytes of device memory, 8-byte aligned; afterwards it holds the window, readable with oai_intensity_window_result
+ * (copies {wmin, wmax} to the host and synchronises the stream).
+ * ------------------------------------------------------------------------------------------------------------ */
+OAI_API size_t oai_intensity_window_workspace(void);
+OAI_API int oai_intensity_window(const float* in, long long n, double perc_lo, double perc_hi, float out_min,
+                                 float out_max, float* out, void* workspace, size_t workspace_bytes, void* stream);
+OAI_API int oai_intensity_window_result(const void* workspace, double* window_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -255,3 +255,24 @@ def convt2_igemm(src, wpack, bias, cout, relu=True, ab_format=0, region=None, ou
     check(lib.oai_convt2_igemm(ptr(src), cin, NT, D, H, W, ptr(wpack), c_size(wpack.numel()), ptr(bias), cout,
                                int(relu), ab_format, ptr(out), ptr(reg), stream_ptr()), "convt2_igemm")
     return out
+
+
+def intensity_window(vol, perc_lo=0.1, perc_hi=99.9, out_min=0.0, out_max=1.0, out=None, return_window=False):
+    """dask_processing.image_normalize on the device: vol float32 cuda tensor (any shape, contiguous) -> windowed copy
+    (or in place with out=vol).  return_window=True also returns (window_min, window_max) (synchronises)."""
+    assert vol.dtype == torch.float32 and vol.is_contiguous()
+    if out is None:
+        out = torch.empty_like(vol)
+    nbytes = int(lib.oai_intensity_window_workspace())
+    key = (vol.device, "window")
+    if key not in _scratch or _scratch[key].numel() < nbytes:
+        _scratch[key] = torch.empty(nbytes, dtype=torch.uint8, device=vol.device)
+    ws = _scratch[key]
+    check(lib.oai_intensity_window(ptr(vol), c_ll(vol.numel()), ctypes.c_double(perc_lo), ctypes.c_double(perc_hi),
+                                   c_float(out_min), c_float(out_max), ptr(out), ptr(ws), c_size(nbytes),
+                                   stream_ptr()), "intensity_window")
+    if return_window:
+        w = (ctypes.c_double * 2)()
+        check(lib.oai_intensity_window_result(ptr(ws), w, stream_ptr()), "intensity_window_result")
+        return out, (w[0], w[1])
+    return out

@@ -60,6 +60,14 @@ def main():
         ms = timeit(lambda: ops.compose((n, n, n), u, False))
         b = 36 * n ** 3
         print(json.dumps(dict(op="compose2", n=n, ms=ms, gbs=b / ms / 1e6, frac_of_measured_hbm=b / ms / 1e6 / peak)), flush=True)
+    # intensity windowing of one knee: 3 histogram reads + 1 apply read + 1 write = 20 B / voxel
+    vol = torch.rand(160, 384, 384, device="cuda") * 900.0
+    out = torch.empty_like(vol)
+    flush.zero_()
+    ms = timeit(lambda: ops.intensity_window(vol, 0.1, 99.9, 0.0, 1.0, out=out))
+    b = 20 * vol.numel()
+    print(json.dumps(dict(op="intensity_window", n=[160, 384, 384], ms=ms, gbs=b / ms / 1e6,
+                          frac_of_measured_hbm=b / ms / 1e6 / peak)), flush=True)
 
 
 if __name__ == "__main__":
