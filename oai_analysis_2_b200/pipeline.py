@@ -77,6 +77,85 @@ class KneePipeline:
         self._graph.replay()
         return self._g_out
 
+    def run_stream(self, items, return_fields=True):
+        """Throughput form of run() for a sequence of knees: `items` yields (volume, vertices) host buffers (pinned for
+        real overlap) matching the captured graph.  The H2D copy of knee i+1 and the D2H copy of knee i-1 run on their
+        own streams while knee i computes (device staging buffers on both sides of the graph's static I/O).  Yields one
+        result dict per knee, in order; its arrays are views of double-buffered pinned memory and stay valid until the
+        generator has been advanced twice more."""
+        if getattr(self, "_graph", None) is None:
+            raise RuntimeError("run_stream needs KneePipeline.capture() first")
+        dev = self.device
+        comp = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_rs"):
+            g = self._g_out
+            outs = {"warped": g["warped"], "phi_AB": g["phi_AB"].disp, "phi_BA": g["phi_BA"].disp}
+            if self._g_verts is not None:
+                outs["verts"] = g["vertices"]
+            self._rs = dict(
+                h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev), outs=outs,
+                vol=[torch.empty_like(self._g_vol) for _ in range(2)],
+                verts=[None if self._g_verts is None else torch.empty_like(self._g_verts) for _ in range(2)],
+                dstage=[{k: torch.empty_like(v) for k, v in outs.items()} for _ in range(2)],
+                host=[{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in outs.items()}
+                      for _ in range(2)],
+                ev_h2d=[torch.cuda.Event() for _ in range(2)], ev_comp=[torch.cuda.Event() for _ in range(2)],
+                ev_d2h=[torch.cuda.Event() for _ in range(2)])
+        rs = self._rs
+        keys = [k for k in rs["outs"] if return_fields or not k.startswith("phi")]
+
+        def upload(item, b):
+            vol_h, verts_h = item
+            with torch.cuda.stream(rs["h2d"]):
+                rs["h2d"].wait_event(rs["ev_comp"][b])      # the compute that last read this staging slot is done
+                rs["vol"][b].copy_(torch.as_tensor(vol_h), non_blocking=True)
+                if rs["verts"][b] is not None:
+                    rs["verts"][b].copy_(torch.as_tensor(verts_h, dtype=torch.float64), non_blocking=True)
+                rs["ev_h2d"][b].record(rs["h2d"])
+
+        def result(b):
+            rs["ev_d2h"][b].synchronize()
+            h = rs["host"][b]
+            res = {"FC_atlas": h["warped"][0].numpy(), "TC_atlas": h["warped"][1].numpy(),
+                   "phi_AB": self._g_out["phi_AB"], "phi_BA": self._g_out["phi_BA"]}
+            if return_fields:
+                res["phi_AB_field"], res["phi_BA_field"] = h["phi_AB"].numpy(), h["phi_BA"].numpy()
+            if "verts" in h:
+                res["vertices_atlas"] = h["verts"].numpy()
+            res["d2h_bytes"] = sum(h[k].numel() * h[k].element_size() for k in keys)
+            res["h2d_bytes"] = self._g_vol.numel() * 4 + (0 if self._g_verts is None else self._g_verts.numel() * 8)
+            return res
+
+        it = iter(items)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        upload(nxt, 0)
+        i = 0
+        while nxt is not None:
+            b = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(nxt, b ^ 1)                           # flies while knee i computes
+            comp.wait_event(rs["ev_h2d"][b])
+            self._g_vol.copy_(rs["vol"][b], non_blocking=True)
+            if self._g_verts is not None:
+                self._g_verts.copy_(rs["verts"][b], non_blocking=True)
+            self._graph.replay()
+            comp.wait_event(rs["ev_d2h"][b])                 # the D2H that last read this output slot is done
+            for k in keys:
+                rs["dstage"][b][k].copy_(rs["outs"][k], non_blocking=True)
+            rs["ev_comp"][b].record(comp)
+            with torch.cuda.stream(rs["d2h"]):
+                rs["d2h"].wait_event(rs["ev_comp"][b])
+                for k in keys:
+                    rs["host"][b][k].copy_(rs["dstage"][b][k], non_blocking=True)
+                rs["ev_d2h"][b].record(rs["d2h"])
+            if i > 0:
+                yield result(b ^ 1)
+            i += 1
+        yield result((i - 1) & 1)
+
     def _pin(self, name, shape, dtype):
         key = (name, tuple(shape), dtype)
         if key not in self._pinned:
