@@ -134,9 +134,188 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
   }
 }
 
+// ---- tensor-path variant for C0 = 32 --------------------------------------------------------------------------------
+// Same block structure (4 rows x 128 x, rolling 3-slice window), but the 27-tap x 32-channel contraction of a row runs
+// on mma.sync.m16n8k16: M = 16 x-adjacent voxels, K = 27 taps padded to 32, N = 32 channels.  Input samples and
+// weights are split into fp16 hi + lo pairs and hi*hi + lo*hi + hi*lo is accumulated in fp32, so the result matches the
+// fp32 FMA kernel to ~2^-22 (the output is rounded to 16 bits anyway).  The window holds one word per sample,
+// (hi | lo << 16), split once when the slice is loaded; an A-fragment register is two such words re-paired with PRMT.
+// A warp owns one row: 8 m-tiles per slice, 24 MMAs each.  The n index of the B fragments is permuted (column n of
+// n-tile nt = channel 8 (n / 2) + 2 nt + n % 2) so that a lane's C fragments are 8 consecutive channels: one 16-byte
+// store per voxel, a warp store covers 8 voxels x 64 bytes contiguously.
+__device__ __forceinline__ void stem_mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void stem_split(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ uint32_t stem_split1(float x) {  // (fp16(x) | fp16(x - fp16(x)) << 16)
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn(x - __half2float(h));
+  return static_cast<uint32_t>(__half_as_ushort(h)) | (static_cast<uint32_t>(__half_as_ushort(l)) << 16);
+}
+
+__global__ void __launch_bounds__(128) stem_mma_kernel(const StemParams p) {
+  constexpr int SW = kStemTW + 2, SH = kStemTH + 2, C0 = 32;
+  __shared__ __align__(16) uint32_t s_in[3 * SH * SW];  // [3 slots][SH][SW] words (hi | lo << 16)
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, g = lane >> 2, t = lane & 3;
+
+  const int nbx = (p.tw + kStemTW - 1) / kStemTW, nby = (p.th + kStemTH - 1) / kStemTH;
+  int blk = blockIdx.x;
+  const int bx = blk % nbx; blk /= nbx;
+  const int by = blk % nby; blk /= nby;
+  const int tl = blk;  // tile within batch
+  const int tile = p.tile0 + tl;
+  const int tk = tile % p.gw, tj = (tile / p.gw) % p.gh, ti = tile / (p.gw * p.gh);
+  const int oz = ti * p.ed - p.od, oy = tj * p.eh - p.oh, ox = tk * p.ew - p.ow;
+  const int x0 = bx * kStemTW, y0 = by * kStemTH;
+
+  // a thread fills the same (row, x) positions of the window for every slice: their in-slice offsets (reflect padding,
+  // tile-border zeros) are computed once
+  constexpr int NE = (SH * SW + 127) / 128;
+  int eoff[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int i = tid + 128 * e;
+    eoff[e] = -1;
+    if (i < SH * SW) {
+      const int xx = i % SW, yy = i / SW;
+      const int ly = y0 + yy - 1, lx = x0 + xx - 1;
+      if (ly >= 0 && ly < p.th && lx >= 0 && lx < p.tw) {
+        int gy = oy + ly, gx = ox + lx;
+        if (gy < 0 || gy >= p.VH) gy = reflect_idx(gy, p.VH);
+        if (gx < 0 || gx >= p.VW) gx = reflect_idx(gx, p.VW);
+        eoff[e] = gy * p.VW + gx;
+      }
+    }
+  }
+  // slice lz (tile-local; -1 and td are the conv's zero padding at the TILE border) -> slot (lz + 3) % 3.  fetch() only
+  // issues the global loads; commit() splits and stores them, one slice later, so the latency hides behind the MMAs
+  auto fetch = [&](int lz, float (&v)[NE]) {
+    const bool zin = lz >= 0 && lz < p.td;
+    const float* src = p.vol + static_cast<size_t>(zin ? reflect_idx(oz + lz, p.VD) : 0) * p.VH * p.VW;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) v[e] = (zin && eoff[e] >= 0) ? __ldg(src + eoff[e]) : 0.f;
+  };
+  auto commit = [&](int lz, const float (&v)[NE]) {
+    uint32_t* dst = s_in + ((lz + 3) % 3) * SH * SW;
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+      if (tid + 128 * e < SH * SW) dst[tid + 128 * e] = stem_split1(v[e]);
+  };
+  float pv[NE];
+  fetch(-1, pv); commit(-1, pv);
+  fetch(0, pv);  commit(0, pv);
+  fetch(1, pv);
+
+  // B fragments (weights) and the bias stay in registers for the whole block: k = tap (27 real + 5 zero),
+  // column n = g of n-tile nt = channel 8 (g / 2) + 2 nt + g % 2
+  uint32_t bh[2][4][2], bl[2][4][2];
+  float bias[4][2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = 16 * s + 8 * h + 2 * t, co = 8 * (g >> 1) + 2 * nt + (g & 1);
+        const float w0 = k < 27 ? __ldg(p.w + k * C0 + co) : 0.f, w1 = k + 1 < 27 ? __ldg(p.w + (k + 1) * C0 + co) : 0.f;
+        stem_split(w0, w1, bh[s][nt][h], bl[s][nt][h]);
+      }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {   // C columns 2t, 2t+1 of n-tile nt = channels 8t + 2nt, 8t + 2nt + 1
+    bias[nt][0] = __ldg(p.b + 8 * t + 2 * nt);
+    bias[nt][1] = __ldg(p.b + 8 * t + 2 * nt + 1);
+  }
+  // this thread's 8 taps (A columns 2t, 2t+1, 2t+8, 2t+9 of both k-steps): slice selector and in-slice offset
+  int tkd[8], trel[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = 16 * (i >> 2) + 8 * ((i >> 1) & 1) + 2 * t + (i & 1);
+    const int kk = k < 27 ? k : 0;   // padded taps read a valid sample; their weights are zero
+    tkd[i] = kk / 9;
+    trel[i] = ((kk / 3) % 3) * SW + kk % 3;
+  }
+  const int ly = wrp, y = y0 + ly;
+  int slot0 = 2;   // slot of slice d - 1 = (d + 2) % 3
+  for (int d = 0; d < p.td; ++d) {
+    commit(d + 1, pv);
+    __syncthreads();
+    fetch(d + 2, pv);   // in flight while slice d computes
+    if (y < p.th) {
+      int off[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int sl = slot0 + tkd[i];
+        sl = sl >= 3 ? sl - 3 : sl;
+        off[i] = sl * SH * SW + trel[i] + ly * SW + g;
+      }
+      uint16_t* row_out = reinterpret_cast<uint16_t*>(p.out) +
+                          (((static_cast<size_t>(tl) * p.td + d) * p.th + y) * p.tw + x0) * C0;
+#pragma unroll 2
+      for (int j = 0; j < kStemTW / 16; ++j) {
+        if (x0 + 16 * j >= p.tw) break;
+        // A fragments: rows g / g+8 = voxels 16j+g / 16j+g+8, columns = taps; words (hi | lo << 16) re-paired
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {       // h: column half (taps 2t.. / 2t+8..)
+            const int i0 = 4 * s + 2 * h;
+            const uint32_t a0 = s_in[off[i0] + 16 * j], a1 = s_in[off[i0 + 1] + 16 * j];
+            const uint32_t c0 = s_in[off[i0] + 16 * j + 8], c1 = s_in[off[i0 + 1] + 16 * j + 8];
+            ah[s][2 * h] = __byte_perm(a0, a1, 0x5410);     al[s][2 * h] = __byte_perm(a0, a1, 0x7632);      // row g
+            ah[s][2 * h + 1] = __byte_perm(c0, c1, 0x5410); al[s][2 * h + 1] = __byte_perm(c0, c1, 0x7632);  // row g+8
+          }
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          acc[nt][0] = acc[nt][2] = bias[nt][0];
+          acc[nt][1] = acc[nt][3] = bias[nt][1];
+        }
+#pragma unroll
+        for (int term = 0; term < 3; ++term)
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+              stem_mma16816(acc[nt], term == 1 ? al[s] : ah[s], term == 2 ? bl[s][nt][0] : bh[s][nt][0],
+                            term == 2 ? bl[s][nt][1] : bh[s][nt][1]);
+        // ReLU + 16-bit pack: this lane holds channels 8t .. 8t+7 of voxels g (acc[.][0..1]) and g + 8 (acc[.][2..3])
+        uint4 o0, o1;
+        o0.x = pack16(fmaxf(acc[0][0], 0.f), fmaxf(acc[0][1], 0.f), p.fmt);
+        o0.y = pack16(fmaxf(acc[1][0], 0.f), fmaxf(acc[1][1], 0.f), p.fmt);
+        o0.z = pack16(fmaxf(acc[2][0], 0.f), fmaxf(acc[2][1], 0.f), p.fmt);
+        o0.w = pack16(fmaxf(acc[3][0], 0.f), fmaxf(acc[3][1], 0.f), p.fmt);
+        o1.x = pack16(fmaxf(acc[0][2], 0.f), fmaxf(acc[0][3], 0.f), p.fmt);
+        o1.y = pack16(fmaxf(acc[1][2], 0.f), fmaxf(acc[1][3], 0.f), p.fmt);
+        o1.z = pack16(fmaxf(acc[2][2], 0.f), fmaxf(acc[2][3], 0.f), p.fmt);
+        o1.w = pack16(fmaxf(acc[3][2], 0.f), fmaxf(acc[3][3], 0.f), p.fmt);
+        const int xa = x0 + 16 * j + g, xb = xa + 8;
+        if (xa < p.tw) *reinterpret_cast<uint4*>(row_out + static_cast<size_t>(16 * j + g) * C0 + 8 * t) = o0;
+        if (xb < p.tw) *reinterpret_cast<uint4*>(row_out + static_cast<size_t>(16 * j + g + 8) * C0 + 8 * t) = o1;
+      }
+    }
+    __syncthreads();  // everyone is done with slice d-1 before its slot is overwritten by slice d+2
+    slot0 = slot0 == 2 ? 0 : slot0 + 1;
+  }
+}
+
 int stem_launch(const StemParams& p, cudaStream_t st) {
   const int nbx = (p.tw + kStemTW - 1) / kStemTW, nby = (p.th + kStemTH - 1) / kStemTH;
   const long long blocks = static_cast<long long>(p.ntiles) * nby * nbx;
+  static const bool no_mma = getenv("OAI_STEM_FP32") != nullptr;   // A/B switch: the fp32 FMA kernel
+  if (p.c0 == 32 && !no_mma) {
+    stem_mma_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(p);
+    return launched("stem_mma_kernel");
+  }
   const size_t smem = (27 * p.c0 + p.c0 + 3 * (kStemTH + 2) * (kStemTW + 2)) * sizeof(float);
   stem_kernel<<<static_cast<unsigned>(blocks), 128, smem, st>>>(p);
   return launched("stem_kernel");
