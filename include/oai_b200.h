@@ -137,7 +137,12 @@ OAI_API int oai_seg_head(const void* act, int C, int ncls, const float* w, const
 OAI_API int oai_reg_conv3(const float* in, long long in_nstride, long long in_cstride, int cin, const int* in_dims,
                           const float* w, const float* bias, float* out, long long out_nstride, long long out_cstride,
                           int cout, int cout_pad, int N, int stride, int leaky_in, int residual, float out_scale,
-                          void* stream);
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Optional device scratch for oai_reg_conv3 (may be NULL / 0): with oai_reg_conv3_workspace(...) bytes the deep
+ * levels (stride 2, cin >= 64, at most 4096 output voxels over the batch: weight-streaming GEMMs) run split-K over
+ * blocks with a fixed-order (deterministic) reduction; returns 0 for layers that do not use it. */
+OAI_API size_t oai_reg_conv3_workspace(int cin, int cout, const int* in_dims, int N, int stride, int leaky_in);
 
 /* icon networks.UNet2 up step: BatchNorm3d(eval)( ConvTranspose3d(k4,s2,p1)(leaky_relu(in)) +
  * F.interpolate(in[:, :cout], scale_factor=2, trilinear, align_corners=False) ), cropped to out_dims.
@@ -155,7 +160,8 @@ OAI_API int oai_reg_pack_convt4(const float* w, int cin, int cout, int wexp, voi
 
 /* Same operator as oai_reg_convt4 (icon networks.UNet2 up step) on the tensor path: implicit GEMM with
  * mma.sync.m16n8k16, operands split into fp16 hi + lo pairs (hi*hi + lo*hi + hi*lo, fp32 accumulate: fp32-level
- * accuracy).  Levels narrower than 12 input points run the fp32 kernels of oai_reg_convt4 on w; workspace: see
+ * accuracy).  Levels narrower than 12 input points run as split-K fp32 GEMMs on w (deterministic reduction);
+ * workspace: see
  * oai_reg_convt4_mma_workspace (16-byte aligned). */
 OAI_API int oai_reg_convt4_mma(const float* in, long long in_nstride, long long in_cstride, int cin,
                                const int* in_dims, const float* w, const void* wpk, int wexp, const float* bias,
@@ -163,9 +169,10 @@ OAI_API int oai_reg_convt4_mma(const float* in, long long in_nstride, long long 
                                long long out_cstride, int cout, const int* out_dims, int N, void* workspace,
                                size_t workspace_bytes, void* stream);
 
-/* Bytes of caller-owned device scratch oai_reg_convt4_mma needs (the layer input rewritten once as leaky-ReLU'd
- * hi / lo fp16 channel pairs): N * cin * D * H * W * 4. */
-OAI_API size_t oai_reg_convt4_mma_workspace(int cin, const int* in_dims, int N);
+/* Bytes of caller-owned device scratch oai_reg_convt4_mma needs: the layer input rewritten once as leaky-ReLU'd
+ * hi / lo fp16 channel pairs (N * cin * D * H * W * 4), or, for levels narrower than 12 points, the split-K partial
+ * sums of their fp32 GEMM form. */
+OAI_API size_t oai_reg_convt4_mma_workspace(int cin, int cout, const int* in_dims, int N);
 
 /* Composition of displacement maps and image warp, fused (icon network_wrappers.TwoStepRegistration /
  * FunctionFromVectorField closures; mermaidlite.compute_warped_image_multiNC == F.grid_sample(bilinear, border,

@@ -16,10 +16,19 @@ Affine3 affine_from(const double* a) {
 }
 }  // namespace
 
+extern "C" size_t oai_reg_conv3_workspace(int cin, int cout, const int* in_dims, int N, int stride, int leaky_in) {
+  if (!in_dims || cin <= 0 || cout <= 0 || N <= 0 || stride < 1) return 0;
+  Conv3Params p{};
+  p.cin = cin; p.cout = cout; p.N = N; p.stride = stride; p.leaky_in = leaky_in;
+  p.Di = in_dims[0]; p.Hi = in_dims[1]; p.Wi = in_dims[2];
+  p.Do = (p.Di - 1) / stride + 1; p.Ho = (p.Hi - 1) / stride + 1; p.Wo = (p.Wi - 1) / stride + 1;
+  return conv3_splitk_bytes(p);
+}
+
 extern "C" int oai_reg_conv3(const float* in, long long in_nstride, long long in_cstride, int cin, const int* in_dims,
                              const float* w, const float* bias, float* out, long long out_nstride,
                              long long out_cstride, int cout, int cout_pad, int N, int stride, int leaky_in,
-                             int residual, float out_scale, void* stream) {
+                             int residual, float out_scale, void* workspace, size_t workspace_bytes, void* stream) {
   OAI_REQUIRE(in && in_dims && w && bias && out, "reg_conv3: null pointer");
   OAI_REQUIRE(stride == 1 || stride == 2, "reg_conv3: stride %d unsupported", stride);
   OAI_REQUIRE(!residual || (stride == 2 && cout >= cin), "reg_conv3: residual needs stride 2 and cout >= cin");
@@ -30,6 +39,7 @@ extern "C" int oai_reg_conv3(const float* in, long long in_nstride, long long in
   p.cout = cout; p.cout_pad = cout_pad;
   p.Do = (p.Di - 1) / stride + 1; p.Ho = (p.Hi - 1) / stride + 1; p.Wo = (p.Wi - 1) / stride + 1;
   p.N = N; p.stride = stride; p.leaky_in = leaky_in; p.residual = residual; p.out_scale = out_scale;
+  p.splitk_ws = static_cast<float*>(workspace); p.splitk_bytes = workspace ? workspace_bytes : 0;
   return conv3_launch(p, static_cast<cudaStream_t>(stream));
 }
 
@@ -47,7 +57,7 @@ extern "C" int oai_reg_convt4(const float* in, long long in_nstride, long long i
   p.w = w; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
   p.out = out; p.out_nstride = out_nstride; p.out_cstride = out_cstride; p.cout = cout;
   p.Do = out_dims[0]; p.Ho = out_dims[1]; p.Wo = out_dims[2]; p.N = N;
-  p.wpk = nullptr; p.wexp = 0; p.xsplit = nullptr;
+  p.wpk = nullptr; p.wexp = 0; p.xsplit = nullptr; p.xsplit_bytes = 0; p.debug = 0;
   return convt4_launch(p, static_cast<cudaStream_t>(stream));
 }
 
@@ -59,9 +69,12 @@ extern "C" int oai_reg_pack_convt4(const float* w, int cin, int cout, int wexp, 
   return reg_pack_convt4_launch(w, cin, cout, wexp, static_cast<uint4*>(wpk), static_cast<cudaStream_t>(stream));
 }
 
-extern "C" size_t oai_reg_convt4_mma_workspace(int cin, const int* in_dims, int N) {
-  if (!in_dims || cin <= 0 || N <= 0) return 0;
-  return static_cast<size_t>(N) * cin * in_dims[0] * in_dims[1] * in_dims[2] * 4;
+extern "C" size_t oai_reg_convt4_mma_workspace(int cin, int cout, const int* in_dims, int N) {
+  if (!in_dims || cin <= 0 || cout <= 0 || N <= 0) return 0;
+  ConvT4Params p{};
+  p.cin = cin; p.cout = cout; p.N = N; p.Di = in_dims[0]; p.Hi = in_dims[1]; p.Wi = in_dims[2];
+  const size_t deep = convt4_splitk_bytes(p);   // levels narrower than 12 points: split-K partial sums
+  return deep ? deep : static_cast<size_t>(N) * cin * in_dims[0] * in_dims[1] * in_dims[2] * 4;
 }
 
 extern "C" int oai_reg_convt4_mma(const float* in, long long in_nstride, long long in_cstride, int cin,
@@ -71,10 +84,10 @@ extern "C" int oai_reg_convt4_mma(const float* in, long long in_nstride, long lo
                                   size_t workspace_bytes, void* stream) {
   OAI_REQUIRE(in && in_dims && w && wpk && bias && bn_scale && bn_shift && out && out_dims && workspace,
               "reg_convt4_mma: null pointer");
-  OAI_REQUIRE(workspace_bytes >= oai_reg_convt4_mma_workspace(cin, in_dims, N) &&
+  OAI_REQUIRE(workspace_bytes >= oai_reg_convt4_mma_workspace(cin, cout, in_dims, N) &&
                   (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
               "reg_convt4_mma: workspace of %zu bytes, 16-byte aligned, required",
-              oai_reg_convt4_mma_workspace(cin, in_dims, N));
+              oai_reg_convt4_mma_workspace(cin, cout, in_dims, N));
   OAI_REQUIRE(cout <= cin, "reg_convt4_mma: the residual keeps the first cout of cin channels (cout=%d cin=%d)", cout,
               cin);
   OAI_REQUIRE(cin % 16 == 0 && cout % 16 == 0, "reg_convt4_mma: cin and cout must be multiples of 16");
@@ -88,6 +101,7 @@ extern "C" int oai_reg_convt4_mma(const float* in, long long in_nstride, long lo
   p.out = out; p.out_nstride = out_nstride; p.out_cstride = out_cstride; p.cout = cout;
   p.Do = out_dims[0]; p.Ho = out_dims[1]; p.Wo = out_dims[2]; p.N = N;
   p.wpk = static_cast<const uint4*>(wpk); p.wexp = wexp; p.xsplit = static_cast<uint32_t*>(workspace);
+  p.xsplit_bytes = workspace_bytes; p.debug = 0;
   return convt4_launch(p, static_cast<cudaStream_t>(stream));
 }
 

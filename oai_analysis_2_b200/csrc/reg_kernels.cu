@@ -922,6 +922,217 @@ __global__ void reg_pack_convt4_kernel(const float* __restrict__ w, int cin, int
   }
 }
 
+// ------------------------------------------------------------------------------------------------ deep levels, split-K
+// The deepest levels of tallUNet2 have a few hundred output voxels and up to 512 channels: they are weight-streaming
+// GEMMs (M = N x voxels <= a few thousand, K = taps x Cin up to 13 824, 14 - 34 MB of weights) that the direct kernels
+// above run at ~0.1 TB/s because one block walks the whole K range.  Here K is split over blocks: block
+// (m-tile, co-tile, ks) computes a 64 x 64 partial over one tap and one range of input channels with a register-tiled
+// fp32 SGEMM whose A operand is gathered on the fly (leaky-ReLU applied), and writes it to a caller-owned workspace
+// [ks][class][M][cout]; a second kernel adds the partials IN FIXED ORDER (deterministic, unlike atomics) and applies
+// the layer's epilogue (bias + residual [+ BatchNorm]).
+//   MODE 0: Conv3d k3 s2 p1: m = (n, zo, yo, xo), tap (kd, kh, kw), input (2 zo - 1 + kd, ...)
+//   MODE 1: ConvTranspose3d k4 s2 p1, one output parity class per grid.y slice: m = (n, q), tap t in {0,1}^3,
+//           k = k0 + 2 t, input q + (p + 1 - k0) / 2 - t per axis (k0 = (p + 1) & 1)
+struct DeepGemmParams {
+  const float* in;
+  long long in_nstride, in_cstride;
+  int cin, Di, Hi, Wi;
+  const float* w;      // [cin][taps_total][wld]
+  int taps_total, wld; // 27 / 64; leading dimension of the co axis
+  int cout;
+  int N, Mo_d, Mo_h, Mo_w;  // m-space: (n, d, h, w) with these extents
+  int ntaps;           // taps per block-group: 27 (conv) or 8 (one parity class)
+  int ci_per_split, nsplit;
+  float* ws;           // [ntaps * nsplit][ncls][M][cout]
+  int ncls;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) deep_gemm_kernel(const DeepGemmParams p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ __align__(16) float sA[2][BK][BM];
+  __shared__ __align__(16) float sW[2][BK][BN];
+  const int tid = threadIdx.x;
+  const long long M = static_cast<long long>(p.N) * p.Mo_d * p.Mo_h * p.Mo_w;
+  const int mtiles = static_cast<int>((M + BM - 1) / BM);
+  const int m0 = (blockIdx.x % mtiles) * BM, co0 = (blockIdx.x / mtiles) * BN;
+  const int cls = blockIdx.y;
+  const int ks = blockIdx.z, tap = ks / p.nsplit, split = ks % p.nsplit;
+  const int ci_begin = split * p.ci_per_split, ci_end = min(p.cin, ci_begin + p.ci_per_split);
+  // ---- A gather set-up: this thread always loads row m = m0 + tid % 64 (4 channels per chunk)
+  const int am = tid & 63, ac = tid >> 6;
+  long long a_off = -1;
+  {
+    const long long m = m0 + am;
+    if (m < M) {
+      long long r = m;
+      const int x = r % p.Mo_w; r /= p.Mo_w;
+      const int y = r % p.Mo_h; r /= p.Mo_h;
+      const int z = r % p.Mo_d; r /= p.Mo_d;
+      const int n = static_cast<int>(r);
+      int iz, iy, ix;
+      if (MODE == 0) {
+        iz = 2 * z - 1 + tap / 9; iy = 2 * y - 1 + (tap / 3) % 3; ix = 2 * x - 1 + tap % 3;
+      } else {
+        const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
+        const int tz = tap >> 2, ty = (tap >> 1) & 1, tx = tap & 1;
+        iz = z + (pz ? 1 : 0) - tz; iy = y + (py ? 1 : 0) - ty; ix = x + (px ? 1 : 0) - tx;
+      }
+      if (iz >= 0 && iz < p.Di && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi)
+        a_off = n * p.in_nstride + (static_cast<long long>(iz) * p.Hi + iy) * p.Wi + ix;
+    }
+  }
+  // ---- W set-up: tap index into the [taps_total] axis
+  int wtap = tap;
+  if (MODE == 1) {
+    const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
+    const int kz = ((pz + 1) & 1) + 2 * (tap >> 2), ky = ((py + 1) & 1) + 2 * ((tap >> 1) & 1),
+              kx = ((px + 1) & 1) + 2 * (tap & 1);
+    wtap = (kz * 4 + ky) * 4 + kx;
+  }
+  const int wc = tid >> 4, wn = (tid & 15) * 4;   // this thread loads W[ci = wc][co0 + wn .. +3]
+  const bool wvec = (p.wld & 3) == 0 && co0 + wn + 3 < p.wld;
+  float ra[4];
+  float4 rw;
+  auto gload = [&](int ci0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + ac + 4 * j;
+      ra[j] = (a_off >= 0 && ci < ci_end) ? leaky(__ldg(p.in + a_off + ci * p.in_cstride)) : 0.f;
+    }
+    const int ci = ci0 + wc;
+    rw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ci < ci_end) {
+      const float* wp = p.w + (static_cast<size_t>(ci) * p.taps_total + wtap) * p.wld + co0 + wn;
+      if (wvec) {
+        rw = __ldg(reinterpret_cast<const float4*>(wp));
+      } else {
+        rw.x = co0 + wn < p.wld ? __ldg(wp) : 0.f;
+        rw.y = co0 + wn + 1 < p.wld ? __ldg(wp + 1) : 0.f;
+        rw.z = co0 + wn + 2 < p.wld ? __ldg(wp + 2) : 0.f;
+        rw.w = co0 + wn + 3 < p.wld ? __ldg(wp + 3) : 0.f;
+      }
+    }
+  };
+  auto sstore = [&](int b) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sA[b][ac + 4 * j][am] = ra[j];
+    *reinterpret_cast<float4*>(&sW[b][wc][wn]) = rw;
+  };
+  const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  gload(ci_begin);
+  sstore(0);
+  __syncthreads();
+  int b = 0;
+  for (int ci0 = ci_begin; ci0 < ci_end; ci0 += BK) {
+    const bool more = ci0 + BK < ci_end;
+    if (more) gload(ci0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&sA[b][kk][tm]);
+      const float4 w = *reinterpret_cast<const float4*>(&sW[b][kk][tn]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    if (more) sstore(b ^ 1);
+    __syncthreads();
+    b ^= 1;
+  }
+  float* dst = p.ws + (static_cast<size_t>(ks) * p.ncls + cls) * M * p.cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + tm + i;
+    if (m >= M) break;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (co0 + tn + j < p.cout) dst[m * p.cout + co0 + tn + j] = acc[i][j];
+  }
+}
+
+// out = (sum_ks partial + bias [+ pad_or_crop(avg_pool3d(in, 2, ceil_mode=True))]) * out_scale   (conv3 epilogue)
+__global__ void __launch_bounds__(256) deep_reduce_conv3_kernel(const Conv3Params p, const float* __restrict__ ws,
+                                                                int nks) {
+  const long long vol = static_cast<long long>(p.Do) * p.Ho * p.Wo, M = p.N * vol, total = M * p.cout;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % p.cout);
+    const long long m = i / p.cout;
+    float r = 0.f;
+    for (int k = 0; k < nks; ++k) r += ws[(static_cast<size_t>(k) * M + m) * p.cout + co];
+    r += p.bias[co];
+    const long long v = m % vol;
+    const int n = static_cast<int>(m / vol);
+    const int xo = static_cast<int>(v % p.Wo), yo = static_cast<int>((v / p.Wo) % p.Ho),
+              zo = static_cast<int>(v / (static_cast<long long>(p.Wo) * p.Ho));
+    if (p.residual) {
+      const int cs = co - (p.cout - p.cin);
+      if (cs >= 0) {
+        const float* plane = p.in + n * p.in_nstride + cs * p.in_cstride;
+        float sum = 0.f;
+        int cnt = 0;
+        for (int dz = 0; dz < 2; ++dz)
+          for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+              const int z = 2 * zo + dz, y = 2 * yo + dy, x = 2 * xo + dx;
+              if (z < p.Di && y < p.Hi && x < p.Wi) {
+                sum += plane[(static_cast<size_t>(z) * p.Hi + y) * p.Wi + x];
+                ++cnt;
+              }
+            }
+        r += sum / static_cast<float>(cnt);
+      }
+    }
+    p.out[n * p.out_nstride + co * p.out_cstride + v] = r * p.out_scale;
+  }
+}
+
+// out = BN( sum_ks partial[class of o][q = o / 2] + bias + upsample2x_trilinear(in[:, :cout]) )   (convT4 epilogue)
+__global__ void __launch_bounds__(256) deep_reduce_convt4_kernel(const ConvT4Params p, const float* __restrict__ ws,
+                                                                 int nks) {
+  const long long ovol = static_cast<long long>(p.Do) * p.Ho * p.Wo, total = p.N * ovol * p.cout;
+  const long long qvol = static_cast<long long>(p.Di) * p.Hi * p.Wi, M = p.N * qvol;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % p.cout);
+    long long r0 = i / p.cout;
+    const int xo = static_cast<int>(r0 % p.Wo); r0 /= p.Wo;
+    const int yo = static_cast<int>(r0 % p.Ho); r0 /= p.Ho;
+    const int zo = static_cast<int>(r0 % p.Do);
+    const int n = static_cast<int>(r0 / p.Do);
+    const int cls = ((zo & 1) << 2) | ((yo & 1) << 1) | (xo & 1);
+    const long long m = n * qvol + (static_cast<long long>(zo >> 1) * p.Hi + (yo >> 1)) * p.Wi + (xo >> 1);
+    float acc = 0.f;
+    for (int k = 0; k < nks; ++k) acc += ws[((static_cast<size_t>(k) * 8 + cls) * M + m) * p.cout + co];
+    int i0[3], i1[3];
+    float l[3];
+    const int o[3] = {zo, yo, xo}, nd[3] = {p.Di, p.Hi, p.Wi};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float sc = fmaxf(0.5f * (o[a] + 0.5f) - 0.5f, 0.f);
+      i0[a] = static_cast<int>(sc);
+      i1[a] = i0[a] + (i0[a] < nd[a] - 1 ? 1 : 0);
+      l[a] = sc - i0[a];
+    }
+    const float* pl = p.in + n * p.in_nstride + co * p.in_cstride;
+    auto at = [&](int z, int y, int x) { return pl[(static_cast<size_t>(z) * p.Hi + y) * p.Wi + x]; };
+    const float lz = l[0], ly = l[1], lx = l[2];
+    const float res = (1.f - lz) * ((1.f - ly) * ((1.f - lx) * at(i0[0], i0[1], i0[2]) + lx * at(i0[0], i0[1], i1[2])) +
+                                    ly * ((1.f - lx) * at(i0[0], i1[1], i0[2]) + lx * at(i0[0], i1[1], i1[2]))) +
+                      lz * ((1.f - ly) * ((1.f - lx) * at(i1[0], i0[1], i0[2]) + lx * at(i1[0], i0[1], i1[2])) +
+                            ly * ((1.f - lx) * at(i1[0], i1[1], i0[2]) + lx * at(i1[0], i1[1], i1[2])));
+    const long long ovox = (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + xo;
+    p.out[n * p.out_nstride + co * p.out_cstride + ovox] = (acc + p.bias[co] + res) * p.bn_scale[co] + p.bn_shift[co];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ sampling helpers
 // F.grid_sample(bilinear, border, align_corners=True) at normalised coordinate g = 2c-1 along each axis.
 struct Tri {
@@ -1265,8 +1476,45 @@ static void conv3_dispatch(const Conv3Params& p, cudaStream_t st) {
   else conv3_kernel<CO_T, XS, 2, KS><<<g, 128, 0, st>>>(p);
 }
 
+// ci range per block so that the grid has a few hundred blocks
+static int deep_ci_split(int cin, long long blocks_per_split) {
+  int nsplit = 1;
+  while (blocks_per_split * nsplit < 592 && cin / (nsplit * 2) >= 64) nsplit *= 2;
+  return nsplit;
+}
+
+size_t conv3_splitk_bytes(const Conv3Params& p) {
+  const long long M = static_cast<long long>(p.N) * p.Do * p.Ho * p.Wo;
+  if (p.stride != 2 || !p.leaky_in || p.cin < 64 || M > 4096) return 0;
+  const long long tiles = ((M + 63) / 64) * ((p.cout + 63) / 64) * 27;
+  return static_cast<size_t>(27) * deep_ci_split(p.cin, tiles) * M * p.cout * sizeof(float);
+}
+
+size_t convt4_splitk_bytes(const ConvT4Params& p) {
+  if (p.Wi >= 12) return 0;
+  const long long M = static_cast<long long>(p.N) * p.Di * p.Hi * p.Wi;
+  const long long tiles = ((M + 63) / 64) * ((p.cout + 63) / 64) * 64;
+  return static_cast<size_t>(8) * deep_ci_split(p.cin, tiles) * 8 * M * p.cout * sizeof(float);
+}
+
 int conv3_launch(const Conv3Params& p, cudaStream_t st) {
   const long long nvox = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+  const size_t need = conv3_splitk_bytes(p);
+  if (need && p.splitk_ws && p.splitk_bytes >= need) {
+    DeepGemmParams g;
+    g.in = p.in; g.in_nstride = p.in_nstride; g.in_cstride = p.in_cstride; g.cin = p.cin;
+    g.Di = p.Di; g.Hi = p.Hi; g.Wi = p.Wi;
+    g.w = p.w; g.taps_total = 27; g.wld = p.cout_pad; g.cout = p.cout;
+    g.N = p.N; g.Mo_d = p.Do; g.Mo_h = p.Ho; g.Mo_w = p.Wo;
+    g.ntaps = 27; g.ncls = 1; g.ws = p.splitk_ws;
+    const long long M = static_cast<long long>(p.N) * nvox;
+    const long long tiles = ((M + 63) / 64) * ((p.cout + 63) / 64);
+    g.nsplit = deep_ci_split(p.cin, tiles * 27);
+    g.ci_per_split = (p.cin + g.nsplit - 1) / g.nsplit;
+    deep_gemm_kernel<0><<<dim3(static_cast<unsigned>(tiles), 1, 27 * g.nsplit), 256, 0, st>>>(g);
+    deep_reduce_conv3_kernel<<<grid_for(M * p.cout, 256, 8), 256, 0, st>>>(p, p.splitk_ws, 27 * g.nsplit);
+    return launched("deep_gemm_kernel (conv3)");
+  }
   if (p.cout <= 4) conv3_dispatch<4, 8, 1>(p, st);              // lastConv: 18 -> 3 at full resolution
   else if (nvox * ((p.cout + 7) / 8) >= (1 << 16)) conv3_dispatch<8, 4, 1>(p, st);
   else if (p.cin >= 32) conv3_dispatch<8, 1, 4>(p, st);          // deep levels: few voxels, many channels
@@ -1311,8 +1559,24 @@ int reg_pack_convt4_launch(const float* w, int cin, int cout, int wexp, uint4* w
 
 int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
   const long long nout = static_cast<long long>(p.Do) * p.Ho * p.Wo;
-  // levels narrower than 12 lattice points (the two deepest) stay on the fp32 parity-class kernel: their 3x3 / 6x6
-  // planes fill too little of an MMA tile (measured 0.57 ms vs 0.35 ms for 512 -> 256 at 3x6x6)
+  // levels narrower than 12 lattice points (the two deepest): 3x3 / 6x6 planes fill too little of an MMA tile; with a
+  // workspace they run as split-K fp32 GEMMs, otherwise on the parity-class kernel below
+  if (const size_t need = convt4_splitk_bytes(p); need && p.xsplit && p.xsplit_bytes >= need) {
+    DeepGemmParams g;
+    g.in = p.in; g.in_nstride = p.in_nstride; g.in_cstride = p.in_cstride; g.cin = p.cin;
+    g.Di = p.Di; g.Hi = p.Hi; g.Wi = p.Wi;
+    g.w = p.w; g.taps_total = 64; g.wld = p.cout; g.cout = p.cout;
+    g.N = p.N; g.Mo_d = p.Di; g.Mo_h = p.Hi; g.Mo_w = p.Wi;
+    g.ntaps = 8; g.ncls = 8; g.ws = reinterpret_cast<float*>(p.xsplit);
+    const long long M = static_cast<long long>(p.N) * p.Di * p.Hi * p.Wi;
+    const long long tiles = ((M + 63) / 64) * ((p.cout + 63) / 64);
+    g.nsplit = deep_ci_split(p.cin, tiles * 64);
+    g.ci_per_split = (p.cin + g.nsplit - 1) / g.nsplit;
+    deep_gemm_kernel<1><<<dim3(static_cast<unsigned>(tiles), 8, 8 * g.nsplit), 256, 0, st>>>(g);
+    deep_reduce_convt4_kernel<<<grid_for(static_cast<long long>(p.N) * nout * p.cout, 256, 8), 256, 0, st>>>(
+        p, reinterpret_cast<const float*>(p.xsplit), 8 * g.nsplit);
+    return launched("deep_gemm_kernel (convt4)");
+  }
   if (p.wpk && p.xsplit && p.cin % 16 == 0 && p.cout % 16 == 0 && p.Wi >= 12) {
     if (p.Wi > 16) convt4_mma_dispatch<32>(p, st);
     else convt4_mma_dispatch<16>(p, st);

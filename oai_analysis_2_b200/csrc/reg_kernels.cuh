@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdint>
 
 namespace oai {
@@ -21,6 +22,8 @@ struct Conv3Params {
   int leaky_in;      // apply leaky_relu(0.01) to the input on load
   int residual;      // 1: add pad_or_crop(avg_pool3d(in, 2, ceil_mode=True)) (zero-padded IN FRONT to cout channels)
   float out_scale;   // multiplies (acc + bias [+ residual])
+  float* splitk_ws;  // optional workspace for the split-K path of the deep levels (conv3_splitk_bytes)
+  size_t splitk_bytes;
 };
 
 // Direct fp32 transposed convolution, kernel 4, stride 2, pad 1 (output = 2x input), fused with the icon UNet2 up-path:
@@ -40,6 +43,7 @@ struct ConvT4Params {
   const uint4* wpk;
   int wexp;
   int debug;         // development switches (OAI_CONVT4_DEBUG): 1 no residual, 2 no MMAs, 4 no staging, 8 no stores
+  size_t xsplit_bytes;
   uint32_t* xsplit;  // workspace of N*cin*Di*Hi*Wi words for the mma.sync path: the layer input as hi / lo fp16 pairs
 };
 
@@ -83,6 +87,8 @@ struct WarpPointsParams {
 };
 
 int conv3_launch(const Conv3Params& p, cudaStream_t st);
+size_t conv3_splitk_bytes(const Conv3Params& p);
+size_t convt4_splitk_bytes(const ConvT4Params& p);
 int convt4_launch(const ConvT4Params& p, cudaStream_t st);
 int reg_pack_convt4_launch(const float* w, int cin, int cout, int wexp, uint4* wpk, cudaStream_t st);
 int chain_launch(const ChainParams& p, cudaStream_t st);

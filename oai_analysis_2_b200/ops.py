@@ -104,28 +104,36 @@ def _dims(*v):
     return np.asarray(v, dtype=np.int32)
 
 
+_scratch = {}
+
+
+def _scratch_buf(device, tag, nbytes):
+    key = (device, tag)
+    if key not in _scratch or _scratch[key].numel() < nbytes:
+        _scratch[key] = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    return _scratch[key]
+
+
 def reg_conv3(x, cin, w, bias, out, cout, stride, leaky_in, residual, out_scale=1.0):
     """x / out: views [N, C, D, H, W] float32 whose channel slice may be part of a larger buffer."""
     N, _, D, H, W = x.shape
-    check(lib.oai_reg_conv3(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(_dims(D, H, W)), ptr(w), ptr(bias),
+    dims = _dims(D, H, W)
+    need = int(lib.oai_reg_conv3_workspace(cin, cout, ptr(dims), N, stride, int(leaky_in)))
+    ws = _scratch_buf(x.device, "conv3", need) if need else None
+    check(lib.oai_reg_conv3(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(dims), ptr(w), ptr(bias),
                             ptr(out), c_ll(out.stride(0)), c_ll(out.stride(1)), cout, w.shape[-1], N, stride,
-                            int(leaky_in), int(residual), c_float(out_scale), stream_ptr()), "reg_conv3")
+                            int(leaky_in), int(residual), c_float(out_scale), ptr(ws), c_size(need), stream_ptr()),
+          "reg_conv3")
     return out
-
-
-_scratch = {}
 
 
 def reg_convt4(x, cin, w, bias, bn_scale, bn_shift, out, cout, wpk=None, wexp=0, workspace=None):
     N, _, D, H, W = x.shape
     od = _dims(*out.shape[2:])
     if wpk is not None:
-        need = N * cin * D * H * W * 4
+        need = int(lib.oai_reg_convt4_mma_workspace(cin, cout, ptr(_dims(D, H, W)), N))
         if workspace is None or workspace.numel() < need:
-            key = (x.device, "convt4")
-            if key not in _scratch or _scratch[key].numel() < need:
-                _scratch[key] = torch.empty(need, dtype=torch.uint8, device=x.device)
-            workspace = _scratch[key]
+            workspace = _scratch_buf(x.device, "convt4", need)
         check(lib.oai_reg_convt4_mma(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(_dims(D, H, W)), ptr(w),
                                      ptr(wpk), wexp, ptr(bias), ptr(bn_scale), ptr(bn_shift), ptr(out),
                                      c_ll(out.stride(0)), c_ll(out.stride(1)), cout, ptr(od), N, ptr(workspace),

@@ -72,6 +72,32 @@ def test_unet2_layers_match_torch():
     assert (out.cpu() - ref).abs().max() < 3e-5
 
 
+@pytest.mark.parametrize("cin,cout,dims", [(64, 96, (5, 7, 9)), (256, 512, (6, 12, 12)), (128, 130, (3, 4, 5))])
+def test_conv3_deep_levels_split_k_matches_torch(cin, cout, dims):
+    """Down-path layers with few voxels and many channels run as split-K GEMMs with a fixed-order reduction
+    (oai_reg_conv3 with a workspace): must match torch and be bitwise reproducible."""
+    _cuda()
+    from oai_analysis_2_b200 import _lib, ops
+    from oracle.reg_oracle import pad_or_crop
+    g = torch.Generator().manual_seed(5)
+    N = 2
+    x = torch.randn(N, cin, *dims, generator=g)
+    w, b = torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.03, torch.randn(cout, generator=g) * 0.1
+    y = F.conv3d(F.leaky_relu(x).double(), w.double(), b.double(), stride=2, padding=1)
+    ref = y + pad_or_crop(F.avg_pool3d(x.double(), 2, ceil_mode=True), cout)
+    need = _lib.lib.oai_reg_conv3_workspace(cin, cout, ops.ptr(ops._dims(*dims)), N, 2, 1)
+    assert need > 0                                     # these shapes take the split-K path
+    wp = w.permute(1, 2, 3, 4, 0).reshape(cin, 27, cout).contiguous().cuda()
+    outs = []
+    for _ in range(2):
+        out = torch.zeros(N, cout, *ref.shape[2:]).cuda()
+        ops.reg_conv3(x.cuda(), cin, wp, b.cuda(), out, cout, 2, True, True)
+        outs.append(out.cpu())
+    scale = max(1.0, ref.abs().max().item())
+    assert (outs[0].double() - ref).abs().max().item() < 2e-6 * scale
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("cin,cout,dims,crop", [
     (48, 16, (3, 9, 40), (6, 17, 79)),      # TX=32 tiles, ragged x/y, odd crops
     (96, 32, (2, 12, 14), (4, 24, 28)),     # TX=16 tiles, two output-channel blocks (residual chunk 1)
