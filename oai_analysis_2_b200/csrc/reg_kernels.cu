@@ -11,6 +11,8 @@
 //                           (oai_analysis/dask_processing.py:100-109), float64 coordinate arithmetic
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "api_common.h"
 #include "reg_kernels.cuh"
 
@@ -688,32 +690,40 @@ __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p
   // zero-filled outside the volume (the transposed conv's implicit padding).  Per row: TX/4 16-byte pieces + 2 halo
   // words when rows are 16-byte aligned, TX + 2 words otherwise.
   const bool vec = (p.Wi & 3) == 0;
-  const int items = vec ? TX / 4 + 2 : TX + 2;
   const uint32_t* xs_n = p.xsplit + static_cast<long long>(n) * (p.cin / 2) * vol;
   const long long arr_stride = static_cast<long long>(p.N) * (p.cin / 2) * vol;
-  auto fetch_chunk = [&](int ch, int b) {
+  const int plane = p.Hi * p.Wi;
+  auto fetch_chunk_impl = [&](int ch, int b, auto vec_tag) {
+    constexpr bool VEC = decltype(vec_tag)::value;
+    constexpr int ITEMS = VEC ? TX / 4 + 2 : TX + 2;      // compile-time divisors: the index math is a few IMADs
     uint32_t* dbuf = s_mma + b * 16 * PS;
-    const int total = 2 * 8 * 3 * SY * items;
-    for (int e = tid; e < total; e += 128) {
-      const int r = e / items, it = e - r * items;
-      const int sy = r % SY, sz = (r / SY) % 3, pair = (r / (3 * SY)) & 7, arr = r / (24 * SY);
+    const uint32_t* xs_c = xs_n + static_cast<long long>(ch) * 8 * vol;
+    constexpr int TOTAL = 2 * 8 * 3 * SY * ITEMS;
+#pragma unroll 2
+    for (int e = tid; e < TOTAL; e += 128) {
+      const int r = e / ITEMS, it = e - r * ITEMS;
+      const int sy = r % SY, r2 = r / SY, sz = r2 % 3, r3 = r2 / 3, pair = r3 & 7, arr = r3 >> 3;
       const int z = qz - 1 + sz, y = qy0 - 1 + sy;
-      const bool rowok = z >= 0 && z < p.Di && y >= 0 && y < p.Hi;
-      const uint32_t* src = xs_n + arr * arr_stride + (ch * 8 + pair) * vol +
-                            (rowok ? (static_cast<long long>(z) * p.Hi + y) * p.Wi : 0);
+      const bool rowok = static_cast<unsigned>(z) < static_cast<unsigned>(p.Di) &&
+                         static_cast<unsigned>(y) < static_cast<unsigned>(p.Hi);
+      const uint32_t* src = xs_c + arr * arr_stride + pair * vol + (rowok ? z * plane + y * p.Wi : 0);
       uint32_t* dst = dbuf + (arr * 8 + pair) * PS + (sz * SY + sy) * SX;
-      if (vec && it < TX / 4) {
+      if (VEC && it < TX / 4) {
         const int x = qx0 + 4 * it;
         const bool ok = rowok && x < p.Wi;
         cp_async_16z(dst + 4 + 4 * it, ok ? src + x : xs_n, ok);
       } else {
-        const int sx = vec ? (it == TX / 4 ? 0 : TX + 1) : it;  // tile-relative column incl. halo (0 .. TX+1)
+        const int sx = VEC ? (it == TX / 4 ? 0 : TX + 1) : it;  // tile-relative column incl. halo (0 .. TX+1)
         const int x = qx0 - 1 + sx;
-        const bool ok = rowok && x >= 0 && x < p.Wi;
+        const bool ok = rowok && static_cast<unsigned>(x) < static_cast<unsigned>(p.Wi);
         cp_async_4(reinterpret_cast<float*>(dst + 3 + sx), reinterpret_cast<const float*>(ok ? src + x : xs_n), ok);
       }
     }
     cp_async_commit();
+  };
+  auto fetch_chunk = [&](int ch, int b) {
+    if (vec) fetch_chunk_impl(ch, b, std::true_type{});
+    else fetch_chunk_impl(ch, b, std::false_type{});
   };
   // ---- cp.async of the 16 raw residual channels (fp32, replicate-clamped = the upsample's border rule)
   const bool vec_in = vec && (p.in_cstride & 3) == 0 && (p.in_nstride & 3) == 0 &&
