@@ -13,7 +13,10 @@
 
 #include <type_traits>
 
+#include <cuda.h>
+
 #include "api_common.h"
+#include "ptx.cuh"
 #include "reg_kernels.cuh"
 
 namespace oai {
@@ -602,12 +605,14 @@ __global__ void __launch_bounds__(128) convt4_par_kernel(const ConvT4Params p) {
 //   o = 2 i - 1 + k: class p = 0 uses (k = 1, i = q), (k = 3, i = q - 1); p = 1 uses (k = 2, i = q), (k = 0, i = q + 1).
 // reg_split_kernel first rewrites the layer input once as leaky-ReLU'd hi / lo fp16 channel pairs (one 32-bit word =
 // one A-fragment register).  A block owns TX x TY x 1 lattice points (all 8 classes = 2TX x 2TY x 2 outputs) and 16
-// output channels; per chunk of 16 input channels the 3 x (TY+2) x (TX+2) neighbourhood of both arrays is copied to
-// shared memory by cp.async (double buffered: chunk c+1 flies while chunk c computes).  Each of the 27 neighbour shifts loads its A fragments once and feeds
+// output channels; per chunk of 16 input channels the 3 x (TY+2) x (TX+8) neighbourhood of both arrays arrives as two
+// TMA boxes issued by one thread (zero fill outside the volume = the conv's padding; double buffered: chunk c+1 flies
+// while chunk c computes), so the kernel spends no instructions on staging.  Each of the 27 neighbour shifts loads its A fragments once and feeds
 // every (class, tap) pair that maps to it: 64 weight taps x 2 m-tiles x 2 n-tiles x 3 split terms = 768 MMAs per warp
 // per chunk against 432 shared-memory loads.  The residual (2x trilinear upsample of the raw input channels, fixed
-// 0.25 / 0.75 weights), bias and BatchNorm are applied in the epilogue from the 16 raw residual channels, fetched
-// into the free buffer (replicate-clamped coordinates = the interpolation's border rule) during the last chunk's MMAs.
+// 0.25 / 0.75 weights), bias and BatchNorm are applied in the epilogue from the 16 raw residual channels, which one
+// more TMA box brings into the free buffer during the last chunk's MMAs (the epilogue clamps its neighbour indices =
+// the interpolation's replicate border).
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -647,19 +652,24 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("pre
 template <int TX>
 struct ConvT4MmaCfg {
   static constexpr int TY = 128 / TX;             // 4 / 8 lattice rows per block for TX = 32 / 16
-  // shared-memory row: col 3 = left halo, cols 4 .. TX+3 = the tile (16-byte aligned for cp.async), col TX+4 = right halo
+  // shared-memory row = one TMA box row.  The innermost start coordinate of a TMA box must be 16-byte aligned
+  // (measured: scripts/micro/tma_probe.cu -- x = qx0 - 1 raises "illegal instruction", qx0 - 4 works), so the box
+  // starts 4 words left of the tile: col 3 = left halo, cols 4 .. TX+3 = the tile, col TX+4 = right halo
   static constexpr int SX = TX + 8, SY = TY + 2;
-  static constexpr int PS0 = 3 * SY * SX;
-  // words per channel pair, padded to 8 (mod 16): A-fragment loads (pair = lane % 4, point = lane / 4) conflict-free
-  static constexpr int PS = PS0 + ((8 - PS0 % 16) + 16) % 16;
-  static constexpr size_t smem_bytes = 2 * 16 * PS * 4;  // two buffers of (hi, lo) x 8 pairs
+  static constexpr int PS = 3 * SY * SX;          // words per channel pair (720: pairs t and t+2 share banks, 2-way)
+  static constexpr int BUF = 16 * PS;             // words per buffer: (hi, lo) x 8 pairs = two TMA boxes
+  static constexpr size_t smem_bytes = 2 * BUF * 4 + 128;       // + alignment slack
 };
 
 template <int TX>
-__global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p) {
+__global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                            const __grid_constant__ CUtensorMap tm_res,
+                                                            const ConvT4Params p) {
   using Cfg = ConvT4MmaCfg<TX>;
-  constexpr int TY = Cfg::TY, SX = Cfg::SX, SY = Cfg::SY, PS = Cfg::PS;
-  extern __shared__ __align__(16) uint32_t s_mma[];  // [2 buffers][hi, lo][8 pairs][PS]
+  constexpr int TY = Cfg::TY, SX = Cfg::SX, SY = Cfg::SY, PS = Cfg::PS, BUF = Cfg::BUF;
+  extern __shared__ uint8_t s_mma_raw[];
+  uint32_t* s_mma = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(s_mma_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t full_bar[2];                   // TMA completion of buffer 0 / 1
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int ntx = (p.Wi + TX - 1) / TX, nty = (p.Hi + TY - 1) / TY;
   const int qx0 = static_cast<int>(blockIdx.x % ntx) * TX, qy0 = static_cast<int>((blockIdx.x / ntx) % nty) * TY;
@@ -686,84 +696,45 @@ __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) acc[c][j][nt][0] = acc[c][j][nt][1] = acc[c][j][nt][2] = acc[c][j][nt][3] = 0.f;
 
-  // ---- cp.async of one chunk: (hi, lo) x 8 channel pairs x 3 x SY rows of the pre-split input (reg_split_kernel),
-  // zero-filled outside the volume (the transposed conv's implicit padding).  Per row: TX/4 16-byte pieces + 2 halo
-  // words when rows are 16-byte aligned, TX + 2 words otherwise.
-  const bool vec = (p.Wi & 3) == 0;
-  const uint32_t* xs_n = p.xsplit + static_cast<long long>(n) * (p.cin / 2) * vol;
-  const long long arr_stride = static_cast<long long>(p.N) * (p.cin / 2) * vol;
-  const int plane = p.Hi * p.Wi;
-  auto fetch_chunk_impl = [&](int ch, int b, auto vec_tag) {
-    constexpr bool VEC = decltype(vec_tag)::value;
-    constexpr int ITEMS = VEC ? TX / 4 + 2 : TX + 2;      // compile-time divisors: the index math is a few IMADs
-    uint32_t* dbuf = s_mma + b * 16 * PS;
-    const uint32_t* xs_c = xs_n + static_cast<long long>(ch) * 8 * vol;
-    constexpr int TOTAL = 2 * 8 * 3 * SY * ITEMS;
-#pragma unroll 2
-    for (int e = tid; e < TOTAL; e += 128) {
-      const int r = e / ITEMS, it = e - r * ITEMS;
-      const int sy = r % SY, r2 = r / SY, sz = r2 % 3, r3 = r2 / 3, pair = r3 & 7, arr = r3 >> 3;
-      const int z = qz - 1 + sz, y = qy0 - 1 + sy;
-      const bool rowok = static_cast<unsigned>(z) < static_cast<unsigned>(p.Di) &&
-                         static_cast<unsigned>(y) < static_cast<unsigned>(p.Hi);
-      const uint32_t* src = xs_c + arr * arr_stride + pair * vol + (rowok ? z * plane + y * p.Wi : 0);
-      uint32_t* dst = dbuf + (arr * 8 + pair) * PS + (sz * SY + sy) * SX;
-      if (VEC && it < TX / 4) {
-        const int x = qx0 + 4 * it;
-        const bool ok = rowok && x < p.Wi;
-        cp_async_16z(dst + 4 + 4 * it, ok ? src + x : xs_n, ok);
-      } else {
-        const int sx = VEC ? (it == TX / 4 ? 0 : TX + 1) : it;  // tile-relative column incl. halo (0 .. TX+1)
-        const int x = qx0 - 1 + sx;
-        const bool ok = rowok && static_cast<unsigned>(x) < static_cast<unsigned>(p.Wi);
-        cp_async_4(reinterpret_cast<float*>(dst + 3 + sx), reinterpret_cast<const float*>(ok ? src + x : xs_n), ok);
-      }
-    }
-    cp_async_commit();
+  // ---- one chunk = two TMA boxes (hi, lo) of 8 channel pairs x 3 x SY x (TX + 4) words of the pre-split input
+  // (reg_split_kernel); coordinates outside the volume are zero-filled by TMA = the transposed conv's implicit padding
+  const int planes_n = p.cin / 2;                    // channel pairs per sample
+  // the descriptors must be addressed in parameter space: take the addresses here, not inside a capturing lambda
+  const CUtensorMap* const ptm_x = &tm_x;
+  const CUtensorMap* const ptm_res = &tm_res;
+  auto fetch_chunk = [&](int ch, int b) {            // one elected thread
+    uint32_t* dbuf = s_mma + b * BUF;
+    mbar_arrive_expect_tx(&full_bar[b], BUF * 4);
+    tma_load_5d(dbuf, ptm_x, &full_bar[b], qx0 - 4, qy0 - 1, qz - 1, n * planes_n + ch * 8, 0);
+    tma_load_5d(dbuf + 8 * PS, ptm_x, &full_bar[b], qx0 - 4, qy0 - 1, qz - 1, (p.N + n) * planes_n + ch * 8, 0);
   };
-  auto fetch_chunk = [&](int ch, int b) {
-    if (vec) fetch_chunk_impl(ch, b, std::true_type{});
-    else fetch_chunk_impl(ch, b, std::false_type{});
+  // ---- the 16 raw fp32 residual channels co0 .. co0+15: one TMA box into the buffer the last chunk does not use
+  // (zero-filled outside the volume; the epilogue clamps its neighbour indices = the upsample's replicate border)
+  auto fetch_res = [&](int b) {                      // one elected thread
+    mbar_arrive_expect_tx(&full_bar[b], BUF * 4);
+    tma_load_5d(s_mma + b * BUF, ptm_res, &full_bar[b], qx0 - 4, qy0 - 1, qz - 1, n * p.res_planes_per_n + co0, 0);
   };
-  // ---- cp.async of the 16 raw residual channels (fp32, replicate-clamped = the upsample's border rule)
-  const bool vec_in = vec && (p.in_cstride & 3) == 0 && (p.in_nstride & 3) == 0 &&
-                      (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
-  auto fetch_res = [&](int b) {
-    float* dbuf = reinterpret_cast<float*>(s_mma + b * 16 * PS);
-    constexpr int IT = TX / 4 + 2;
-    const int total = 16 * 3 * SY * IT;
-    for (int e = tid; e < total; e += 128) {
-      const int r = e / IT, it = e - r * IT;
-      const int sy = r % SY, sz = (r / SY) % 3, c = r / (3 * SY);
-      const int zc = min(max(qz - 1 + sz, 0), p.Di - 1), yc = min(max(qy0 - 1 + sy, 0), p.Hi - 1);
-      const float* src = in_n + (co0 + c) * p.in_cstride + (static_cast<long long>(zc) * p.Hi + yc) * p.Wi;
-      float* dst = dbuf + c * PS + (sz * SY + sy) * SX;
-      if (it < TX / 4) {
-        const int x = qx0 + 4 * it;
-        if (vec_in && x + 3 < p.Wi) {
-          cp_async_16(dst + 4 + 4 * it, src + x);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cp_async_4(dst + 4 + 4 * it + i, src + min(x + i, p.Wi - 1), true);
-        }
-      } else {
-        const int sx = it == TX / 4 ? 0 : TX + 1;
-        cp_async_4(dst + 3 + sx, src + min(max(qx0 - 1 + sx, 0), p.Wi - 1), true);
-      }
-    }
-    cp_async_commit();
-  };
-
   const int rb = nchunks & 1;  // buffer the last chunk does not use: the residual channels land there
-  fetch_chunk(0, 0);
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0 && !(p.debug & 4)) fetch_chunk(0, 0);
+  uint32_t phase[2] = {0u, 0u};
   for (int ch = 0; ch < nchunks; ++ch) {
-    cp_async_wait<0>();
-    __syncthreads();  // chunk ch has landed; every warp is done with chunk ch - 1, whose buffer is refilled now
+    fence_proxy_async_smem();   // this thread's reads of the buffer refilled below are ordered before the TMA writes
+    __syncthreads();            // every warp is done with chunk ch - 1
     if (!(p.debug & 4)) {
-      if (ch + 1 < nchunks) fetch_chunk(ch + 1, (ch + 1) & 1);
-      else fetch_res(rb);
+      if (tid == 0) {
+        if (ch + 1 < nchunks) fetch_chunk(ch + 1, (ch + 1) & 1);
+        else fetch_res(rb);
+      }
+      mbar_wait(&full_bar[ch & 1], phase[ch & 1], 40 + ch);
+      phase[ch & 1] ^= 1u;
     }
-    const uint32_t* sHi = s_mma + (ch & 1) * 16 * PS;
+    const uint32_t* sHi = s_mma + (ch & 1) * BUF;
     const uint32_t* sLo = sHi + 8 * PS;
     // ---- MMAs: 27 neighbour shifts, A fragments loaded once per shift
     const uint4* wq = p.wpk + (static_cast<size_t>(coblk) * nchunks + ch) * (64 * 2 * 32) + lane;
@@ -825,9 +796,9 @@ __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p
               }
         }
   }
-  cp_async_wait<0>();
-  __syncthreads();  // raw residual channels co0 .. co0+15 (replicate-clamped) have landed in buffer rb
-  const float* sRaw = reinterpret_cast<const float*>(s_mma + rb * 16 * PS);
+  if (!(p.debug & 4)) mbar_wait(&full_bar[rb], phase[rb], 39);   // raw residual channels have landed in buffer rb
+  const float* sRaw = reinterpret_cast<const float*>(s_mma + rb * BUF);
+  const int rz[3] = {max(qz - 1, 0) - (qz - 1), 1, min(qz + 1, p.Di - 1) - (qz - 1)};  // replicate-clamped planes
 
   // ---- epilogue: out = BN( acc * 2^-wexp + bias + upsample2x(raw in[co]) ), cropped to (Do, Ho, Wo)
   const float inv = exp2f(static_cast<float>(-p.wexp));
@@ -846,14 +817,16 @@ __global__ void __launch_bounds__(128, 2) convt4_mma_kernel(const ConvT4Params p
           const int xl = tx[j][h], yl = ty[j][h];
           const int qx = qx0 + xl, qy = qy0 + yl;
           if (qx >= p.Wi || qy >= p.Hi || (p.debug & 8)) continue;
-          // separable 0.25 / 0.75 interpolation of the 3x3x3 raw neighbourhood -> the 8 class values
+          // separable 0.25 / 0.75 interpolation of the 3x3x3 raw neighbourhood (replicate-clamped) -> 8 class values
+          const int ry[3] = {max(qy - 1, 0) - (qy0 - 1), yl + 1, min(qy + 1, p.Hi - 1) - (qy0 - 1)};
+          const int rx[3] = {max(qx - 1, 0) - (qx0 - 4), xl + 4, min(qx + 1, p.Wi - 1) - (qx0 - 4)};
           float ax[3][3][2];
 #pragma unroll
           for (int dz = 0; dz < 3; ++dz)
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-              const float* row = sRaw + cl * PS + (dz * SY + yl + dy) * SX + xl + 3;
-              const float v0 = (p.debug & 1) ? 0.f : row[0], v1 = (p.debug & 1) ? 0.f : row[1], v2 = (p.debug & 1) ? 0.f : row[2];
+              const float* row = sRaw + cl * PS + (rz[dz] * SY + ry[dy]) * SX;
+              const float v0 = row[rx[0]], v1 = row[rx[1]], v2 = row[rx[2]];
               ax[dz][dy][0] = 0.25f * v0 + 0.75f * v1;
               ax[dz][dy][1] = 0.75f * v1 + 0.25f * v2;
             }
@@ -1541,8 +1514,38 @@ static void convt4_dispatch(const ConvT4Params& p, cudaStream_t st) {
   convt4_kernel<CO_T, XP, KS><<<g, 128, 0, st>>>(p);
 }
 
+// `planes` dense planes of Di x Hi x Wi 32-bit words as a rank-5 TMA tensor (W, H, D, plane, 1);
+// box = (bx, by, 3, box_planes, 1) words, no swizzle, zero fill outside
+static int make_plane_tmap(CUtensorMap* tm, void* base, unsigned long long planes, int box_planes,
+                           const ConvT4Params& p, int bx, int by) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess &&
+        r == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  if (!fn) return fail("convt4_mma: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[5] = {(cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.Di, planes, 1};
+  cuuint64_t strides[4] = {(cuuint64_t)p.Wi * 4, (cuuint64_t)p.Hi * p.Wi * 4, (cuuint64_t)p.Di * p.Hi * p.Wi * 4,
+                           planes * p.Di * p.Hi * p.Wi * 4};
+  cuuint32_t box[5] = {(cuuint32_t)bx, (cuuint32_t)by, 3, (cuuint32_t)box_planes, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("convt4_mma: cuTensorMapEncodeTiled failed with %d (W=%d H=%d D=%d planes=%llu box %dx%d)", (int)r, p.Wi,
+                p.Hi, p.Di, (unsigned long long)planes, bx, by);
+  return 0;
+}
+
 template <int TX>
-static void convt4_mma_dispatch(const ConvT4Params& p, cudaStream_t st) {
+static int convt4_mma_dispatch(const ConvT4Params& p, cudaStream_t st) {
   using Cfg = ConvT4MmaCfg<TX>;
   static bool configured = false;
   if (!configured) {
@@ -1550,6 +1553,14 @@ static void convt4_mma_dispatch(const ConvT4Params& p, cudaStream_t st) {
                          static_cast<int>(Cfg::smem_bytes));
     configured = true;
   }
+  CUtensorMap tm, tm_res;
+  if (int rc = make_plane_tmap(&tm, p.xsplit, static_cast<unsigned long long>(2) * p.N * (p.cin / 2), 8, p, Cfg::SX,
+                               Cfg::SY))
+    return rc;
+  // raw fp32 input planes for the residual: sample n, channel c = plane n * (in_nstride / in_cstride) + c
+  const unsigned long long ratio = static_cast<unsigned long long>(p.in_nstride / p.in_cstride);
+  if (int rc = make_plane_tmap(&tm_res, const_cast<float*>(p.in), (p.N - 1) * ratio + p.cin, 16, p, Cfg::SX, Cfg::SY))
+    return rc;
   const long long vol = static_cast<long long>(p.Di) * p.Hi * p.Wi;
   reg_split_kernel<<<grid_for(p.N * (p.cin / 2) * vol, 256, 16), 256, 0, st>>>(p.in, p.in_nstride, p.in_cstride, p.N,
                                                                               p.cin, vol, p.xsplit);
@@ -1558,7 +1569,9 @@ static void convt4_mma_dispatch(const ConvT4Params& p, cudaStream_t st) {
   static const int dbg = getenv("OAI_CONVT4_DEBUG") ? atoi(getenv("OAI_CONVT4_DEBUG")) : 0;
   ConvT4Params q = p;
   q.debug = dbg;
-  convt4_mma_kernel<TX><<<g, 128, Cfg::smem_bytes, st>>>(q);
+  q.res_planes_per_n = static_cast<int>(ratio);
+  convt4_mma_kernel<TX><<<g, 128, Cfg::smem_bytes, st>>>(tm, tm_res, q);
+  return 0;
 }
 
 int reg_pack_convt4_launch(const float* w, int cin, int cout, int wexp, uint4* wpk, cudaStream_t st) {
@@ -1587,9 +1600,12 @@ int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
         p, reinterpret_cast<const float*>(p.xsplit), 8 * g.nsplit);
     return launched("deep_gemm_kernel (convt4)");
   }
-  if (p.wpk && p.xsplit && p.cin % 16 == 0 && p.cout % 16 == 0 && p.Wi >= 12) {
-    if (p.Wi > 16) convt4_mma_dispatch<32>(p, st);
-    else convt4_mma_dispatch<16>(p, st);
+  // tensor path: rows must be 16-byte multiples for the TMA boxes (every tallUNet2 level that is wide enough is)
+  if (p.wpk && p.xsplit && p.cin % 16 == 0 && p.cout % 16 == 0 && p.Wi >= 12 && p.Wi % 4 == 0 &&
+      p.in_cstride == static_cast<long long>(p.Di) * p.Hi * p.Wi && p.in_nstride % p.in_cstride == 0 &&
+      (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 &&
+      p.xsplit_bytes >= static_cast<size_t>(p.N) * p.cin * p.Di * p.Hi * p.Wi * 4) {
+    if (int rc = p.Wi > 16 ? convt4_mma_dispatch<32>(p, st) : convt4_mma_dispatch<16>(p, st)) return rc;
     return launched("convt4_mma_kernel");
   }
   if (nout * ((p.cout + 7) / 8) >= (1 << 17) && p.cout % 8 == 0) {

@@ -43,6 +43,7 @@ struct ConvT4Params {
   const uint4* wpk;
   int wexp;
   int debug;         // development switches (OAI_CONVT4_DEBUG): 1 no residual, 2 no MMAs, 4 no staging, 8 no stores
+  int res_planes_per_n;  // filled by the launcher: in_nstride / in_cstride
   size_t xsplit_bytes;
   uint32_t* xsplit;  // workspace of N*cin*Di*Hi*Wi words for the mma.sync path: the layer input as hi / lo fp16 pairs
 };

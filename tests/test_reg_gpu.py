@@ -100,8 +100,9 @@ def test_conv3_deep_levels_split_k_matches_torch(cin, cout, dims):
 
 @pytest.mark.parametrize("cin,cout,dims,crop", [
     (48, 16, (3, 9, 40), (6, 17, 79)),      # TX=32 tiles, ragged x/y, odd crops
-    (96, 32, (2, 12, 14), (4, 24, 28)),     # TX=16 tiles, two output-channel blocks (residual chunk 1)
-    (32, 32, (2, 5, 33), (3, 10, 66)),      # cin == cout, partial tiles in both axes
+    (96, 32, (2, 12, 16), (4, 24, 31)),     # TX=16 tiles, two output-channel blocks (residual chunk 1)
+    (32, 32, (2, 5, 36), (3, 10, 71)),      # cin == cout, partial tiles in both axes, odd crop
+    (48, 16, (2, 6, 14), (4, 12, 28)),      # rows not a multiple of 16 bytes -> fp32 kernels (no TMA boxes)
     (64, 48, (3, 6, 6), (5, 12, 12)),       # TX=8 tiles (deep levels), three output-channel blocks
     (32, 16, (2, 3, 3), (3, 5, 6)),         # deepest level of the quarter-resolution nets
 ])
