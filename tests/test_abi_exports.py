@@ -66,3 +66,41 @@ def test_gpu_entry_points_fail_loudly_without_a_device():
     from oai_analysis_2_b200.segmentation.networks import UNet
     with pytest.raises(RuntimeError, match="CUDA"):
         UNet(1, 2, True, True).to("cpu")
+
+
+def test_workspace_queries_follow_the_dispatch_rules():
+    """Host-only ABI helpers: which registration layers use scratch, and how much (no device needed)."""
+    from oai_analysis_2_b200 import _lib
+    L = _lib.lib
+
+    def dims(*v):
+        return _lib.ptr(np.asarray(v, dtype=np.int32))
+
+    # conv3 split-K: stride 2 + leaky input + cin >= 64 + at most 4096 output voxels over the batch
+    assert L.oai_reg_conv3_workspace(256, 512, dims(5, 12, 12), 2, 2, 1) == 27 * 2 * (3 * 6 * 6) * 512 * 4
+    assert L.oai_reg_conv3_workspace(16, 32, dims(40, 96, 96), 2, 2, 1) == 0          # wide level: direct kernel
+    assert L.oai_reg_conv3_workspace(18, 3, dims(80, 192, 192), 2, 1, 0) == 0         # last conv (stride 1)
+    assert L.oai_reg_conv3_workspace(32, 64, dims(10, 24, 24), 2, 2, 1) == 0          # cin < 64
+    assert L.oai_reg_conv3_workspace(0, 64, dims(4, 4, 4), 2, 2, 1) == 0              # invalid arguments
+    # transposed conv: tensor path needs the input once as hi/lo words; the two deepest levels need split-K partials
+    assert L.oai_reg_convt4_mma_workspace(48, 16, dims(40, 96, 96), 2) == 2 * 48 * 40 * 96 * 96 * 4
+    deep = L.oai_reg_convt4_mma_workspace(512, 256, dims(3, 6, 6), 2)
+    assert deep == 8 * 8 * (2 * 3 * 6 * 6) * 256 * 4
+    assert L.oai_intensity_window_workspace() >= 2048 * 4 * 5
+
+
+def test_new_entry_points_reject_bad_arguments_with_messages():
+    from oai_analysis_2_b200 import _lib
+    L = _lib.lib
+    buf = np.zeros(64, dtype=np.float32)
+    ws = np.zeros(1 << 17, dtype=np.uint8)
+    rc = L.oai_intensity_window(_lib.ptr(buf), ctypes.c_longlong(64), ctypes.c_double(60.0), ctypes.c_double(40.0),
+                                ctypes.c_float(0), ctypes.c_float(1), _lib.ptr(buf), _lib.ptr(ws),
+                                ctypes.c_size_t(ws.size), None)
+    assert rc != 0 and b"percentiles" in L.oai_last_error()
+    rc = L.oai_intensity_window(_lib.ptr(buf), ctypes.c_longlong(64), ctypes.c_double(0.1), ctypes.c_double(99.9),
+                                ctypes.c_float(0), ctypes.c_float(1), _lib.ptr(buf), _lib.ptr(ws), ctypes.c_size_t(8),
+                                None)
+    assert rc != 0 and b"workspace" in L.oai_last_error()
+    rc = L.oai_reg_pack_convt4(_lib.ptr(buf), 24, 16, 0, _lib.ptr(ws), None)
+    assert rc != 0 and b"multiples of 16" in L.oai_last_error()

@@ -27,3 +27,18 @@ def test_output_range_and_monotonicity():
     o = np.argsort(a)
     assert np.all(np.diff(out[o]) >= 0)
     assert wmin < wmax
+
+
+def test_percentiles_match_the_committed_numpy_fixture():
+    """tests/golden/normalize_percentiles.json was written by numpy 2.3.5 (float32 arrays: virtual index and lerp in
+    float32, NEP 50).  The device kernel restates exactly that; a numpy with different semantics must show up here."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "normalize_percentiles.json")
+    fx = json.load(open(path))
+    rng = np.random.default_rng(2024)
+    for c in fx["cases"]:
+        a = (rng.standard_normal(c["n"]) * 37.0 + 5.0).astype(np.float32)
+        assert float(a[0]) == c["first"] and float(a[-1]) == c["last"]
+        _, (wmin, wmax) = image_normalize(a, c["lo"], c["hi"], 0.0, 1.0)
+        assert wmin == c["wmin"] and wmax == c["wmax"], (c, wmin, wmax)
