@@ -202,14 +202,21 @@ extern "C" int oai_intensity_window(const float* in, long long n, double perc_lo
   SelectState* s = static_cast<SelectState*>(workspace);
   const unsigned grid = static_cast<unsigned>(num_sms()) * 4;
   window_init_kernel<<<1, 256, 0, st>>>(s, n, perc_lo, perc_hi);
+  if (int rc = launched("window_init_kernel")) return rc;
   window_hist_kernel<0><<<grid, 512, 0, st>>>(in, n, s);
+  if (int rc = launched("window_hist_kernel<0>")) return rc;
   window_pick_kernel<0><<<1, 32 * kTargets, 0, st>>>(s, out_min, out_max);
+  if (int rc = launched("window_pick_kernel<0>")) return rc;
   window_hist_kernel<1><<<grid, 512, 0, st>>>(in, n, s);
+  if (int rc = launched("window_hist_kernel<1>")) return rc;
   window_pick_kernel<1><<<1, 32 * kTargets, 0, st>>>(s, out_min, out_max);
+  if (int rc = launched("window_pick_kernel<1>")) return rc;
   window_hist_kernel<2><<<grid, 512, 0, st>>>(in, n, s);
+  if (int rc = launched("window_hist_kernel<2>")) return rc;
   window_pick_kernel<2><<<1, 32 * kTargets, 0, st>>>(s, out_min, out_max);
+  if (int rc = launched("window_pick_kernel<2>")) return rc;
   window_apply_kernel<<<grid * 2, 256, 0, st>>>(in, n, s, out_min, out_max, out);
-  return launched("intensity_window");
+  return launched("window_apply_kernel");
 }
 
 extern "C" int oai_intensity_window_result(const void* workspace, double* window_host, void* stream) {

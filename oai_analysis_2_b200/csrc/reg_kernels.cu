@@ -1490,8 +1490,9 @@ int conv3_launch(const Conv3Params& p, cudaStream_t st) {
     g.nsplit = deep_ci_split(p.cin, tiles * 27);
     g.ci_per_split = (p.cin + g.nsplit - 1) / g.nsplit;
     deep_gemm_kernel<0><<<dim3(static_cast<unsigned>(tiles), 1, 27 * g.nsplit), 256, 0, st>>>(g);
+    if (int rc = launched("deep_gemm_kernel (conv3)")) return rc;
     deep_reduce_conv3_kernel<<<grid_for(M * p.cout, 256, 8), 256, 0, st>>>(p, p.splitk_ws, 27 * g.nsplit);
-    return launched("deep_gemm_kernel (conv3)");
+    return launched("deep_reduce_conv3_kernel");
   }
   if (p.cout <= 4) conv3_dispatch<4, 8, 1>(p, st);              // lastConv: 18 -> 3 at full resolution
   else if (nvox * ((p.cout + 7) / 8) >= (1 << 16)) conv3_dispatch<8, 4, 1>(p, st);
@@ -1559,6 +1560,7 @@ static int convt4_mma_dispatch(const ConvT4Params& p, cudaStream_t st) {
   const long long vol = static_cast<long long>(p.Di) * p.Hi * p.Wi;
   reg_split_kernel<<<grid_for(p.N * (p.cin / 2) * vol, 256, 16), 256, 0, st>>>(p.in, p.in_nstride, p.in_cstride, p.N,
                                                                               p.cin, vol, p.xsplit);
+  if (int rc = launched("reg_split_kernel")) return rc;
   const int ntx = (p.Wi + TX - 1) / TX, nty = (p.Hi + Cfg::TY - 1) / Cfg::TY;
   dim3 g(static_cast<unsigned>(ntx) * nty * p.Di, p.cout / 16, p.N);
   static const int dbg = getenv("OAI_CONVT4_DEBUG") ? atoi(getenv("OAI_CONVT4_DEBUG")) : 0;
@@ -1591,9 +1593,10 @@ int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
     g.nsplit = deep_ci_split(p.cin, tiles * 64);
     g.ci_per_split = (p.cin + g.nsplit - 1) / g.nsplit;
     deep_gemm_kernel<1><<<dim3(static_cast<unsigned>(tiles), 8, 8 * g.nsplit), 256, 0, st>>>(g);
+    if (int rc = launched("deep_gemm_kernel (convt4)")) return rc;
     deep_reduce_convt4_kernel<<<grid_for(static_cast<long long>(p.N) * nout * p.cout, 256, 8), 256, 0, st>>>(
         p, reinterpret_cast<const float*>(p.xsplit), 8 * g.nsplit);
-    return launched("deep_gemm_kernel (convt4)");
+    return launched("deep_reduce_convt4_kernel");
   }
   // tensor path: rows must be 16-byte multiples for the TMA boxes (every tallUNet2 level that is wide enough is)
   if (p.wpk && p.xsplit && p.cin % 16 == 0 && p.cout % 16 == 0 && p.Wi >= 12 && p.Wi % 4 == 0 &&

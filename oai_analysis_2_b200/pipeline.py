@@ -82,7 +82,7 @@ class KneePipeline:
         real overlap) matching the captured graph.  The H2D copy of knee i+1 and the D2H copy of knee i-1 run on their
         own streams while knee i computes (device staging buffers on both sides of the graph's static I/O).  Yields one
         result dict per knee, in order; its arrays are views of double-buffered pinned memory and stay valid until the
-        generator has been advanced twice more."""
+        generator is advanced again (copy what must outlive that)."""
         if getattr(self, "_graph", None) is None:
             raise RuntimeError("run_stream needs KneePipeline.capture() first")
         dev = self.device
