@@ -66,3 +66,27 @@ def test_parity_class_tap_mapping_reproduces_conv_transpose():
                             visits += 1
     assert visits == 64
     assert (out - ref).abs().max() < 1e-12
+
+
+def test_split_k_gemm_view_of_the_strided_conv():
+    """deep_gemm_kernel<0> treats Conv3d k3 s2 p1 as one GEMM per tap: A[m][ci] = x[ci][2 o - 1 + k] (zero outside),
+    partials summed over (tap, channel range) in a fixed order.  Emulated in numpy against torch."""
+    g = torch.Generator().manual_seed(2)
+    cin, cout, dims = 6, 5, (5, 6, 7)
+    x = torch.randn(1, cin, *dims, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv3d(x, w, stride=2, padding=1)[0]
+    Do, Ho, Wo = ref.shape[1:]
+    xp = F.pad(x[0], (1, 1, 1, 1, 1, 1))
+    nsplit, per = 2, 3                                            # two channel ranges per tap, like ci_per_split
+    partial = torch.zeros(27 * nsplit, cout, Do, Ho, Wo, dtype=torch.float64)
+    for tap in range(27):
+        kd, kh, kw = tap // 9, (tap // 3) % 3, tap % 3
+        a = xp[:, kd:kd + 2 * Do:2, kh:kh + 2 * Ho:2, kw:kw + 2 * Wo:2]   # input at 2 o - 1 + k
+        for s in range(nsplit):
+            cs = slice(s * per, (s + 1) * per)
+            partial[tap * nsplit + s] = torch.einsum("izyx,oi->ozyx", a[cs], w[:, cs, kd, kh, kw])
+    out = torch.zeros_like(ref)
+    for k in range(27 * nsplit):                                  # the reduce kernel's fixed order
+        out += partial[k]
+    assert (out - ref).abs().max() < 1e-12
