@@ -108,6 +108,11 @@ _scratch = {}
 
 
 def _scratch_buf(device, tag, nbytes):
+    """Device scratch for the kernels that need a workspace.  Eager calls share one growing buffer per (device, tag);
+    while a CUDA graph is being captured the buffer comes from the graph's own memory pool instead, so replays never
+    depend on the shared buffer (which a later, larger eager call may reallocate)."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
     key = (device, tag)
     if key not in _scratch or _scratch[key].numel() < nbytes:
         _scratch[key] = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
@@ -272,10 +277,7 @@ def intensity_window(vol, perc_lo=0.1, perc_hi=99.9, out_min=0.0, out_max=1.0, o
     if out is None:
         out = torch.empty_like(vol)
     nbytes = int(lib.oai_intensity_window_workspace())
-    key = (vol.device, "window")
-    if key not in _scratch or _scratch[key].numel() < nbytes:
-        _scratch[key] = torch.empty(nbytes, dtype=torch.uint8, device=vol.device)
-    ws = _scratch[key]
+    ws = _scratch_buf(vol.device, "window", nbytes)
     check(lib.oai_intensity_window(ptr(vol), c_ll(vol.numel()), ctypes.c_double(perc_lo), ctypes.c_double(perc_hi),
                                    c_float(out_min), c_float(out_max), ptr(out), ptr(ws), c_size(nbytes),
                                    stream_ptr()), "intensity_window")
