@@ -41,7 +41,9 @@ class KneePipeline:
     # -- CUDA graph of the whole per-knee path (about a hundred launches; replaying one graph removes the launch gaps)
     def capture(self, vol_shape, geom, n_vertices=None, on_record=None):
         """Record run_device for volumes of `vol_shape` (and `n_vertices` mesh vertices) into a CUDA graph with static
-        input / output buffers.  Afterwards run_device_graph / run replay it."""
+        input / output buffers.  Afterwards run_device_graph / run replay it.  The graph holds the addresses of the
+        models' cached buffers (packed weights, the registration nets' concatenation buffers), so after capture this
+        segmenter / registration model must not be run eagerly on other shapes (that would re-size those caches)."""
         dev = self.device
         self._g_vol = torch.zeros(tuple(vol_shape), dtype=torch.float32, device=dev)
         self._g_verts = None if not n_vertices else torch.zeros((int(n_vertices), 3), dtype=torch.float64, device=dev)
