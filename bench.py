@@ -347,9 +347,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--tiles-per-batch", type=int, default=None)
+    ap.add_argument("--precision", default=None, choices=["fp16", "mixed", "fp16x2", "fp16x3", "bf16"],
+                    help="segmentation precision plan (default: the product default, 'mixed')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the CUDA graph")
     args = ap.parse_args()
+    if args.precision:
+        os.environ["OAI_B200_SEG_PRECISION"] = args.precision
     if args.impl == "reference":
         run_reference(args)
     else:

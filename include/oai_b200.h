@@ -97,12 +97,37 @@ OAI_API int oai_conv3d_igemm_plan(int D, int H, int W, int c0, int c1, int cout,
 OAI_API int oai_pack_conv_weights(const float* w, int cout, int c0, int c1, int D, int H, int W, int pointwise, int ab_format,
                           int flags, void* dst, size_t dst_bytes);
 
+/* Split-precision forms.  fp16 carries 11 significant bits (what the reference's cuDNN path gets from TF32); where the
+ * north-star Dice bar needs more, a tensor is stored as two 16-bit planes per voxel, [hi | lo] with hi = rn16(x) and
+ * lo = rn16(x - hi) (2*C channels, ~22 bits), and a layer K-concatenates `terms` products in the same accumulator:
+ *   terms 1: a*w                       (sources may still be split tensors: only their hi plane is read)
+ *   terms 2: (a_hi + a_lo) * w         (sources must be split)
+ *   terms 3: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo   (fp32-faithful; weights packed as hi + lo too)
+ * in_split: the sources are [hi | lo] tensors; out_split: write the output as a [hi | lo] tensor (dense NDHWC with
+ * 2*cout channels).  pointwise as above (2 = ConvTranspose3d(k2,s2), out on the 2x grid); region may be NULL.
+ * plan[10]: the 9 values of oai_conv3d_igemm_plan + the packed size in 16-byte units. */
+OAI_API int oai_conv3d_igemm_plan_ex(int D, int H, int W, int c0, int c1, int cout, int pointwise, int terms, int flags,
+                                     int* plan);
+OAI_API int oai_pack_conv_weights_ex(const float* w, int cout, int c0, int c1, int D, int H, int W, int pointwise,
+                                     int terms, int ab_format, int flags, void* dst, size_t dst_bytes);
+OAI_API int oai_conv3d_igemm_ex(const void* src0, int c0, const void* src1, int c1, int in_split, int NT, int D, int H,
+                                int W, const void* wpack, size_t wpack_bytes, const float* bias, int cout,
+                                int pointwise, int relu, int ab_format, int terms, void* out, int out_split, int flags,
+                                const int* region, void* stream);
+
+/* fp16 saturation guard: how many epilogue threads of the conv kernel (on the current device, since the last reset) saw
+ * an activation outside the fp16 range (|x| > 65504, or NaN) before rounding it.  Non-zero means the 16-bit tensors hold
+ * inf: re-run with ab_format = 1 (bf16).  Synchronises `stream`. */
+OAI_API int oai_conv_overflow_count(long long* count, int reset, void* stream);
+
 /* Per-launch timing of oai_conv3d_igemm with CUDA events on the launch stream (bench.py's roofline numbers):
  * between begin and end every conv launch is bracketed by an event pair; end waits for them and returns the summed
  * kernel time, the number of launches, their algorithmic FLOPs (2*voxels*cout*cin*taps over the whole layer, i.e. what
  * the reference executes) and the FLOPs actually issued (dead-halo rows skipped, see oai_conv3d_igemm_region). */
 OAI_API int oai_profile_begin(void);
 OAI_API int oai_profile_end(double* conv_ms, long long* conv_launches, double* conv_flops, double* conv_exec_flops);
+/* launch i of the current profile (call before oai_profile_end): kernel ms, algorithmic and issued FLOPs */
+OAI_API int oai_profile_entry(int i, double* ms, double* flops, double* exec_flops);
 
 /* Tiling geometry arrays used below (all z,y,x): geom[12] = {tile[3], effective[3], overlap[3], grid[3]} exactly as
  * Partition computes them (image_transforms.py:389-391,404-406); vol_dims[3] = image size. */
@@ -116,6 +141,14 @@ OAI_API int oai_seg_stem(const float* vol, const int* vol_dims, const int* geom,
 
 /* nn.MaxPool3d(2) (networks.py:52-54) on act16 [N,D,H,W,C] -> [N,D/2,H/2,W/2,C]. */
 OAI_API int oai_maxpool3d_2(const void* in, void* out, int N, int D, int H, int W, int C, int ab_format, void* stream);
+/* Same on split tensors: in_split: the input is [hi | lo] (2C channels per voxel); out_split: the output too (the
+ * winner is chosen by hi + lo and both halves are kept); in_split without out_split pools the hi plane only. */
+OAI_API int oai_maxpool3d_2_ex(const void* in, void* out, int N, int D, int H, int W, int C, int in_split, int out_split,
+                               int ab_format, void* stream);
+/* oai_seg_stem writing a [hi | lo] tensor [ntiles, td, th, tw, 2*c0] when out_split != 0. */
+OAI_API int oai_seg_stem_ex(const float* vol, const int* vol_dims, const int* geom, int tile0, int ntiles,
+                            const float* w27c, const float* bias, int c0, void* out, int ab_format, int out_split,
+                            void* stream);
 
 /* dc0 = Conv3d(C->ncls,k1) (networks.py:66,148) + torch.sigmoid (segmenter.py:121) [+ ">0.5" when out_mode==1,
  * segmenter.py:123-124; out_mode==2 writes raw logits] + Partition.assemble (image_transforms.py:492-513): each tile's interior is written to its
@@ -123,6 +156,59 @@ OAI_API int oai_maxpool3d_2(const void* in, void* out, int N, int D, int H, int 
 OAI_API int oai_seg_head(const void* act, int C, int ncls, const float* w, const float* b, float* out,
                          const int* vol_dims, const int* geom, int tile0, int ntiles, const int* crop_zyx, int out_mode,
                          int ab_format, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stage-level segmentation  (reference: Segmenter3DInPatchClassWise.segment, oai_analysis/segmentation/
+ * segmenter.py:100-131, with pred_setup :51-62): two calls segment a volume; layer order, skip wiring, BatchNorm
+ * folding, weight packing, dead-halo regions and the workspace layout live inside the library.
+ * ------------------------------------------------------------------------------------------------------------ */
+enum {
+  OAI_SEG_PRECISION_FP16 = 0,    /* 16-bit operands everywhere (TF32-class mantissa, the reference's cuDNN default) */
+  OAI_SEG_PRECISION_MIXED = 1,   /* default: the two full-resolution decoder layers (dc2, dc1) read fp16 hi+lo inputs */
+  OAI_SEG_PRECISION_FP16X2 = 2,  /* every layer reads fp16 hi+lo activations (terms 2) */
+  OAI_SEG_PRECISION_FP16X3 = 3,  /* fp32-faithful: activations and weights both hi+lo (terms 3) */
+  OAI_SEG_PRECISION_CUSTOM = 4   /* layer_terms[] below */
+};
+
+typedef struct {
+  int in_channels, n_classes, bias, BN;   /* training-config "model_setting" (segmenter.py:56) */
+  int patch_xyz[3];                       /* training-config "patch_size" (x,y,z; segmenter.py:53) */
+  int overlap_xyz[3];                     /* segmenter_config "overlap_size" (x,y,z; analysis_object.py:23) */
+  int ab_format;                          /* 0 fp16, 1 bf16 */
+  int precision;                          /* OAI_SEG_PRECISION_* */
+  int layer_terms[17];                    /* CUSTOM only: terms (1..3) of ec0..ec7, dc9..dc1 (ec0 is always exact) */
+} oai_seg_config;
+
+/* one entry of the reference's state_dict: float32, contiguous, host memory, torch layout */
+typedef struct {
+  const char* name;
+  const float* data;
+  int ndim;
+  long long shape[5];
+} oai_tensor;
+
+typedef struct oai_seg_handle* oai_seg_t;
+
+/* Dead-halo elimination (host arithmetic, no GPU): boxes[17][6] = inclusive {lo z,y,x, hi z,y,x} of the output
+ * sub-box each layer ec0..ec7, dc9..dc1 must compute for the kept tile interior (the reference computes whole tiles
+ * and crops afterwards, image_transforms.py:497-503); up-convs are boxed on their input grid, encoder layers whole. */
+OAI_API int oai_seg_needed_regions(const int* tile_zyx, const int* overlap_zyx, int* boxes);
+/* the per-layer terms a precision preset expands to (terms17[0] = ec0 ... terms17[16] = dc1) */
+OAI_API int oai_seg_layer_terms(int precision, int* terms17);
+/* UNet(in_channels, n_classes, bias, BN) + load_state_dict(strict=True) (networks.py:39-66, utils.py:20-41) on the
+ * current device.  state_dict uses the reference's keys ("ec0.0.weight", "dc9.1.running_var", "dc0.bias", ...);
+ * missing, mis-shaped or unexpected keys fail.  The handle owns the packed weights (about 40 MB). */
+OAI_API int oai_seg_create(const oai_seg_config* cfg, const oai_tensor* state_dict, int n_tensors, oai_seg_t* handle);
+OAI_API int oai_seg_destroy(oai_seg_t handle);
+/* tiles Partition cuts the volume into (image_transforms.py:404-406) and the device workspace one forward needs when
+ * tiles_per_batch tiles (<= 0: all) go through the network together */
+OAI_API int oai_seg_num_tiles(oai_seg_t handle, const int* vol_dims);
+OAI_API size_t oai_seg_workspace_bytes(oai_seg_t handle, const int* vol_dims, int tiles_per_batch);
+/* vol: float32 [D][H][W] on the device; out: float32 [n_classes][D][H][W] (class 0 = FC, 1 = TC), out_mode 0 = sigmoid
+ * probabilities, 1 = (p > 0.5) masks, 2 = logits.  workspace: 256-byte aligned device memory of at least
+ * oai_seg_workspace_bytes(); asynchronous on `stream`. */
+OAI_API int oai_seg_forward(oai_seg_t handle, const float* vol, const int* vol_dims, float* out, int out_mode,
+                            int tiles_per_batch, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * ICON / GradICON registration  (reference call sites: oai_analysis/registration.py:20,25,

@@ -30,6 +30,10 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kTmemCols = 512;
 
+// activations that left the fp16 range (|x| > 65504 before rounding) since the last reset: a real checkpoint with large
+// folded-BatchNorm scales would otherwise turn into inf / NaN silently
+__device__ unsigned int g_fp16_overflow = 0;
+
 struct BlockInfo {
   int c, kh, kw, kdlo, nkd;
   int ns;  // taps stacked along N in this block's weight rows (== nkd except kModeUp2)
@@ -103,6 +107,16 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
   }
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// rn16(x - hi) for the pair whose rounded hi halves are already packed in `hi`
+__device__ __forceinline__ uint32_t pack2_residual(float a, float b, uint32_t hi, int fmt) {
+  if (fmt == 0) {
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    return pack2(a - h.x, b - h.y, fmt);
+  }
+  const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi));
+  return pack2(a - h.x, b - h.y, fmt);
 }
 
 // acc[k] += sum_i relu(v[i] + bias[i]) * w[k][i] over one 32-column chunk (w rows are 64 floats apart)
@@ -182,9 +196,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         const UnitInfo ui = decode_unit(p, u);
         for (int b = 0; b < p.nblk; ++b) {
           const BlockInfo bi = decode_block(p, b);
-          const bool src0 = bi.c < p.nchunk0;
-          const CUtensorMap* tm = src0 ? &tm0 : &tm1;
-          const int cc = (src0 ? bi.c : bi.c - p.nchunk0) * 64;
+          const CUtensorMap* tm = p.chunk_src[bi.c] == 0 ? &tm0 : &tm1;
+          const int cc = p.chunk_cc[bi.c];
           const int kdhi = bi.kdlo + bi.nkd - 1;
           const int dlo = max(0, ui.d0 + bi.kdlo - 1);
           const int dhi = min(p.D - 1, ui.d0 + ui.rd - 1 + kdhi - 1);
@@ -385,6 +398,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     const int th = m / p.TW, tw = m % p.TW;
     uint32_t use_bits = 0;
     uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
+    float amax = 0.f;   // largest |activation| this thread rounded to 16 bits
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
       const UnitInfo ui = decode_unit(p, u);
       const long long off0 = p.obase + ui.n * p.osN + (ui.h0 + th) * p.osH + (ui.w0 + tw) * p.osW +
@@ -469,12 +483,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               if (p.relu) {
                 x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
               }
+              amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fmaxf(fabsf(x2), fabsf(x3))));
               o[2 * i] = pack2(x0, x1, p.ab_format);
               o[2 * i + 1] = pack2(x2, x3, p.ab_format);
             }
             uint4* d4 = reinterpret_cast<uint4*>(dst + (j + h) * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            if (p.out_split) {
+              // lo plane: the rounding residual of the hi plane, so hi + lo carries ~22 mantissa bits
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sb + (j + h) * 32 + 4 * i);
+                float x0 = __uint_as_float(v[h][4 * i]) + b4.x, x1 = __uint_as_float(v[h][4 * i + 1]) + b4.y;
+                float x2 = __uint_as_float(v[h][4 * i + 2]) + b4.z, x3 = __uint_as_float(v[h][4 * i + 3]) + b4.w;
+                if (p.relu) {
+                  x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+                }
+                o[2 * i] = pack2_residual(x0, x1, o[2 * i], p.ab_format);
+                o[2 * i + 1] = pack2_residual(x2, x3, o[2 * i + 1], p.ab_format);
+              }
+              uint4* l4 = reinterpret_cast<uint4*>(dst + p.out_lo_off + (j + h) * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) l4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
           }
         }
         continue;  // accumulator already released
@@ -485,6 +517,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
       }
       use_bits ^= (1u << ui.ra) - 1u;
     }
+    if (p.ab_format == 0 && !(amax <= 65504.f)) atomicAdd(&g_fp16_overflow, 1u);   // also catches NaN
   }
 
   tc_fence_before();
@@ -502,15 +535,27 @@ static size_t conv_igemm_smem_bytes(const ConvIgemmParams& p) {
   return 1024 + p.n_wbuf * wstride + static_cast<size_t>(p.n_astage) * p.astage_stride + 48 * 8 + 2112 + 2048;
 }
 
+cudaError_t conv_overflow_count(unsigned int* count, bool reset, cudaStream_t stream) {
+  cudaError_t e = cudaMemcpyFromSymbolAsync(count, g_fp16_overflow, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess || !reset) return e;
+  const unsigned int zero = 0;
+  return cudaMemcpyToSymbolAsync(g_fp16_overflow, &zero, sizeof(unsigned int), 0, cudaMemcpyHostToDevice, stream);
+}
+
 cudaError_t conv_igemm_launch(const ConvIgemmParams& p, const CUtensorMap& tm0, const CUtensorMap& tm1, int num_sms,
                               cudaStream_t stream) {
   const size_t smem = conv_igemm_smem_bytes(p);
-  static size_t configured = 0;
-  if (smem > configured) {
+  // the attribute is per device: cache what has been configured for each device of this process
+  static size_t configured[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || smem > configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    configured = smem;
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
   }
   const int grid = p.nunits < num_sms ? p.nunits : num_sms;
   conv_igemm_kernel<<<grid, kThreads, smem, stream>>>(tm0, tm1, p);

@@ -6,6 +6,8 @@
 
 namespace oai {
 
+constexpr int kMaxChunks = 48;
+
 enum ConvMode : int {
   kModeRowShared = 0,  // 3x3x3, M tile = one full 128-wide row; w halo loaded once, kw taps = smem row shifts
   kModePerTap = 1,     // 3x3x3, one TMA box per (kh,kw) shift; M tile = TH x TW patch
@@ -39,8 +41,12 @@ struct ConvIgemmParams {
   int hp_lo, hp_cnt;  // ... and patch rows [hp_lo, hp_lo+hp_cnt) (units of TH voxel rows); the rest is dead halo
   int cout;         // N per accumulator (multiple of 16, <= 256)
   int nhalf;        // N splits (cout_total = nhalf*cout)
-  int nchunk0;      // 64-channel K chunks read from source 0
-  int nchunk1;      // ... then from source 1 (skip connection); 0 if single source
+  int nchunks;      // K chunks (one TMA box of 64 channels each, 32 when row_bytes == 64) per tap set
+  // chunk c reads channels [chunk_cc[c], +64) of tensor map chunk_src[c].  A plain layer lists source 0's channels then
+  // source 1's (the decoder's torch.cat).  Split-precision layers (terms 2 / 3) read tensors stored as [hi | lo] fp16
+  // planes (2C channels per voxel) and list more chunks: K-concatenation of a_hi*w, a_lo*w (and a_hi*w_lo).
+  uint16_t chunk_cc[kMaxChunks];
+  uint8_t chunk_src[kMaxChunks];
   int k16_steps;    // K=16 MMA steps per chunk: 4 (64 channels) or 2 (32 channels)
   int row_bytes;    // shared-memory row pitch of one voxel's K slice: 128 (64 ch, SWIZZLE_128B) or 64 (32 ch, SWIZZLE_64B)
   int mode;         // ConvMode
@@ -61,6 +67,10 @@ struct ConvIgemmParams {
   // output addressing (element units, 16-bit elements): off = obase + n*osN + d*osD + h*osH + w*osW + nh*cout + c
   void* out;
   long long obase, osN, osD, osH, osW;
+  // split output: besides hi = rn16(x) also write lo = rn16(x - hi) out_lo_off elements further (the [hi | lo] layout
+  // split-precision consumers read); the os* strides then address the 2*C-channel voxel rows
+  int out_split;
+  long long out_lo_off;
   int nunits;
   HeadFuse head;
 };

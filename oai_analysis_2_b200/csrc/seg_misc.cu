@@ -26,6 +26,11 @@ __device__ __forceinline__ float2 unpack16(uint32_t u, int fmt) {
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
 
+__device__ __forceinline__ uint32_t pack16_residual(float a, float b, uint32_t hi, int fmt) {
+  const float2 h = unpack16(hi, fmt);
+  return pack16(a - h.x, b - h.y, fmt);
+}
+
 // numpy 'reflect' (edge sample not repeated), valid for pads smaller than the axis length
 __device__ __forceinline__ int reflect_idx(int i, int n) {
   if (n == 1) return 0;
@@ -98,8 +103,9 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
 #pragma unroll
           for (int i = 0; i < kStemXS + 2; ++i) in[kd * 3 + kh][i] = sl[(ly + kh) * SW + lx + i];
       }
+      const int CP = p.out_split ? 2 * p.c0 : p.c0;
       uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) +
-                      ((((static_cast<size_t>(t) * p.td + d) * p.th + y) * p.tw + x) * p.c0);
+                      ((((static_cast<size_t>(t) * p.td + d) * p.th + y) * p.tw + x) * CP);
       for (int c8 = 0; c8 < p.c0; c8 += 8) {
         float acc[kStemXS][8];
 #pragma unroll
@@ -126,7 +132,15 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
           o.y = pack16(fmaxf(acc[v][2], 0.f), fmaxf(acc[v][3], 0.f), p.fmt);
           o.z = pack16(fmaxf(acc[v][4], 0.f), fmaxf(acc[v][5], 0.f), p.fmt);
           o.w = pack16(fmaxf(acc[v][6], 0.f), fmaxf(acc[v][7], 0.f), p.fmt);
-          *reinterpret_cast<uint4*>(dst + static_cast<size_t>(v) * p.c0 + c8) = o;
+          *reinterpret_cast<uint4*>(dst + static_cast<size_t>(v) * CP + c8) = o;
+          if (p.out_split) {
+            uint4 l;
+            l.x = pack16_residual(fmaxf(acc[v][0], 0.f), fmaxf(acc[v][1], 0.f), o.x, p.fmt);
+            l.y = pack16_residual(fmaxf(acc[v][2], 0.f), fmaxf(acc[v][3], 0.f), o.y, p.fmt);
+            l.z = pack16_residual(fmaxf(acc[v][4], 0.f), fmaxf(acc[v][5], 0.f), o.z, p.fmt);
+            l.w = pack16_residual(fmaxf(acc[v][6], 0.f), fmaxf(acc[v][7], 0.f), o.w, p.fmt);
+            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(v) * CP + p.c0 + c8) = l;
+          }
         }
       }
     }
@@ -257,8 +271,9 @@ __global__ void __launch_bounds__(128) stem_mma_kernel(const StemParams p) {
         sl = sl >= 3 ? sl - 3 : sl;
         off[i] = sl * SH * SW + trel[i] + ly * SW + g;
       }
+      const int CP = p.out_split ? 2 * C0 : C0;   // channels per voxel row of the output tensor
       uint16_t* row_out = reinterpret_cast<uint16_t*>(p.out) +
-                          (((static_cast<size_t>(tl) * p.td + d) * p.th + y) * p.tw + x0) * C0;
+                          (((static_cast<size_t>(tl) * p.td + d) * p.th + y) * p.tw + x0) * CP;
 #pragma unroll 2
       for (int j = 0; j < kStemTW / 16; ++j) {
         if (x0 + 16 * j >= p.tw) break;
@@ -299,8 +314,21 @@ __global__ void __launch_bounds__(128) stem_mma_kernel(const StemParams p) {
         o1.z = pack16(fmaxf(acc[2][2], 0.f), fmaxf(acc[2][3], 0.f), p.fmt);
         o1.w = pack16(fmaxf(acc[3][2], 0.f), fmaxf(acc[3][3], 0.f), p.fmt);
         const int xa = x0 + 16 * j + g, xb = xa + 8;
-        if (xa < p.tw) *reinterpret_cast<uint4*>(row_out + static_cast<size_t>(16 * j + g) * C0 + 8 * t) = o0;
-        if (xb < p.tw) *reinterpret_cast<uint4*>(row_out + static_cast<size_t>(16 * j + g + 8) * C0 + 8 * t) = o1;
+        if (xa < p.tw) *reinterpret_cast<uint4*>(row_out + static_cast<size_t>(16 * j + g) * CP + 8 * t) = o0;
+        if (xb < p.tw) *reinterpret_cast<uint4*>(row_out + static_cast<size_t>(16 * j + g + 8) * CP + 8 * t) = o1;
+        if (p.out_split) {   // lo plane: rounding residuals of the hi plane
+          uint4 l0, l1;
+          l0.x = pack16_residual(fmaxf(acc[0][0], 0.f), fmaxf(acc[0][1], 0.f), o0.x, p.fmt);
+          l0.y = pack16_residual(fmaxf(acc[1][0], 0.f), fmaxf(acc[1][1], 0.f), o0.y, p.fmt);
+          l0.z = pack16_residual(fmaxf(acc[2][0], 0.f), fmaxf(acc[2][1], 0.f), o0.z, p.fmt);
+          l0.w = pack16_residual(fmaxf(acc[3][0], 0.f), fmaxf(acc[3][1], 0.f), o0.w, p.fmt);
+          l1.x = pack16_residual(fmaxf(acc[0][2], 0.f), fmaxf(acc[0][3], 0.f), o1.x, p.fmt);
+          l1.y = pack16_residual(fmaxf(acc[1][2], 0.f), fmaxf(acc[1][3], 0.f), o1.y, p.fmt);
+          l1.z = pack16_residual(fmaxf(acc[2][2], 0.f), fmaxf(acc[2][3], 0.f), o1.z, p.fmt);
+          l1.w = pack16_residual(fmaxf(acc[3][2], 0.f), fmaxf(acc[3][3], 0.f), o1.w, p.fmt);
+          if (xa < p.tw) *reinterpret_cast<uint4*>(row_out + static_cast<size_t>(16 * j + g) * CP + C0 + 8 * t) = l0;
+          if (xb < p.tw) *reinterpret_cast<uint4*>(row_out + static_cast<size_t>(16 * j + g + 8) * CP + C0 + 8 * t) = l1;
+        }
       }
     }
     __syncthreads();  // everyone is done with slice d-1 before its slot is overwritten by slice d+2
@@ -322,8 +350,11 @@ int stem_launch(const StemParams& p, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------ max pool 2x2x2
+// in: [N,D,H,W,Cin8*8] of which the first C8*8 channels are pooled (a [hi | lo] tensor pooled through its hi plane:
+// rounding is monotonic, so max(hi) is the hi of the max).  With split != 0 the tensor is [hi | lo] on both sides and
+// the winner is chosen by hi + lo; its two halves are copied unchanged.
 __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N,
-                                                       int D, int H, int W, int C8, int fmt) {
+                                                       int D, int H, int W, int C8, int Cin8, int split, int fmt) {
   const int Do = D / 2, Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(N) * Do * Ho * Wo * C8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -334,9 +365,9 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__
     const int h = r % Ho; r /= Ho;
     const int d = r % Do; r /= Do;
     const int n = static_cast<int>(r);
-    float m[8];
+    float m[8], mh[8], ml[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; mh[j] = 0.f; ml[j] = 0.f; }
 #pragma unroll
     for (int dz = 0; dz < 2; ++dz)
 #pragma unroll
@@ -344,26 +375,51 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
           const size_t off =
-              ((((static_cast<size_t>(n) * D + 2 * d + dz) * H + 2 * h + dy) * W + 2 * w + dx) * C8) + c;
+              ((((static_cast<size_t>(n) * D + 2 * d + dz) * H + 2 * h + dy) * W + 2 * w + dx) * Cin8) + c;
           const uint4 v = __ldg(in + off);
           const float2 a = unpack16(v.x, fmt), b = unpack16(v.y, fmt), cc = unpack16(v.z, fmt), e = unpack16(v.w, fmt);
-          m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], b.x); m[3] = fmaxf(m[3], b.y);
-          m[4] = fmaxf(m[4], cc.x); m[5] = fmaxf(m[5], cc.y); m[6] = fmaxf(m[6], e.x); m[7] = fmaxf(m[7], e.y);
+          const float f[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, e.x, e.y};
+          if (!split) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+          } else {
+            const uint4 u = __ldg(in + off + C8);
+            const float2 a2 = unpack16(u.x, fmt), b2 = unpack16(u.y, fmt), c2 = unpack16(u.z, fmt),
+                         e2 = unpack16(u.w, fmt);
+            const float g[8] = {a2.x, a2.y, b2.x, b2.y, c2.x, c2.y, e2.x, e2.y};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float t = f[j] + g[j];
+              if (t > m[j]) { m[j] = t; mh[j] = f[j]; ml[j] = g[j]; }
+            }
+          }
         }
     uint4 o;
-    o.x = pack16(m[0], m[1], fmt); o.y = pack16(m[2], m[3], fmt);
-    o.z = pack16(m[4], m[5], fmt); o.w = pack16(m[6], m[7], fmt);
-    out[i] = o;
+    if (!split) {
+      o.x = pack16(m[0], m[1], fmt); o.y = pack16(m[2], m[3], fmt);
+      o.z = pack16(m[4], m[5], fmt); o.w = pack16(m[6], m[7], fmt);
+      out[i] = o;
+    } else {
+      const size_t ob = (i / C8) * (2 * C8) + c;
+      o.x = pack16(mh[0], mh[1], fmt); o.y = pack16(mh[2], mh[3], fmt);
+      o.z = pack16(mh[4], mh[5], fmt); o.w = pack16(mh[6], mh[7], fmt);
+      out[ob] = o;
+      o.x = pack16(ml[0], ml[1], fmt); o.y = pack16(ml[2], ml[3], fmt);
+      o.z = pack16(ml[4], ml[5], fmt); o.w = pack16(ml[6], ml[7], fmt);
+      out[ob + C8] = o;
+    }
   }
 }
 
-int maxpool2_launch(const void* in, void* out, int N, int D, int H, int W, int C, int fmt, cudaStream_t st) {
+int maxpool2_launch(const void* in, void* out, int N, int D, int H, int W, int C, int in_split, int out_split, int fmt,
+                    cudaStream_t st) {
   const long long total = static_cast<long long>(N) * (D / 2) * (H / 2) * (W / 2) * (C / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   maxpool2_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const uint4*>(in),
-                                                                   static_cast<uint4*>(out), N, D, H, W, C / 8, fmt);
+                                                                   static_cast<uint4*>(out), N, D, H, W, C / 8,
+                                                                   (in_split ? 2 : 1) * (C / 8), out_split, fmt);
   return launched("maxpool2_kernel");
 }
 

@@ -15,8 +15,9 @@ struct StemParams {
   int c0;            // output channels (<= 64, multiple of 8)
   const float* w;    // [27][c0] folded weights (tap-major)
   const float* b;    // [c0]
-  void* out;         // [ntiles, td, th, tw, c0] 16-bit
+  void* out;         // [ntiles, td, th, tw, c0] 16-bit ([.., 2*c0] = [hi | lo] planes when out_split)
   int fmt;
+  int out_split;
 };
 
 struct HeadParams {
@@ -33,7 +34,8 @@ struct HeadParams {
 };
 
 int stem_launch(const StemParams& p, cudaStream_t st);
-int maxpool2_launch(const void* in, void* out, int N, int D, int H, int W, int C, int fmt, cudaStream_t st);
+int maxpool2_launch(const void* in, void* out, int N, int D, int H, int W, int C, int in_split, int out_split, int fmt,
+                    cudaStream_t st);
 int head_launch(const HeadParams& p, cudaStream_t st);
 
 }  // namespace oai

@@ -63,28 +63,173 @@ def conv3d_igemm(src0, src1, wpack, bias, cout, pointwise=False, relu=True, ab_f
     return out
 
 
+# ------------------------------------------------------------------------------------------------ stage-level segmentation
+class _SegConfig(ctypes.Structure):
+    _fields_ = [("in_channels", c_int), ("n_classes", c_int), ("bias", c_int), ("BN", c_int),
+                ("patch_xyz", c_int * 3), ("overlap_xyz", c_int * 3), ("ab_format", c_int), ("precision", c_int),
+                ("layer_terms", c_int * 17)]
+
+
+class _Tensor(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.c_void_p), ("ndim", c_int), ("shape", c_ll * 5)]
+
+
+def seg_layer_terms(precision):
+    t = (c_int * 17)()
+    check(lib.oai_seg_layer_terms(int(precision), t), "seg_layer_terms")
+    return list(t)
+
+
+def seg_needed_regions(tile_zyx, overlap_zyx):
+    """[17, 6] int array: inclusive lo(z,y,x), hi(z,y,x) per layer ec0..dc1 (host arithmetic in the library)."""
+    boxes = np.zeros((17, 6), dtype=np.int32)
+    check(lib.oai_seg_needed_regions(ptr(np.asarray(tile_zyx, dtype=np.int32)),
+                                     ptr(np.asarray(overlap_zyx, dtype=np.int32)), ptr(boxes)), "seg_needed_regions")
+    return boxes
+
+
+class SegHandle:
+    """oai_seg_create / oai_seg_forward / oai_seg_destroy: the whole segmentation stage behind one handle."""
+
+    def __init__(self, state_dict, in_channels, n_classes, bias, BN, patch_xyz, overlap_xyz, ab_format=0, precision=1,
+                 layer_terms=None):
+        cfg = _SegConfig(int(in_channels), int(n_classes), int(bool(bias)), int(bool(BN)),
+                         (c_int * 3)(*[int(v) for v in patch_xyz]), (c_int * 3)(*[int(v) for v in overlap_xyz]),
+                         int(ab_format), 4 if layer_terms is not None else int(precision),
+                         (c_int * 17)(*([int(v) for v in layer_terms] if layer_terms is not None else [1] * 17)))
+        keep, arr = [], (_Tensor * len(state_dict))()
+        for i, (k, v) in enumerate(state_dict.items()):
+            a = np.ascontiguousarray(torch.as_tensor(v).detach().cpu().numpy(), dtype=np.float32)
+            keep.append(a)
+            shape = list(a.shape) + [0] * (5 - a.ndim)
+            arr[i] = _Tensor(k.encode(), a.ctypes.data, a.ndim, (c_ll * 5)(*shape))
+        self._h = ctypes.c_void_p()
+        self._auto = {}
+        self.n_classes = int(n_classes)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        check(lib.oai_seg_create(ctypes.byref(cfg), arr, len(state_dict), ctypes.byref(self._h)), "seg_create")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.oai_seg_destroy(h)
+
+    def num_tiles(self, vol_shape):
+        return int(lib.oai_seg_num_tiles(self._h, ptr(np.asarray(vol_shape, dtype=np.int32))))
+
+    def workspace_bytes(self, vol_shape, tiles_per_batch=0):
+        return int(lib.oai_seg_workspace_bytes(self._h, ptr(np.asarray(vol_shape, dtype=np.int32)),
+                                               int(tiles_per_batch or 0)))
+
+    def auto_tiles_per_batch(self, vol_shape, fraction=0.85):
+        """All tiles in one batch when the activation workspace fits `fraction` of the free device memory (plus what
+        torch's caching allocator already holds), otherwise the largest even split that does."""
+        key = tuple(int(v) for v in vol_shape)
+        if key in self._auto:   # decided once per shape (also keeps CUDA-graph capture free of memory queries)
+            return self._auto[key]
+        T = self.num_tiles(vol_shape)
+        free, _ = torch.cuda.mem_get_info(self.device)
+        budget = fraction * (free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device))
+        for parts in range(1, T + 1):
+            nb = -(-T // parts)
+            if self.workspace_bytes(vol_shape, nb) <= budget:
+                self._auto[key] = nb
+                return nb
+        raise OaiErrorNoMemory(f"not even one tile's activations fit the free device memory ({free} bytes)")
+
+    def forward(self, vol, out_mode=0, tiles_per_batch=0, out=None, workspace=None):
+        """vol: float32 [D,H,W] cuda -> float32 [ncls, D, H, W] (0 probabilities, 1 masks, 2 logits)."""
+        assert vol.dtype == torch.float32 and vol.is_contiguous() and vol.is_cuda
+        dims = np.asarray(vol.shape, dtype=np.int32)
+        if out is None:
+            out = torch.empty((self.n_classes,) + tuple(vol.shape), dtype=torch.float32, device=vol.device)
+        need = self.workspace_bytes(vol.shape, tiles_per_batch)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=vol.device)
+        check(lib.oai_seg_forward(self._h, ptr(vol), ptr(dims), ptr(out), int(out_mode), int(tiles_per_batch or 0),
+                                  ptr(workspace), c_size(workspace.numel()), stream_ptr()), "seg_forward")
+        return out
+
+
+def conv_overflow_count(reset=True):
+    """fp16 saturation guard of the conv epilogue (synchronises the current stream)."""
+    n = c_ll(0)
+    check(lib.oai_conv_overflow_count(ctypes.byref(n), int(reset), stream_ptr()), "conv_overflow_count")
+    return int(n.value)
+
+
+class OaiErrorNoMemory(RuntimeError):
+    pass
+
+
 # ------------------------------------------------------------------------------------------------ segmentation misc
 def make_geom(tile_zyx, effective_zyx, overlap_zyx, grid_zyx):
     """geom[12] = tile, effective, overlap, grid (all z,y,x) as the C ABI expects."""
     return np.asarray(list(tile_zyx) + list(effective_zyx) + list(overlap_zyx) + list(grid_zyx), dtype=np.int32)
 
 
-def seg_stem(vol, geom, tile0, ntiles, w27c, bias, ab_format=0):
-    """vol: float32 [D,H,W] cuda.  Returns act16 [ntiles, td, th, tw, c0]."""
+def seg_stem(vol, geom, tile0, ntiles, w27c, bias, ab_format=0, out_split=False):
+    """vol: float32 [D,H,W] cuda.  Returns act16 [ntiles, td, th, tw, c0] ([.., 2*c0] = [hi | lo] when out_split)."""
     assert vol.dtype == torch.float32 and vol.is_contiguous()
     dims = np.asarray(vol.shape, dtype=np.int32)
     c0 = w27c.shape[1]
     td, th, tw = (int(v) for v in geom[:3])
-    out = torch.empty((ntiles, td, th, tw, c0), dtype=_DT16[ab_format], device=vol.device)
-    check(lib.oai_seg_stem(ptr(vol), ptr(dims), ptr(geom), tile0, ntiles, ptr(w27c), ptr(bias), c0, ptr(out),
-                           ab_format, stream_ptr()), "seg_stem")
+    out = torch.empty((ntiles, td, th, tw, c0 * (2 if out_split else 1)), dtype=_DT16[ab_format], device=vol.device)
+    check(lib.oai_seg_stem_ex(ptr(vol), ptr(dims), ptr(geom), tile0, ntiles, ptr(w27c), ptr(bias), c0, ptr(out),
+                              ab_format, int(out_split), stream_ptr()), "seg_stem")
     return out
 
 
-def maxpool2(x, ab_format=0):
-    N, D, H, W, C = x.shape
-    out = torch.empty((N, D // 2, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
-    check(lib.oai_maxpool3d_2(ptr(x), ptr(out), N, D, H, W, C, ab_format, stream_ptr()), "maxpool3d_2")
+def maxpool2(x, ab_format=0, in_split=False, out_split=False):
+    """x: act16 [N,D,H,W,C] ([.., 2C] = [hi | lo] when in_split)."""
+    N, D, H, W, CP = x.shape
+    C = CP // 2 if in_split else CP
+    out = torch.empty((N, D // 2, H // 2, W // 2, C * (2 if out_split else 1)), dtype=x.dtype, device=x.device)
+    check(lib.oai_maxpool3d_2_ex(ptr(x), ptr(out), N, D, H, W, C, int(in_split), int(out_split), ab_format,
+                                 stream_ptr()), "maxpool3d_2")
+    return out
+
+
+def split16(x, ab_format=0):
+    """float32 [..., C] -> act16 [..., 2C] = [hi | lo] (hi = rn16(x), lo = rn16(x - hi)): the split-tensor layout."""
+    hi = x.to(_DT16[ab_format])
+    lo = (x - hi.float()).to(_DT16[ab_format])
+    return torch.cat((hi, lo), dim=-1).contiguous()
+
+
+def conv_plan_ex(D, H, W, c0, c1, cout, pointwise=0, terms=1, flags=0):
+    plan = (c_int * 10)()
+    check(lib.oai_conv3d_igemm_plan_ex(D, H, W, c0, c1, cout, int(pointwise), int(terms), flags, plan), "conv plan")
+    keys = ("mode", "kd_per_block", "R", "nhalf", "cout_per_half", "nblk", "wblock_bytes", "nchunks", "row_bytes",
+            "packed_16B")
+    return dict(zip(keys, list(plan)))
+
+
+def pack_conv_weights_ex(w, c0, c1, D, H, W, pointwise=0, terms=1, ab_format=0, flags=0, device="cuda"):
+    """w: float32 conv orientation [cout, c0+c1, taps...] (27 taps, none, or 2x2x2 for pointwise 0 / 1 / 2)."""
+    w = np.ascontiguousarray(w.detach().cpu().numpy() if hasattr(w, "detach") else w, dtype=np.float32)
+    cout = w.shape[0]
+    assert w.shape[1] == c0 + c1
+    nbytes = conv_plan_ex(D, H, W, c0, c1, cout, pointwise, terms, flags)["packed_16B"] * 16
+    dst = np.zeros(nbytes, dtype=np.uint8)
+    check(lib.oai_pack_conv_weights_ex(ptr(w), cout, c0, c1, D, H, W, int(pointwise), int(terms), ab_format, flags,
+                                       ptr(dst), c_size(nbytes)), "pack weights")
+    return dst if device is None else torch.from_numpy(dst).to(device)
+
+
+def conv3d_igemm_ex(src0, src1, wpack, bias, cout, c0, c1=0, pointwise=0, relu=True, ab_format=0, terms=1,
+                    in_split=False, out_split=False, region=None, flags=0):
+    """Split-precision form of conv3d_igemm: src* are [NT,D,H,W,C] (or [.., 2C] = [hi | lo] when in_split)."""
+    NT, D, H, W, _ = src0.shape
+    assert src0.is_contiguous() and (src1 is None or src1.is_contiguous())
+    up = 2 if pointwise == 2 else 1
+    out = torch.empty((NT, up * D, up * H, up * W, cout * (2 if out_split else 1)), dtype=_DT16[ab_format],
+                      device=src0.device)
+    reg = None if region is None else np.asarray(region, dtype=np.int32)
+    check(lib.oai_conv3d_igemm_ex(ptr(src0), c0, ptr(src1), c1, int(in_split), NT, D, H, W, ptr(wpack),
+                                  c_size(wpack.numel()), ptr(bias), cout, int(pointwise), int(relu), ab_format,
+                                  int(terms), ptr(out), int(out_split), flags, ptr(reg), stream_ptr()),
+          "conv3d_igemm_ex")
     return out
 
 

@@ -60,31 +60,19 @@ class Segmenter3DInPatchClassWise(Segmenter3DInPatch):
     def __init__(self, mode=None, config=None):
         super().__init__(mode, config)
 
-    def segment_device(self, volume, if_output_prob_map=False, tiles_per_batch=None):
+    def segment_device(self, volume, if_output_prob_map=False, tiles_per_batch=None, out=None):
         """volume: float32 [D,H,W] tensor already on the device.  Returns float32 [n_classes, D, H, W] on the device
-        (class 0 = FC, class 1 = TC), i.e. segmenter.py:105-129 without the host round trips."""
+        (class 0 = FC, class 1 = TC), i.e. segmenter.py:105-129 without the host round trips: one oai_seg_forward."""
         if not self.ready:
             self.pred_setup()
-        part = self.partition.plan(volume.shape)
-        geom = part.geom()
-        model = self.model
-        P = model.prepare(part.tile_size)
-        fmt = model._fmt()
-        ncls = model.n_classes
-        out = torch.empty((ncls,) + tuple(volume.shape), dtype=torch.float32, device=volume.device)
-        T = part.num_tiles
+        part = self.partition.plan(volume.shape)   # validates the geometry exactly like the reference's Partition
+        handle = self.model.seg_handle(self.partition.tile_size[::-1], self.config["overlap_size"])
         # the reference batches config['batch_size'] tiles per forward (results do not depend on it: BN is in eval
-        # mode); with 180 GB of HBM the whole tile set is one batch unless the caller bounds it
-        nb = T if tiles_per_batch is None else max(1, min(T, int(tiles_per_batch)))
-        ov = self.config["overlap_size"]  # x, y, z; assemble indexes crop_size[2], [0], [1] for z, y, x (:511)
-        crop_zyx = (ov[2], ov[0], ov[1])
-        for t0 in range(0, T, nb):
-            n = min(nb, T - t0)
-            e0 = ops.seg_stem(volume, geom, t0, n, P["ec0"]["w"], P["ec0"]["b"], fmt)
-            d2 = model.forward_features(P, e0, part.overlap_size)
-            model.head(P, d2, out, geom, t0, crop_zyx, 0 if if_output_prob_map else 1)
-            del d2
-        return out
+        # mode); here the whole tile set is one batch unless the workspace would not fit the free device memory
+        if tiles_per_batch is None:
+            tiles_per_batch = handle.auto_tiles_per_batch(volume.shape)
+        return handle.forward(volume, out_mode=0 if if_output_prob_map else 1, tiles_per_batch=tiles_per_batch,
+                              out=out)
 
     def segment(self, image, if_output_prob_map=False, if_output_itk=True):
         if not self.ready:
@@ -93,6 +81,9 @@ class Segmenter3DInPatchClassWise(Segmenter3DInPatch):
         vol = torch.from_numpy(arr).to(self.device, non_blocking=True)
         out = self.segment_device(vol, if_output_prob_map, self.config.get("tiles_per_batch"))
         host = out.cpu().numpy().astype(np.float64)  # the reference assembles into float64 (np.zeros default, :493)
+        if self.model._fmt() == 0 and ops.conv_overflow_count(reset=True):
+            raise FloatingPointError("segmentation activations left the fp16 range (|x| > 65504) with this checkpoint; "
+                                     "set model.precision = 'bf16' (UNet.precision / OAI_B200_SEG_PRECISION)")
         fc, tc = host[0], host[1]
         if if_output_itk:
             return itk_compat.image_from_array(fc, like=image), itk_compat.image_from_array(tc, like=image)

@@ -54,18 +54,34 @@ def _box(src, n, dp, ch, cw, cc, bh, bw, elems=64):
     return out.reshape(bh * bw, elems)
 
 
-def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", region=None):
-    """x0/x1: [NT,D,H,W,C] float16 arrays (x1 may be None); wpack: uint8 array; returns float32 [NT,D,H,W,cout]."""
+def build_chunks(c0, c1, terms):
+    """(source, first channel) of every K chunk, in the order api_conv.cu::build_chunks lists them."""
+    chunks = []
+    for src, c in ((0, c0), (1, c1)):
+        if c == 0:
+            continue
+        wide = 2 * c if terms >= 2 else c
+        chunks += [(src, j * 64) for j in range((wide + 63) // 64)]
+        if terms == 3:
+            chunks += [(src, j * 64) for j in range((c + 63) // 64)]
+    return chunks
+
+
+def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", region=None, terms=1, split=False):
+    """x0/x1: [NT,D,H,W,C] float16 arrays (x1 may be None; [.., 2C] = [hi | lo] planes when split); wpack: uint8 array;
+    returns float32 [NT,D,H,W,cout]."""
     f16 = np.float16
     NT, D, H, W, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[-1]
+    if split:
+        c0, c1 = c0 // 2, c1 // 2
+    chunks = build_chunks(c0, c1, terms)
     mode, kpb, R, nhalf, cph, nblk, wbytes = (plan[k] for k in ("mode", "kd_per_block", "R", "nhalf",
                                                                   "cout_per_half", "nblk", "wblock_bytes"))
     TW = min(W, 128)
     TH = 128 // TW
     elems = plan.get("row_bytes", 128) // 2
     rb = elems * 2
-    nchunk0 = (c0 + 63) // 64
     xs = (x0.view(np.uint16), None if x1 is None else x1.view(np.uint16))
     w16 = np.frombuffer(wpack.tobytes(), dtype=np.uint16)
     out = np.zeros((NT, D, H, W, cout), dtype=np.float32)
@@ -92,8 +108,7 @@ def emulate(x0, x1, wpack, bias, plan, cout, relu=True, k16_steps=4, fp="f16", r
                             else:
                                 c, kh, kw0, kdlo, nkd = b, 1, 1, 1, 1
                             blk = w16[((nh * nblk + b) * wbytes) // 2:((nh * nblk + b + 1) * wbytes) // 2]
-                            src = xs[0] if c < nchunk0 else xs[1]
-                            cc = (c if c < nchunk0 else c - nchunk0) * 64
+                            src, cc = xs[chunks[c][0]], chunks[c][1]
                             kdhi = kdlo + nkd - 1
                             dlo, dhi = max(0, d0 + kdlo - 1), min(D - 1, d0 + rv - 1 + kdhi - 1)
                             if mode == MODE_ROW_SHARED:

@@ -93,3 +93,71 @@ def test_weight_rounding_error_feedback_cancels_per_filter():
     rn = (w.half().float().numpy().astype(np.float64) - w.numpy()).reshape(cout, cin, 27)
     assert np.abs(err).max() < 2 * np.abs(rn).max() + 1e-9          # each weight still within ~1 ulp
     assert per_filter.mean() < 0.25 * np.abs(rn.sum(-1)).mean()     # but the per-filter sum cancels
+
+
+def _split16(x):
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    return hi, lo
+
+
+@pytest.mark.parametrize("args", [
+    # NT, D, H, W, c0, c1, cout, terms
+    (1, 4, 2, 128, 64, 0, 64, 2),      # row-shared, split activations (K = [hi | lo] x [w | w])
+    (1, 4, 2, 128, 32, 0, 64, 2),      # 32-channel split source: ONE 128-byte chunk holds hi and lo
+    (1, 2, 1, 128, 128, 64, 64, 2),    # decoder layer with a skip source (dc2's shape), both split
+    (1, 4, 4, 64, 64, 0, 128, 3),      # per-tap, three terms: + a_hi x w_lo
+    (1, 4, 2, 128, 32, 0, 64, 3),      # 32-channel source, three terms (second part reads [hi | lo] x [w_lo | 0])
+    (1, 2, 1, 128, 64, 64, 64, 3),     # two sources, three terms
+])
+def test_split_precision_terms_match_fp32_conv(args):
+    """terms 2 / 3 (api_conv.cu::build_chunks + the packer's weight images) through the kernel's software model: the
+    K-concatenated products reproduce an fp32 convolution of the un-rounded activations far below fp16 rounding."""
+    NT, D, H, W, c0, c1, cout, terms = args
+    g = torch.Generator().manual_seed(7)
+    x0 = torch.randn(NT, D, H, W, c0, generator=g)
+    x1 = torch.randn(NT, D, H, W, c1, generator=g) if c1 else None
+    cin = c0 + c1
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    if terms == 2:
+        w = w.half().float()   # two terms keep 16-bit weights: make them exactly representable for this check
+    bias = torch.randn(cout, generator=g)
+    plan = ops.conv_plan_ex(D, H, W, c0, c1, cout, 0, terms)
+    assert plan["nchunks"] == len(__import__("conv_emulator").build_chunks(c0, c1, terms))
+    wpack = ops.pack_conv_weights_ex(w, c0, c1, D, H, W, 0, terms, device=None)
+    s0 = torch.cat(_split16(x0), -1).numpy()
+    s1 = None if x1 is None else torch.cat(_split16(x1), -1).numpy()
+    got = emulate(s0, s1, wpack, bias.numpy(), plan, cout, True, 4, terms=terms, split=True)
+    x = x0 if x1 is None else torch.cat((x0, x1), -1)
+    ref = F.relu(F.conv3d(x.double().permute(0, 4, 1, 2, 3), w.double(), bias.double(), padding=1))
+    ref = ref.permute(0, 2, 3, 4, 1).numpy()
+    err = np.abs(got - ref).max()
+    # plain fp16 operands would land near 1e-3 here; hi+lo operands reach fp32 accumulation noise
+    assert err < 2e-5, (err, plan)
+
+
+def test_single_term_layer_reads_only_the_hi_plane_of_a_split_tensor():
+    NT, D, H, W, c0, cout = 1, 4, 2, 128, 64, 64
+    g = torch.Generator().manual_seed(8)
+    x0 = torch.randn(NT, D, H, W, c0, generator=g)
+    w = (torch.randn(cout, c0, 3, 3, 3, generator=g) / (27 * c0) ** 0.5).half().float()
+    bias = torch.randn(cout, generator=g)
+    plan = ops.conv_plan(D, H, W, c0, 0, cout)
+    wpack = ops.pack_conv_weights(w, c0, 0, D, H, W, False, 0, 0, device="cpu").numpy()
+    hi, lo = _split16(x0)
+    got = emulate(torch.cat((hi, lo), -1).numpy(), None, wpack, bias.numpy(), plan, cout, True, 4, terms=1, split=True)
+    ref = emulate(hi.numpy(), None, wpack, bias.numpy(), plan, cout, True, 4)
+    assert np.array_equal(got, ref)
+
+
+def test_up2_weights_pack_with_terms():
+    """ConvTranspose3d(k2,s2) weight images: size follows nchunks x terms and the one-term image is unchanged."""
+    D, H, W, cin, cout = 4, 16, 16, 128, 128
+    g = torch.Generator().manual_seed(2)
+    w = torch.randn(cout, cin, 2, 2, 2, generator=g) * 0.05
+    one = ops.pack_conv_weights_ex(w, cin, 0, D, H, W, 2, 1, device=None)
+    old = ops.pack_convt2_weights(w, D, H, W, 0, device="cpu").numpy()
+    assert np.array_equal(one, old)
+    two = ops.pack_conv_weights_ex(w, cin, 0, D, H, W, 2, 2, device=None)
+    three = ops.pack_conv_weights_ex(w, cin, 0, D, H, W, 2, 3, device=None)
+    assert two.size == 2 * one.size and three.size == 3 * one.size

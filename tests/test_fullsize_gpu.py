@@ -51,7 +51,7 @@ def test_full_volume_segmentation_matches_oracle_on_sampled_tiles(tmp_path):
         worst = max(worst, float(np.abs(blk - ref_in)[keep].max()))
         dices.append(dice(blk[keep], ref_in[keep]))
     print(f"full volume: prob max-abs {worst:.2e}; Dice on sampled tiles {min(dices):.5f}")
-    assert worst <= 1e-2 and min(dices) >= 0.998
+    assert worst <= 1e-2 and min(dices) >= 0.999   # north-star bars, verbatim
     # batching must not change results (BN in eval mode): 160 tiles at once == 48 per batch
     out2 = seg.segment_device(torch.from_numpy(vol).cuda(), if_output_prob_map=True, tiles_per_batch=48)
     assert torch.equal(out, out2)
