@@ -55,8 +55,9 @@ class TallUNet2:
     def load_state_dict(self, sd, strict=True):
         tmpl = state_dict_template()
         missing = [k for k in tmpl if k not in sd]
-        if strict and missing:
-            raise RuntimeError(f"tallUNet2: missing keys {missing}")
+        unexpected = [k for k in sd if k not in tmpl and not k.endswith("num_batches_tracked")]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"tallUNet2: missing keys {missing}, unexpected keys {unexpected}")
         for k, shape in tmpl.items():
             if k in sd:
                 v = torch.as_tensor(sd[k]).detach().float().cpu()

@@ -9,20 +9,85 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..segmentation.utils import load_checkpoint
 from .networks import TallUNet2
 
-NET_PATHS = {"phi": "netPhi.netPhi.net.netPhi.net", "psi": "netPhi.netPhi.net.netPsi.net",
-             "xi": "netPhi.netPsi.net", "omega": "netPsi.net"}
+# Module tree of OAI_knees_gradICON_model().regis_net as SURVEY App. B.2 recalls it:
+#   TwoStep(TwoStep(Downsample(TwoStep(FFVF(phi), FFVF(psi))), FFVF(xi)), FFVF(omega))
+# The un-vendored package cannot be inspected offline, so this is only the DEFAULT (random-init) tree: loading a
+# checkpoint re-derives the tree from the checkpoint's own key paths (parse_tree), e.g. icon's
+# make_network(..., include_last_step=True) layout TwoStep(TwoStep(Down(TwoStep(Down(phi), psi)), xi), omega).
+DEFAULT_PATHS = ("netPhi.netPhi.net.netPhi.net", "netPhi.netPhi.net.netPsi.net", "netPhi.netPsi.net", "netPsi.net")
 INPUT_SHAPE = [1, 1, 80, 192, 192]
 WEIGHTS_ENV = "OAI_B200_GRADICON_WEIGHTS"
+_UNET_PARAMS = ("downConvs.", "upConvs.", "batchNorms.", "lastConv.")
+
+
+def split_checkpoint(sd):
+    """{unet path: {unet key: tensor}} from a regis_net state dict (keys with or without the 'regis_net.' prefix).
+    Every key must belong to a tallUNet2 somewhere in the tree; `identity_map` buffers (older icon versions saved
+    them) are the only thing skipped.  Anything else raises: a checkpoint this loader does not understand must not
+    "load" and leave random weights behind."""
+    out, unknown = {}, []
+    for k, v in sd.items():
+        key = k[len("regis_net."):] if k.startswith("regis_net.") else k
+        if key.endswith("identity_map"):
+            continue
+        cut = min((key.find(h) for h in _UNET_PARAMS if h in key), default=-1)
+        path = key[:cut].rstrip(".") if cut > 0 else ""
+        if cut <= 0 or not path or any(t not in ("netPhi", "netPsi", "net") for t in path.split(".")):
+            unknown.append(k)
+            continue
+        out.setdefault(path, {})[key[cut:]] = v
+    if unknown:
+        raise RuntimeError(f"GradICON checkpoint has {len(unknown)} key(s) outside any tallUNet2 of the registration "
+                           f"tree, e.g. {unknown[:3]}")
+    if not out:
+        raise RuntimeError("GradICON checkpoint holds no tallUNet2 weights")
+    return out
+
+
+def parse_tree(paths):
+    """Registration module tree from the UNets' key paths.  'netPhi' / 'netPsi' are the children of a
+    TwoStepRegistration; 'net' is FunctionFromVectorField.net when it ends a path and DownsampleRegistration.net
+    otherwise.  Returns nested tuples ("twostep", phi, psi) | ("down", child) | ("ffvf", path)."""
+    def build(prefix, rel):
+        if rel == [("net",)]:
+            return ("ffvf", ".".join(prefix + ("net",)))
+        firsts = {r[0] for r in rel if r}
+        if any(not r for r in rel) or not firsts:
+            raise RuntimeError(f"GradICON checkpoint: malformed module path under {'.'.join(prefix) or '<root>'}")
+        if firsts == {"net"}:
+            return ("down", build(prefix + ("net",), [r[1:] for r in rel]))
+        if firsts == {"netPhi", "netPsi"}:
+            return ("twostep", build(prefix + ("netPhi",), [r[1:] for r in rel if r[0] == "netPhi"]),
+                    build(prefix + ("netPsi",), [r[1:] for r in rel if r[0] == "netPsi"]))
+        raise RuntimeError(f"GradICON checkpoint: cannot interpret children {sorted(firsts)} under "
+                           f"{'.'.join(prefix) or '<root>'} (expected netPhi+netPsi, or net)")
+    return build((), [tuple(p.split(".")) for p in sorted(paths)])
+
+
+def tree_leaves(tree):
+    if tree[0] == "ffvf":
+        return [tree[1]]
+    return [p for child in tree[1:] for p in tree_leaves(child)]
+
+
+def describe_tree(tree):
+    if tree[0] == "ffvf":
+        return "FFVF"
+    if tree[0] == "down":
+        return f"Down({describe_tree(tree[1])})"
+    return f"TwoStep({describe_tree(tree[1])}, {describe_tree(tree[2])})"
 
 
 class GradICONModel:
     """Inference-side equivalent of the object OAI_knees_gradICON_model() returns: exposes .identity_map,
     .assign_identity_map, .to/.cuda/.eval, .regis_net state loading, __call__(A, B), .phi_AB / .phi_BA."""
 
-    def __init__(self):
-        self.nets = {k: TallUNet2() for k in NET_PATHS}
+    def __init__(self, paths=DEFAULT_PATHS):
+        self.tree = parse_tree(paths)
+        self.nets = {p: TallUNet2() for p in tree_leaves(self.tree)}
         self.device = torch.device("cpu")
         self.input_shape = list(INPUT_SHAPE)
         self._identity = None
@@ -57,23 +122,59 @@ class GradICONModel:
 
     def state_dict(self):
         sd = {}
-        for name, path in NET_PATHS.items():
-            sd.update(self.nets[name].state_dict(prefix=f"regis_net.{path}."))
+        for path, net in self.nets.items():
+            sd.update(net.state_dict(prefix=f"regis_net.{path}."))
         return sd
 
-    def load_state_dict(self, sd, strict=False):
-        """Accepts the reference checkpoint layout (keys of regis_net, with or without the 'regis_net.' prefix)."""
-        for name, path in NET_PATHS.items():
-            for pre in (path + ".", "regis_net." + path + "."):
-                sub = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
-                if sub:
-                    self.nets[name].load_state_dict(sub, strict=True)
-                    break
-            else:
-                if strict:
-                    raise RuntimeError(f"GradICON state dict has no weights for {path}")
+    def load_state_dict(self, sd, strict=True):
+        """Loads a regis_net checkpoint (keys with or without the 'regis_net.' prefix) and REBUILDS the module tree
+        from its key paths, so both the SURVEY tree and icon's two-level-downsample tree load.  Fails loudly: every
+        tensor in the file must be consumed by exactly one tallUNet2 and every tallUNet2 must be complete -- strict
+        is accepted for signature compatibility (icon calls regis_net.load_state_dict(..., strict=False)) but a
+        partial load is never silently accepted."""
+        groups = split_checkpoint(sd)
+        tree = parse_tree(groups.keys())
+        nets = {}
+        for path in tree_leaves(tree):
+            net = TallUNet2()
+            net.load_state_dict(groups[path], strict=True)   # raises on missing / unexpected / mis-shaped keys
+            nets[path] = net.to(self.device) if self.device.type == "cuda" else net
+        self.tree, self.nets = tree, nets
+        self.phi_AB_vectorfield = self.phi_BA_vectorfield = None
+        return self
 
     # -- inference
+    def _run(self, node, src, tgt, fields_out):
+        """Evaluate one node of the tree on the batched pair (src -> tgt), both [2,D,H,W].  Returns the displacement
+        fields of its leaves in APPLICATION order (first applied first): TwoStep(phi, psi) returns c -> phi(psi(c))."""
+        kind = node[0]
+        if kind == "ffvf":
+            u = self.nets[node[1]](src, tgt)
+            fields_out[node[1]] = u
+            return [u]
+        if kind == "down":   # DownsampleRegistration: avg_pool3d(2, ceil_mode=True) on both images
+            lo_src = ops.avgpool2_ceil(src)
+            return self._run(node[1], lo_src, ops.avgpool2_ceil(tgt), fields_out)
+        f_phi = self._run(node[1], src, tgt, fields_out)
+        warped = self._warp(src, f_phi)              # as_function(image_A)(phi(identity_map))
+        f_psi = self._run(node[2], warped, tgt, fields_out)
+        return f_psi + f_phi
+
+    @staticmethod
+    def _shortcut(fields, shape):
+        # FunctionFromVectorField adds its field without interpolation when handed the identity map of its own shape
+        return tuple(fields[0].shape[2:]) == tuple(shape)
+
+    def _warp(self, img, fields):
+        if len(fields) > 4:
+            raise NotImplementedError("registration trees with more than four cascaded fields")
+        shape = tuple(img.shape[1:])
+        out = torch.empty_like(img)
+        for k in range(img.shape[0]):
+            ops.compose(shape, [f[k] for f in fields], self._shortcut(fields, shape), img[k], want_phi=False,
+                        img_out=out[k])
+        return out
+
     def forward(self, image_A, image_B):
         """image_A/B: [1,1,D,H,W] (or [D,H,W]) float32 cuda at the network resolution.  Runs both directions
         (batched through each UNet) and stores phi_AB / phi_BA evaluated on the identity map."""
@@ -84,24 +185,11 @@ class GradICONModel:
             raise ValueError(f"images must be resized to the network shape {self.input_shape[2:]}, got {list(full)}")
         src = torch.stack((A, B))                    # direction 0 registers A->B, direction 1 B->A
         tgt = torch.stack((B, A))
-        lo_src = ops.avgpool2_ceil(src)
-        lo_tgt = torch.stack((lo_src[1], lo_src[0]))
-        lo = tuple(lo_src.shape[1:])
-        n = self.nets
-        u_phi = n["phi"](lo_src, lo_tgt)
-        warped = torch.empty_like(lo_src)
-        for k in range(2):
-            ops.compose(lo, [u_phi[k]], False, lo_src[k], want_phi=False, img_out=warped[k])
-        u_psi = n["psi"](warped, lo_tgt)
-        warped = torch.empty_like(src)
-        for k in range(2):
-            ops.compose(full, [u_psi[k], u_phi[k]], False, src[k], want_phi=False, img_out=warped[k])
-        u_xi = n["xi"](warped, tgt)
-        for k in range(2):
-            ops.compose(full, [u_xi[k], u_psi[k], u_phi[k]], False, src[k], want_phi=False, img_out=warped[k])
-        u_omega = n["omega"](warped, tgt)
-        maps = [ops.compose(full, [u_omega[k], u_xi[k], u_psi[k], u_phi[k]], True)[0] for k in range(2)]
-        self.displacements = dict(phi=u_phi, psi=u_psi, xi=u_xi, omega=u_omega)
+        self.displacements = {}
+        fields = self._run(self.tree, src, tgt, self.displacements)
+        if len(fields) > 4:
+            raise NotImplementedError("registration trees with more than four cascaded fields")
+        maps = [ops.compose(full, [f[k] for f in fields], self._shortcut(fields, full))[0] for k in range(2)]
         self.phi_AB_vectorfield, self.phi_BA_vectorfield = maps[0][None], maps[1][None]
         return self.phi_AB_vectorfield, self.phi_BA_vectorfield
 
@@ -132,7 +220,7 @@ def OAI_knees_gradICON_model(pretrained=True, weights_path=None):
             raise FileNotFoundError(
                 "pretrained GradICON knee weights not found: pass weights_path= or set $%s (no network access to the "
                 "release the reference downloads from)" % WEIGHTS_ENV)
-        net.load_state_dict(torch.load(path, map_location="cpu", weights_only=False), strict=False)
+        net.load_state_dict(load_checkpoint(path), strict=False)
     if torch.cuda.is_available():
         net.to("cuda")
     net.eval()

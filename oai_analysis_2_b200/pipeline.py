@@ -9,7 +9,7 @@ import torch
 
 from . import ops
 from .icon_registration import itk_wrapper
-from .transforms import CompositeTransform, Geometry
+from .transforms import CompositeTransform, Geometry, HostFieldTransform
 
 
 class KneePipeline:
@@ -69,8 +69,8 @@ class KneePipeline:
                 and (vertices is None or tuple(vertices.shape) == tuple(self._g_verts.shape)))
 
     def run_device_graph(self, vol, geom, vertices=None):
-        """Same contract as run_device; the returned tensors are the graph's static outputs (overwritten by the next
-        replay)."""
+        """Same contract as run_device; the returned tensors AND transforms alias the graph's static outputs: they are
+        overwritten by the next replay (clone what must outlive it; run() / run_stream() hand out owned copies)."""
         if not self._graph_matches(vol, geom, vertices):
             return self.run_device(vol, geom, vertices)
         self._g_vol.copy_(vol, non_blocking=True)
@@ -118,10 +118,14 @@ class KneePipeline:
         def result(b):
             rs["ev_d2h"][b].synchronize()
             h = rs["host"][b]
-            res = {"FC_atlas": h["warped"][0].numpy(), "TC_atlas": h["warped"][1].numpy(),
-                   "phi_AB": self._g_out["phi_AB"], "phi_BA": self._g_out["phi_BA"]}
+            res = {"FC_atlas": h["warped"][0].numpy(), "TC_atlas": h["warped"][1].numpy()}
             if return_fields:
                 res["phi_AB_field"], res["phi_BA_field"] = h["phi_AB"].numpy(), h["phi_BA"].numpy()
+                # this knee's own transforms: the graph's static displacement buffers already hold a later knee, so the
+                # transform objects are rebuilt around the (pinned) host copy of THIS knee's fields
+                g = self._g_out
+                res["phi_AB"] = HostFieldTransform(h["phi_AB"], g["phi_AB"].geom_A, g["phi_AB"].geom_B, self.device)
+                res["phi_BA"] = HostFieldTransform(h["phi_BA"], g["phi_BA"].geom_A, g["phi_BA"].geom_B, self.device)
             if "verts" in h:
                 res["vertices_atlas"] = h["verts"].numpy()
             res["d2h_bytes"] = sum(h[k].numel() * h[k].element_size() for k in keys)
@@ -191,7 +195,13 @@ class KneePipeline:
             v.copy_(r["vertices"], non_blocking=True)
             res["vertices_atlas"] = v.numpy()
         torch.cuda.current_stream().synchronize()
-        res["phi_AB"], res["phi_BA"] = r["phi_AB"], r["phi_BA"]
+        if getattr(self, "_graph", None) is not None and r is self._g_out:
+            # graph path: the static displacement buffers are overwritten by the next replay -- hand out transforms
+            # that own a copy of this knee's fields
+            res["phi_AB"] = CompositeTransform(r["phi_AB"].disp.clone(), r["phi_AB"].geom_A, r["phi_AB"].geom_B)
+            res["phi_BA"] = CompositeTransform(r["phi_BA"].disp.clone(), r["phi_BA"].geom_A, r["phi_BA"].geom_B)
+        else:
+            res["phi_AB"], res["phi_BA"] = r["phi_AB"], r["phi_BA"]
         res["d2h_bytes"] = sum(t.numel() * t.element_size() for (n, _, _), t in self._pinned.items()
                                if n in ("warped", "verts") or (return_fields and n.startswith("phi")))
         res["h2d_bytes"] = vol_h.numel() * 4 + (0 if verts is None else verts.numel() * 8)

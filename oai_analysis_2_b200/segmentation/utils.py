@@ -4,6 +4,20 @@ import os
 import torch
 
 
+def load_checkpoint(path):
+    """torch.load restricted to tensors, containers and numbers (weights_only=True): a checkpoint is data, not code.
+    numpy scalars (e.g. a best_score saved as np.float64) are allow-listed."""
+    import numpy as np
+    safe = []
+    core = getattr(np, "_core", None) or getattr(np, "core")
+    for name in ("scalar", "_reconstruct"):
+        if hasattr(core.multiarray, name):
+            safe.append(getattr(core.multiarray, name))
+    safe += [np.dtype, np.ndarray] + [type(np.dtype(t)) for t in ("float64", "float32", "int64", "int32", "bool")]
+    with torch.serialization.safe_globals(safe):
+        return torch.load(path, map_location="cpu", weights_only=True)
+
+
 def initialize_model(model, optimizer=None, ckpoint_path=None):
     """Load checkpoint['model_state_dict'] (strict) or fall back to model.weights_init() when ckpoint_path is falsy.
 
@@ -13,7 +27,7 @@ def initialize_model(model, optimizer=None, ckpoint_path=None):
         if not os.path.isfile(ckpoint_path):
             raise ValueError("=> no checkpoint found at '{}'".format(ckpoint_path))
         print("=> loading checkpoint '{}'".format(ckpoint_path))
-        checkpoint = torch.load(ckpoint_path, map_location="cpu", weights_only=False)
+        checkpoint = load_checkpoint(ckpoint_path)
         for key in ("best_score", "reg_best_score", "seg_best_score"):
             if key in checkpoint:
                 best_score = checkpoint[key]

@@ -62,17 +62,15 @@ class CompositeTransform:
         self.geom_A, self.geom_B = geom_A, geom_B
         self.to_network_space = resampling_transform(geom_A, self.net_xyz)
         self.from_network_space_inv = _invert(resampling_transform(geom_B, self.net_xyz))
-        self._host = None
 
     # ---- ITK-like accessors
     def GetNumberOfTransforms(self):
         return 3
 
     def displacement_field_array(self):
-        """float64 [D,H,W,3] like itk.array_from_image(tr.GetDisplacementField())."""
-        if self._host is None:
-            self._host = self.disp.cpu().numpy().astype(np.float64)
-        return self._host
+        """float64 [D,H,W,3] like itk.array_from_image(tr.GetDisplacementField()).  Read from the device every time:
+        the field buffer may be a CUDA graph's static output that a later replay rewrites."""
+        return self.disp.cpu().numpy().astype(np.float64)
 
     def transform_points(self, pts_xyz):
         """TransformPoint over an [n,3] array of physical points (float64).  Runs on the GPU."""
@@ -89,3 +87,33 @@ class CompositeTransform:
         a = _compose(self.from_network_space_inv, geom_out.index_to_physical_affine())
         b = _compose(geom_src.physical_to_index_affine(), self.to_network_space)
         return ops.warp_volume(src_dev, self.disp, a, b, tuple(int(v) for v in geom_out.size[::-1]), default_value)
+
+
+class HostFieldTransform(CompositeTransform):
+    """CompositeTransform whose displacement field lives in (pinned) host memory -- what KneePipeline.run_stream hands
+    out per knee.  It wraps THIS knee's field (never the CUDA graph's static buffer, which already holds a later knee)
+    and uploads it on first use by a GPU warp.  Like the result arrays of run_stream it is a view of a double-buffered
+    pinned slot: valid until the generator is advanced again; snapshot() returns a transform that owns its field."""
+
+    def __init__(self, field_host, geom_A, geom_B, device, copy=False):
+        f = field_host.numpy() if hasattr(field_host, "numpy") else np.asarray(field_host)
+        self._field = np.array(f, dtype=np.float32) if copy else f
+        self._device = torch.device(device)
+        self._dev = None
+        d, h, w = self._field.shape[:3]
+        self.net_xyz = np.array([w, h, d])
+        self.geom_A, self.geom_B = geom_A, geom_B
+        self.to_network_space = resampling_transform(geom_A, self.net_xyz)
+        self.from_network_space_inv = _invert(resampling_transform(geom_B, self.net_xyz))
+
+    @property
+    def disp(self):
+        if self._dev is None:
+            self._dev = torch.from_numpy(self._field).to(self._device)
+        return self._dev
+
+    def displacement_field_array(self):
+        return self._field.astype(np.float64)
+
+    def snapshot(self):
+        return HostFieldTransform(self._field, self.geom_A, self.geom_B, self._device, copy=True)

@@ -52,10 +52,18 @@ def make_unet2_state_dict(seed, last_w_std=0.02, last_b_std=0.05):
     return sd
 
 
-def make_gradicon_state_dict(seed, **kw):
+# icon's make_network(input_shape, include_last_step=True) layout (two nested DownsampleRegistration levels):
+#   TwoStep(TwoStep(Down(TwoStep(Down(phi), psi)), xi), omega)   -- quarter, half, full, full resolution
+NET_PATHS_TWO_LEVEL = {
+    "phi": "netPhi.netPhi.net.netPhi.net.net", "psi": "netPhi.netPhi.net.netPsi.net",
+    "xi": "netPhi.netPsi.net", "omega": "netPsi.net",
+}
+
+
+def make_gradicon_state_dict(seed, paths=None, **kw):
     """State dict with the key layout of OAI_knees_gradICON_model().regis_net (four tallUNet2)."""
     sd = {}
-    for i, (name, path) in enumerate(NET_PATHS.items()):
+    for i, (name, path) in enumerate((paths or NET_PATHS).items()):
         for k, v in make_unet2_state_dict(seed * 10 + i, **kw).items():
             sd[f"{path}.{k}"] = v
     return sd
@@ -128,6 +136,51 @@ def regis_net_forward(nets, A, B):
     hires = lambda c: low(t_xi(c))                                           # noqa: E731
     u_omega = unet2_forward(nets["omega"], sample(A, hires(id_full)), B)
     return dict(phi=u_phi, psi=u_psi, xi=u_xi, omega=u_omega)
+
+
+# ---- generic module tree (network_wrappers.py restated as closures, module for module) -------------------------
+_UNET_KEYS = ("downConvs.", "upConvs.", "batchNorms.", "lastConv.")
+
+
+def tree_from_state_dict(sd):
+    """(tree, {path: unet state dict}) from a regis_net state dict: 'netPhi'/'netPsi' are TwoStepRegistration children,
+    a trailing 'net' is FunctionFromVectorField.net, any other 'net' is DownsampleRegistration.net."""
+    groups = {}
+    for k, v in sd.items():
+        k = k[len("regis_net."):] if k.startswith("regis_net.") else k
+        cut = min(k.find(h) for h in _UNET_KEYS if h in k)
+        groups.setdefault(k[:cut - 1], {})[k[cut:]] = v
+
+    def build(prefix, rel):
+        if rel == [("net",)]:
+            return ("ffvf", ".".join(prefix + ("net",)))
+        if {r[0] for r in rel} == {"net"}:
+            return ("down", build(prefix + ("net",), [r[1:] for r in rel]))
+        return ("twostep", build(prefix + ("netPhi",), [r[1:] for r in rel if r[0] == "netPhi"]),
+                build(prefix + ("netPsi",), [r[1:] for r in rel if r[0] == "netPsi"]))
+    return build((), [tuple(p.split(".")) for p in sorted(groups)]), groups
+
+
+def tree_forward(node, nets, A, B):
+    """RegistrationModule.forward(A, B) of a tree node: returns the transform closure t(coords, is_identity_map)."""
+    if node[0] == "ffvf":            # FunctionFromVectorField
+        u = unet2_forward(nets[node[1]], A, B)
+        return lambda c, ident=False: c + u if (ident and c.shape == u.shape) else c + sample(u, c)
+    if node[0] == "down":            # DownsampleRegistration
+        return tree_forward(node[1], nets, F.avg_pool3d(A, 2, ceil_mode=True), F.avg_pool3d(B, 2, ceil_mode=True))
+    phi = tree_forward(node[1], nets, A, B)          # TwoStepRegistration
+    warped = sample(A, phi(identity_map(A.shape[2:], A.dtype), True))
+    psi = tree_forward(node[2], nets, warped, B)
+    return lambda c, ident=False: phi(psi(c, ident))
+
+
+def register_pair_maps_tree(sd, image_A, image_B, shape=INPUT_SHAPE):
+    """register_pair_maps for any module tree, driven by the state dict's key paths."""
+    tree, nets = tree_from_state_dict(sd)
+    A, B = resize_to_network(np.asarray(image_A), shape), resize_to_network(np.asarray(image_B), shape)
+    ident = identity_map(shape)
+    with torch.no_grad():
+        return tree_forward(tree, nets, A, B)(ident, True), tree_forward(tree, nets, B, A)(ident, True)
 
 
 def final_map(u, shape, dtype=torch.float32):

@@ -206,6 +206,34 @@ def test_register_pair_maps_match_oracle(shape, native):
     assert e_ab < 2e-3 and e_ba < 2e-3         # 2e-3 voxel ~ 7e-4 mm at 0.36 mm spacing
 
 
+def test_two_level_downsample_tree_registers_like_its_oracle():
+    """A checkpoint in icon's make_network(include_last_step=True) layout -- TwoStep(TwoStep(Down(TwoStep(Down(phi),
+    psi)), xi), omega): quarter, half, full, full resolution -- loads by its key paths and registers identically to
+    the oracle built from the same state dict; it differs from the SURVEY tree run on the same weights."""
+    _cuda()
+    from oai_analysis_2_b200.icon_registration import itk_wrapper, pretrained_models
+    from oracle import reg_oracle
+    shape, native = (40, 48, 44), (80, 96, 88)
+    sd = reg_oracle.make_gradicon_state_dict(4321, reg_oracle.NET_PATHS_TWO_LEVEL)
+    model = pretrained_models.OAI_knees_gradICON_model(pretrained=False)
+    model.assign_identity_map([1, 1, *shape])
+    model.load_state_dict(sd)
+    assert pretrained_models.describe_tree(model.tree) == "TwoStep(TwoStep(Down(TwoStep(Down(FFVF), FFVF)), FFVF), FFVF)"
+    model.to("cuda")
+    A = (_smooth(native, 40) * 0.3 + 0.5).clamp(0, 1).numpy()
+    B = (_smooth(native, 41) * 0.3 + 0.5).clamp(0, 1).numpy()
+    phi_AB, phi_BA = itk_wrapper.register_pair_device(model, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
+    ref_AB, ref_BA = reg_oracle.register_pair_maps_tree(sd, A, B, shape)
+    vox = torch.tensor([s - 1 for s in shape], dtype=torch.float32).view(1, 3, 1, 1, 1)
+    e_ab = ((phi_AB.cpu() - ref_AB) * vox).abs().max().item()
+    e_ba = ((phi_BA.cpu() - ref_BA) * vox).abs().max().item()
+    flat = reg_oracle.register_pair_maps(reg_oracle.make_gradicon_state_dict(4321), A, B, shape)[0]
+    print(f"two-level tree: map error AB {e_ab:.2e} BA {e_ba:.2e} vox; differs from the one-level tree by "
+          f"{((flat - ref_AB) * vox).abs().max().item():.2f} vox")
+    assert e_ab < 2e-3 and e_ba < 2e-3
+    assert ((flat - ref_AB) * vox).abs().max().item() > 0.05
+
+
 def _geoms():
     from oracle.warp_oracle import Geometry
     th = 0.05
