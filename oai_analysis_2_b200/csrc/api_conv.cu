@@ -333,9 +333,9 @@ int conv_run(const ConvSpec& s, const ConvLaunch& a, cudaStream_t st) {
   OAI_REQUIRE((c1 == 0) == (a.src1 == nullptr), "conv: src1/c1 mismatch");
   const size_t need = plan_wpack_bytes(pl);
   OAI_REQUIRE(a.wpack_bytes == need, "conv: packed weights are %zu bytes, geometry needs %zu", a.wpack_bytes, need);
-  OAI_REQUIRE(a.obase % 8 == 0 && a.osN % 8 == 0 && a.osD % 8 == 0 && a.osH % 8 == 0 && a.osW % 8 == 0 &&
-                  a.out_lo_off % 8 == 0,
-              "conv: output strides must keep 16-byte alignment");
+  OAI_REQUIRE(a.obase % 16 == 0 && a.osN % 16 == 0 && a.osD % 16 == 0 && a.osH % 16 == 0 && a.osW % 16 == 0 &&
+                  a.out_lo_off % 16 == 0 && (head || (reinterpret_cast<uintptr_t>(a.out) & 31) == 0),
+              "conv: output base and strides must keep 32-byte alignment");
   OAI_REQUIRE(!(head && a.out_split), "conv head: the fused head writes class maps, not a split activation");
 
   ConvIgemmParams p;

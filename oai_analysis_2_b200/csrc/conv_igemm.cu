@@ -109,6 +109,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// one 32-byte global store (sm_100: STG.256); p must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // rn16(x - hi) for the pair whose rounded hi halves are already packed in `hi`
 __device__ __forceinline__ uint32_t pack2_residual(float a, float b, uint32_t hi, int fmt) {
   if (fmt == 0) {
@@ -130,6 +137,178 @@ __device__ __forceinline__ void head_dot(const uint32_t (&v)[32], const float* _
     for (int k = 0; k < NC; ++k)
       if (k < ncls) acc[k] = fmaf(f, w[k * 64 + i], acc[k]);
   }
+}
+
+
+// The MMA-issuing warp's whole loop.  NKW / K16N > 0: compile-time (kw taps per A stage, K=16 steps per chunk) fast
+// path; <0, 0>: the general path (debug / A-B flags, uncommon shapes) with run-time trip counts and descriptors rebuilt
+// per MMA.  The whole warp walks the (warp-uniform) schedule so the compiler keeps the descriptor arithmetic in uniform
+// registers; one lane, elected once, issues every tcgen05.mma / tcgen05.commit.
+template <int NKW, int K16N>
+__device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint32_t tmem_base, uint8_t* abuf,
+                                           uint8_t* wbuf, const uint32_t wstride, uint64_t* full_a, uint64_t* empty_a,
+                                           uint64_t* full_w, uint64_t* empty_w, uint64_t* acc_full,
+                                           uint64_t* acc_empty) {
+  constexpr bool kFast = NKW > 0;
+  const int mode = p.mode, R_acc = p.R, cout = p.cout, nblk = p.nblk, nst = p.n_astage, nwb = p.n_wbuf, Dm1 = p.D - 1,
+            kpb = p.kd_per_block;
+  const int nkw = kFast ? NKW : ((mode == kModeRowShared) ? 3 : 1);
+  const int k16n = kFast ? K16N : p.k16_steps;
+  const uint32_t rowb = static_cast<uint32_t>(p.row_bytes), sbo = 8u * rowb, lay = rowb == 128u ? 2u : 4u;
+  const uint32_t cout128 = static_cast<uint32_t>(cout) * rowb;    // bytes of one tap's weight rows
+  const uint32_t tap16 = cout128 >> 4;                             // ... in descriptor units
+  const uint32_t kw_step = rowb >> 4;                              // descriptor units per one-voxel row shift
+  const uint32_t desc_hi32 = (sbo >> 4) | (1u << 14) | (lay << 29);  // SBO, version = 1, swizzle mode
+  const uint32_t a_lo0 = ((smem_u32(abuf) & 0x3FFFF) >> 4) | (1u << 16), a_step = p.astage_stride >> 4;
+  const uint32_t w_lo0 = ((smem_u32(wbuf) & 0x3FFFF) >> 4) | (1u << 16), w_step = wstride >> 4;
+  const int per = max(1, 256 / cout);
+  const uint32_t idesc_1 = umma_idesc_f16(128, static_cast<uint32_t>(cout), p.ab_format);
+  const uint32_t idesc_step = static_cast<uint32_t>(cout >> 3) << 17;  // +1 tap in the N field
+  const bool up2 = mode == kModeUp2;
+  const bool leader = elect_one();
+  int stage = 0, wb = 0;
+  uint32_t aphase = 0, wphase = 0, use_bits = 0;  // use_bits: per-accumulator mbarrier phase (flips per use)
+  uint32_t a_lo = a_lo0;                          // descriptor low word of the current A stage
+  for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+    const UnitInfo ui = decode_unit(p, u);
+    const int d0 = ui.d0, ra = ui.ra, rd = ui.rd;
+    const uint32_t all_acc = (1u << ra) - 1u;
+    uint32_t touched = 0, signaled = 0;
+    int kd_it = 0;  // kd counter of the one-kd-per-block schedule (fastest block index there)
+    for (int b = 0; b < nblk; ++b) {
+      // taps stacked in this block and the input slices it walks (same arithmetic as decode_block, by counters)
+      int kdlo = 0, nkd = 3;
+      if (mode == kModePointwise || up2) { kdlo = 1; nkd = 1; }
+      else if (mode == kModePerTap && kpb == 1) { kdlo = kd_it; nkd = 1; kd_it = kd_it == 2 ? 0 : kd_it + 1; }
+      const int ns = up2 ? R_acc : nkd;
+      const int kdhi = kdlo + nkd - 1;
+      const int dlo = max(0, d0 + kdlo - 1);
+      const int dhi = min(Dm1, d0 + rd - 1 + kdhi - 1);
+      const bool last_blk = b == nblk - 1;
+      mbar_wait(&full_w[wb], wphase, 300 + wb);
+      const uint32_t w_lo = w_lo0 + static_cast<uint32_t>(wb) * w_step;
+      const uint32_t b_kw = static_cast<uint32_t>(ns) * tap16;
+      int a_first = up2 ? 0 : dlo - kdhi + 1 - d0;  // accumulator hit by the first stacked tap
+      for (int dp = dlo; dp <= dhi; ++dp, a_first += (up2 ? 0 : 1)) {
+        mbar_wait(&full_a[stage], aphase, 400 + stage);
+        tc_fence_after();
+        const int acc0 = max(a_first, 0);
+        const int ti_lo = acc0 - a_first;
+        const int nt = min(ns - 1, ra - 1 - a_first) - ti_lo + 1;
+        const uint32_t span = ((1u << nt) - 1u) << acc0;
+        const uint32_t fresh = span & ~touched;
+        if (kFast && fresh == 0) {
+          // steady state: every accumulator of the span already holds partial sums
+          for (int g0 = 0; g0 < nt; g0 += per) {
+            const int ng = min(per, nt - g0);
+            const uint32_t idesc = idesc_1 + static_cast<uint32_t>(ng - 1) * idesc_step;
+            const uint32_t d_addr = tmem_base + static_cast<uint32_t>((acc0 + g0) * cout);
+            const uint32_t b_lo = w_lo + static_cast<uint32_t>(ti_lo + g0) * tap16;
+            if (leader) {
+#pragma unroll
+              for (int kw = 0; kw < (kFast ? NKW : 1); ++kw)
+#pragma unroll
+                for (int k16 = 0; k16 < (kFast ? K16N : 1); ++k16)
+                  umma_f16_ss_lohi(d_addr, a_lo + kw * kw_step + k16 * 2, b_lo + kw * b_kw + k16 * 2, desc_hi32, idesc,
+                                   1u);
+            }
+          }
+        } else if (kFast) {
+          // accumulators seeing their first MMA of the unit: wait until the epilogue has drained their previous
+          // contents; their very first issue (kw = 0, k16 = 0) overwrites instead of accumulating
+          for (int a = acc0; a < acc0 + nt; ++a)
+            if ((fresh >> a) & 1u) mbar_wait(&acc_empty[a], ((use_bits >> a) & 1u) ^ 1u, 500 + a);
+          tc_fence_after();
+          for (int g0 = 0; g0 < nt; g0 += per) {
+            const int ng = min(per, nt - g0);
+            const uint32_t idesc = idesc_1 + static_cast<uint32_t>(ng - 1) * idesc_step;
+            const uint32_t d_addr = tmem_base + static_cast<uint32_t>((acc0 + g0) * cout);
+            const uint32_t b_lo = w_lo + static_cast<uint32_t>(ti_lo + g0) * tap16;
+            const uint32_t gfresh = (fresh >> (acc0 + g0)) & ((1u << ng) - 1u);
+            if (leader) {
+              if (gfresh) {
+                int j = 0;  // first issue of the group, split into runs of equal state
+                while (j < ng) {
+                  const uint32_t f = (gfresh >> j) & 1u;
+                  int len = 1;
+                  while (j + len < ng && ((gfresh >> (j + len)) & 1u) == f) ++len;
+                  umma_f16_ss_lohi(d_addr + static_cast<uint32_t>(j * cout), a_lo,
+                                   b_lo + static_cast<uint32_t>(j) * tap16, desc_hi32,
+                                   idesc_1 + static_cast<uint32_t>(len - 1) * idesc_step, f ? 0u : 1u);
+                  j += len;
+                }
+              }
+#pragma unroll
+              for (int kw = 0; kw < (kFast ? NKW : 1); ++kw)
+#pragma unroll
+                for (int k16 = 0; k16 < (kFast ? K16N : 1); ++k16)
+                  if (!(gfresh && kw == 0 && k16 == 0))
+                    umma_f16_ss_lohi(d_addr, a_lo + kw * kw_step + k16 * 2, b_lo + kw * b_kw + k16 * 2, desc_hi32,
+                                     idesc, 1u);
+            }
+          }
+          touched |= span;
+        } else {
+          // general path: one group per run of equal accumulator state, descriptors rebuilt per MMA
+          const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
+          const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
+          const int ti_hi = ti_lo + nt - 1;
+          for (int kw = 0; kw < nkw; ++kw) {
+            int ti = ti_lo;
+            while (ti <= ti_hi) {
+              const int a0 = a_first + ti;
+              const uint32_t f = (touched >> a0) & 1u;
+              int len = 1;
+              while (ti + len <= ti_hi && ((touched >> (a0 + len)) & 1u) == f && (len + 1) * cout <= 256) ++len;
+              if (!f) {
+                for (int j = 0; j < len; ++j)
+                  mbar_wait(&acc_empty[a0 + j], ((use_bits >> (a0 + j)) & 1u) ^ 1u, 500 + a0 + j);
+                tc_fence_after();
+              }
+              const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * cout), p.ab_format);
+              const uint32_t a_addr = a_base + static_cast<uint32_t>(kw) * rowb;
+              const uint32_t b_addr = w_base + static_cast<uint32_t>(kw * ns + ti) * cout128;
+              const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
+              const uint32_t d_addr = tmem_base + static_cast<uint32_t>(a0 * cout);
+              if (leader) {
+                for (int k16 = 0; k16 < k16n; ++k16) {
+                  const uint64_t adesc = umma_desc_kmajor(a_addr + k16 * 32, sbo, boff, lay);
+                  const uint64_t bdesc = umma_desc_kmajor(b_addr + k16 * 32, sbo, 0, lay);
+                  umma_f16_ss(d_addr, adesc, bdesc, idesc, (f | (k16 > 0)) ? 1u : 0u);
+                }
+              }
+              touched |= ((1u << len) - 1u) << a0;
+              ti += len;
+            }
+          }
+        }
+        // release the A stage; the last block's last tap of an accumulator also publishes it to the epilogue
+        const bool publish = last_blk && a_first >= 0 && a_first < ra;
+        if (leader) {
+          umma_commit(&empty_a[stage]);
+          if (publish) umma_commit(&acc_full[a_first]);
+        }
+        if (publish) signaled |= 1u << a_first;
+        a_lo += a_step;
+        if (++stage == nst) {
+          stage = 0;
+          aphase ^= 1u;
+          a_lo = a_lo0;
+        }
+      }
+      if (leader) umma_commit(&empty_w[wb]);
+      if (++wb == nwb) {
+        wb = 0;
+        wphase ^= 1u;
+      }
+    }
+    if (leader) {
+      for (int a = 0; a < ra; ++a)
+        if (!((signaled >> a) & 1u)) umma_commit(&acc_full[a]);
+    }
+    use_bits ^= all_acc;
+  }
+  __syncwarp();
 }
 
 }  // namespace
@@ -237,160 +416,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------ MMA issuer
-    // The whole warp walks the (warp-uniform) schedule so the compiler keeps everything in uniform registers; one
-    // elected lane issues tcgen05.mma / tcgen05.commit.  This thread is the critical resource of the kernel: the
-    // tensor pipe retires an N=192 MMA every 96 clocks, so the per-stage bookkeeping below is kept to a handful of
-    // integer ops (block indices are counters, descriptors are "stage base + constant", no divisions, no re-reads
-    // of kernel parameters).
-    const int mode = p.mode, R_acc = p.R, cout = p.cout, nblk = p.nblk, k16n = p.k16_steps, nst = p.n_astage,
-              nwb = p.n_wbuf, Dm1 = p.D - 1, kpb = p.kd_per_block;
+    // The single thread that feeds the tensor pipe is the critical resource of the kernel: an ncu source-level profile
+    // (profiles/r02_ncu_ec1_issuer.txt) showed the previous loop executing ~245 warp instructions per A stage -- about
+    // 1300 clocks for a lone warp -- against 6 x 96 clocks of MMAs for a 32-channel stage.  The loop body is therefore
+    // specialised at compile time on (kw taps per stage, K=16 steps per chunk) and kept to descriptor adds.
     const bool general = p.base_off_mode || p.no_fast_path;
-    const uint32_t rowb = static_cast<uint32_t>(p.row_bytes), sbo = 8u * rowb, lay = rowb == 128u ? 2u : 4u;
-    const uint32_t cout128 = static_cast<uint32_t>(cout) * rowb;    // bytes of one tap's weight rows
-    const uint32_t tap16 = cout128 >> 4;                             // ... in descriptor units
-    const uint32_t kw_step = rowb >> 4;                              // descriptor units per one-voxel row shift
-    const uint32_t desc_hi32 = (sbo >> 4) | (1u << 14) | (lay << 29);  // SBO, version = 1, swizzle mode
-    const uint32_t a_lo0 = ((smem_u32(abuf) & 0x3FFFF) >> 4) | (1u << 16), a_step = p.astage_stride >> 4;
-    const uint32_t w_lo0 = ((smem_u32(wbuf) & 0x3FFFF) >> 4) | (1u << 16), w_step = wstride >> 4;
-    const int per = max(1, 256 / cout);
-    const uint32_t idesc_1 = umma_idesc_f16(128, static_cast<uint32_t>(cout), p.ab_format);
-    const uint32_t idesc_step = static_cast<uint32_t>(cout >> 3) << 17;  // +1 tap in the N field
-    int stage = 0, wb = 0;
-    uint32_t aphase = 0, wphase = 0, use_bits = 0;  // use_bits: per-accumulator mbarrier phase (flips per use)
-    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-      const UnitInfo ui = decode_unit(p, u);
-      const int d0 = ui.d0, ra = ui.ra, rd = ui.rd;
-      uint32_t touched = 0, signaled = 0;
-      int kd_it = 0;  // kd counter of the one-kd-per-block schedule (fastest block index there)
-      for (int b = 0; b < nblk; ++b) {
-        // taps stacked in this block and the input slices it walks (same arithmetic as decode_block, by counters)
-        int kdlo = 0, nkd = 3;
-        if (mode == kModePointwise || mode == kModeUp2) { kdlo = 1; nkd = 1; }
-        else if (mode == kModePerTap && kpb == 1) { kdlo = kd_it; nkd = 1; kd_it = kd_it == 2 ? 0 : kd_it + 1; }
-        const int ns = (mode == kModeUp2) ? R_acc : nkd;
-        const int kdhi = kdlo + nkd - 1;
-        const int dlo = max(0, d0 + kdlo - 1);
-        const int dhi = min(Dm1, d0 + rd - 1 + kdhi - 1);
-        mbar_wait(&full_w[wb], wphase, 300 + wb);
-        const uint32_t w_lo = w_lo0 + static_cast<uint32_t>(wb) * w_step;
-        const uint32_t b_kw = static_cast<uint32_t>(ns) * tap16;
-        int a_first = (mode == kModeUp2) ? 0 : dlo - kdhi + 1 - d0;  // accumulator hit by the first stacked tap
-        for (int dp = dlo; dp <= dhi; ++dp, a_first += (mode == kModeUp2 ? 0 : 1)) {
-          mbar_wait(&full_a[stage], aphase, 400 + stage);
-          tc_fence_after();
-          const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step;
-          const int ti_lo = a_first < 0 ? -a_first : 0;
-          const int ti_hi = min(ns - 1, ra - 1 - a_first);
-          const int nt = ti_hi - ti_lo + 1;
-          const int acc0 = a_first + ti_lo;
-          const uint32_t span = ((1u << nt) - 1u) << acc0;
-          const uint32_t fresh = span & ~touched;
-          if (!general) {
-            if (fresh) {
-              // accumulators seeing their first MMA of the unit: wait until the epilogue has drained their previous
-              // contents; their very first issue (kw = 0, k16 = 0) overwrites instead of accumulating
-              for (int a = acc0; a < acc0 + nt; ++a)
-                if ((fresh >> a) & 1u) mbar_wait(&acc_empty[a], ((use_bits >> a) & 1u) ^ 1u, 500 + a);
-              tc_fence_after();
-            }
-            const bool leader = elect_one();
-            for (int g0 = 0; g0 < nt; g0 += per) {
-              const int ng = min(per, nt - g0);
-              const uint32_t idesc = idesc_1 + static_cast<uint32_t>(ng - 1) * idesc_step;
-              const uint32_t d_addr = tmem_base + static_cast<uint32_t>((acc0 + g0) * cout);
-              const uint32_t b_lo = w_lo + static_cast<uint32_t>(ti_lo + g0) * tap16;
-              const uint32_t gfresh = (fresh >> (acc0 + g0)) & ((1u << ng) - 1u);
-              if (leader) {
-                if (gfresh) {
-                  int j = 0;  // first issue of the group, split into runs of equal state
-                  while (j < ng) {
-                    const uint32_t f = (gfresh >> j) & 1u;
-                    int len = 1;
-                    while (j + len < ng && ((gfresh >> (j + len)) & 1u) == f) ++len;
-                    umma_f16_ss_lohi(d_addr + static_cast<uint32_t>(j * cout), a_lo,
-                                     b_lo + static_cast<uint32_t>(j) * tap16, desc_hi32,
-                                     idesc_1 + static_cast<uint32_t>(len - 1) * idesc_step, f ? 0u : 1u);
-                    j += len;
-                  }
-                }
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                  if (kw < nkw) {
-#pragma unroll
-                    for (int k16 = 0; k16 < 4; ++k16) {
-                      if (k16 < k16n && !(gfresh && kw == 0 && k16 == 0))
-                        umma_f16_ss_lohi(d_addr, a_lo + kw * kw_step + k16 * 2, b_lo + kw * b_kw + k16 * 2,
-                                         desc_hi32, idesc, 1u);
-                    }
-                  }
-                }
-              }
-            }
-            __syncwarp();
-            touched |= span;
-          } else {
-            // debug / A-B path: one group per run of equal accumulator state, descriptors rebuilt per MMA
-            const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
-            const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
-            for (int kw = 0; kw < nkw; ++kw) {
-              int ti = ti_lo;
-              while (ti <= ti_hi) {
-                const int a0 = a_first + ti;
-                const uint32_t f = (touched >> a0) & 1u;
-                int len = 1;
-                while (ti + len <= ti_hi && ((touched >> (a0 + len)) & 1u) == f && (len + 1) * cout <= 256) ++len;
-                if (!f) {
-                  for (int j = 0; j < len; ++j)
-                    mbar_wait(&acc_empty[a0 + j], ((use_bits >> (a0 + j)) & 1u) ^ 1u, 500 + a0 + j);
-                  tc_fence_after();
-                }
-                const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * cout), p.ab_format);
-                const uint32_t a_addr = a_base + static_cast<uint32_t>(kw) * rowb;
-                const uint32_t b_addr = w_base + static_cast<uint32_t>(kw * ns + ti) * cout128;
-                const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
-                const uint32_t d_addr = tmem_base + static_cast<uint32_t>(a0 * cout);
-                if (elect_one()) {
-#pragma unroll
-                  for (int k16 = 0; k16 < 4; ++k16) {
-                    if (k16 < k16n) {
-                      const uint64_t adesc = umma_desc_kmajor(a_addr + k16 * 32, sbo, boff, lay);
-                      const uint64_t bdesc = umma_desc_kmajor(b_addr + k16 * 32, sbo, 0, lay);
-                      umma_f16_ss(d_addr, adesc, bdesc, idesc, (f | (k16 > 0)) ? 1u : 0u);
-                    }
-                  }
-                }
-                __syncwarp();
-                touched |= ((1u << len) - 1u) << a0;
-                ti += len;
-              }
-            }
-          }
-          const bool last_block = (b == nblk - 1) && a_first >= 0 && a_first < ra;
-          if (elect_one()) {
-            umma_commit(&empty_a[stage]);
-            if (last_block) umma_commit(&acc_full[a_first]);
-          }
-          __syncwarp();
-          if (last_block) signaled |= 1u << a_first;
-          if (++stage == nst) {
-            stage = 0;
-            aphase ^= 1u;
-          }
-        }
-        if (elect_one()) umma_commit(&empty_w[wb]);
-        __syncwarp();
-        if (++wb == nwb) {
-          wb = 0;
-          wphase ^= 1u;
-        }
-      }
-      if (elect_one()) {
-        for (int a = 0; a < ra; ++a)
-          if (!((signaled >> a) & 1u)) umma_commit(&acc_full[a]);
-      }
-      __syncwarp();
-      use_bits ^= (1u << ra) - 1u;
-    }
+    const int nkw_rt = (p.mode == kModeRowShared) ? 3 : 1;
+    if (general) mma_issuer<0, 0>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
+    else if (nkw_rt == 3 && p.k16_steps == 4) mma_issuer<3, 4>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
+    else if (nkw_rt == 3 && p.k16_steps == 2) mma_issuer<3, 2>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
+    else if (nkw_rt == 1 && p.k16_steps == 4) mma_issuer<1, 4>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
+    else mma_issuer<0, 0>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;
@@ -487,9 +523,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               o[2 * i] = pack2(x0, x1, p.ab_format);
               o[2 * i + 1] = pack2(x2, x3, p.ab_format);
             }
-            uint4* d4 = reinterpret_cast<uint4*>(dst + (j + h) * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            // 32-byte stores: every L2 sector is written whole by one instruction (a thread owns a voxel's channel row, so
+            // the lanes of a warp never share a line -- half as many store instructions is half the LSU line traffic)
+            st_global_256(dst + (j + h) * 32, o);
+            st_global_256(dst + (j + h) * 32 + 16, o + 8);
             if (p.out_split) {
               // lo plane: the rounding residual of the hi plane, so hi + lo carries ~22 mantissa bits
 #pragma unroll
@@ -503,9 +540,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 o[2 * i] = pack2_residual(x0, x1, o[2 * i], p.ab_format);
                 o[2 * i + 1] = pack2_residual(x2, x3, o[2 * i + 1], p.ab_format);
               }
-              uint4* l4 = reinterpret_cast<uint4*>(dst + p.out_lo_off + (j + h) * 32);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) l4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+              st_global_256(dst + p.out_lo_off + (j + h) * 32, o);
+              st_global_256(dst + p.out_lo_off + (j + h) * 32 + 16, o + 8);
             }
           }
         }

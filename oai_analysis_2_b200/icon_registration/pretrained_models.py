@@ -190,10 +190,18 @@ class GradICONModel:
         if len(fields) > 4:
             raise NotImplementedError("registration trees with more than four cascaded fields")
         maps = [ops.compose(full, [f[k] for f in fields], self._shortcut(fields, full))[0] for k in range(2)]
+        self.fields = fields   # the cascade's displacement fields, application order, [2 directions, 3, d, h, w] each
         self.phi_AB_vectorfield, self.phi_BA_vectorfield = maps[0][None], maps[1][None]
         return self.phi_AB_vectorfield, self.phi_BA_vectorfield
 
     __call__ = forward
+
+    def warp_image(self, image, direction=0, out=None):
+        """as_function(image)(phi(identity_map)) for the last registered pair: `image` [D,H,W] at the network resolution
+        warped by phi_AB (direction 0) or phi_BA (1), fused with the composition (no map is materialised)."""
+        shape = tuple(image.shape[-3:])
+        return ops.compose(shape, [f[direction] for f in self.fields], self._shortcut(self.fields, shape),
+                           image.reshape(shape), want_phi=False, img_out=out)[1]
 
     def _eval_on_identity(self, field, coords):
         if field is None:

@@ -357,10 +357,12 @@ def _affine(M, t):
     return np.ascontiguousarray(a)
 
 
-def warp_volume(src, disp, out_index_to_net, net_to_src_index, out_dims, default_value=0.0):
+def warp_volume(src, disp, out_index_to_net, net_to_src_index, out_dims, default_value=0.0, out=None):
     """src: [C, SD, SH, SW] float32; disp: [FD, FH, FW, 3]; affines: (M, t) float64 on x,y,z.  Returns [C, *out_dims]."""
     C = src.shape[0]
-    out = torch.empty((C,) + tuple(int(v) for v in out_dims), dtype=torch.float32, device=src.device)
+    if out is None:
+        out = torch.empty((C,) + tuple(int(v) for v in out_dims), dtype=torch.float32, device=src.device)
+    assert src.is_contiguous() and disp.is_contiguous() and out.is_contiguous()
     a, b = _affine(*out_index_to_net), _affine(*net_to_src_index)
     check(lib.oai_warp_volume(ptr(src), C, ptr(_dims(*src.shape[1:])), ptr(disp), ptr(_dims(*disp.shape[:3])), ptr(a),
                               ptr(b), ptr(out), ptr(_dims(*out.shape[1:])), c_float(default_value), stream_ptr()),

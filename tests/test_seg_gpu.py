@@ -333,9 +333,9 @@ def test_fp16_saturation_is_detected_not_silent(tmp_path):
     from oai_analysis_2_b200.segmentation.segmenter import Segmenter3DInPatchClassWise
     from oracle.seg_oracle import make_unet_state_dict
     # one layer: inputs of 300 through weights summing to ~300 per output -> ~9e4 > 65504
-    x = torch.full((1, 2, 4, 128, 64), 300.0, device="cuda").half()
+    x = torch.full((1, 4, 4, 128, 64), 300.0, device="cuda").half()   # interior voxels see all 27 taps
     w = torch.full((64, 64, 3, 3, 3), 300.0 / (27 * 64))
-    wp = ops.pack_conv_weights_ex(w, 64, 0, 2, 4, 128, 0, 1)
+    wp = ops.pack_conv_weights_ex(w, 64, 0, 4, 4, 128, 0, 1)
     ops.conv_overflow_count(reset=True)
     out = ops.conv3d_igemm_ex(x, None, wp, torch.zeros(64).cuda(), 64, 64)
     assert torch.isinf(out.float()).any()
