@@ -327,6 +327,8 @@ def run_full(args):
     line["config"]["seg_tflop_per_volume"] = SEG_FLOP_PER_VOLUME / 1e12
     if rank == 0:
         if world == 1:
+            del vols_d, verts_d
+            pipe.release_graph()   # the graph's private pool (activation workspace) goes back to the allocator
             if not args.no_dropin:
                 line["e2e_dropin"] = dropin_e2e(pipe, vols_h, geom)
             if not args.no_library_bar:

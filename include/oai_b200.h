@@ -312,6 +312,33 @@ OAI_API int oai_intensity_window(const float* in, long long n, double perc_lo, d
                                  float out_max, float* out, void* workspace, size_t workspace_bytes, void* stream);
 OAI_API int oai_intensity_window_result(const void* workspace, double* window_host, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Iso-surface extraction of the atlas-space probability maps: skimage.measure.marching_cubes(level,
+ * spacing, step_size=1, gradient_direction) of oai_analysis/mesh_processing.py:325-340 (get_mesh) and the
+ * vtkPolyDataConnectivityFilter region filter of mesh_processing.py:102-146 (get_vtk_mesh keeps regions with more than
+ * 3000 cells).  vol: float32 [D][H][W] on the device (z,y,x, the array the reference swaps to x,y,z before the call);
+ * vertices come out as (x*sx, y*sy, z*sz) float32, one per crossed lattice edge; faces are int32 vertex triples wound so
+ * that normals point to ascending values when ascent != 0.  Ambiguous faces use the asymptotic decider.
+ * Two calls: oai_mc_count classifies, scans and returns {n_verts, n_faces} on the host (synchronises the stream);
+ * oai_mc_emit writes them into caller buffers of that size using the SAME workspace (oai_mc_workspace_bytes, 256-byte
+ * aligned, untouched in between).
+ * ------------------------------------------------------------------------------------------------------------ */
+OAI_API size_t oai_mc_workspace_bytes(const int* dims);
+OAI_API int oai_mc_count(const float* vol, const int* dims, float level, void* workspace, size_t workspace_bytes,
+                         long long* counts_host, void* stream);
+OAI_API int oai_mc_emit(const float* vol, const int* dims, float level, const double* spacing_xyz, int ascent,
+                        void* workspace, size_t workspace_bytes, float* verts, int* faces, void* stream);
+/* the generated polygon table (host, no GPU): 256 corner patterns x 64 face resolutions x 32 bytes
+ * {n_triangles, 3 edge ids per triangle ...}; edge id = 4*axis + (u + 2v) */
+OAI_API int oai_mc_table(uint8_t* table, size_t bytes);
+/* get_vtk_mesh's region filter: connected components of the faces over shared vertices; components with MORE than
+ * min_cells faces are kept, vertices compacted and faces re-indexed.  out_verts / out_faces must hold n_verts / n_faces
+ * entries; counts_host receives {kept verts, kept faces} (synchronises the stream). */
+OAI_API size_t oai_mesh_regions_workspace_bytes(long long n_verts, long long n_faces);
+OAI_API int oai_mesh_keep_large_regions(const float* verts, long long n_verts, const int* faces, long long n_faces,
+                                        int min_cells, void* workspace, size_t workspace_bytes, float* out_verts,
+                                        int* out_faces, long long* counts_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

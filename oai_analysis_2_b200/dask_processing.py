@@ -23,7 +23,7 @@ def deform_probmap(phi_AB, image_A, image_B, prob, image_type="FC"):
     arr = np.ascontiguousarray(itk_compat.array_from_image(prob), dtype=np.float32)
     src = torch.from_numpy(arr).to(phi_AB.disp.device)[None]
     out = phi_AB.resample_device(src, Geometry.of(prob), Geometry.of(image_B))
-    return itk_compat.image_from_array(out[0].cpu().numpy().astype(np.float64), like=image_B)
+    return itk_compat.image_from_array(out[0].cpu().to(torch.float64).numpy(), like=image_B)
 
 
 deform_probmap_delayed = deform_probmap

@@ -121,9 +121,10 @@ class SegHandle:
         return int(lib.oai_seg_workspace_bytes(self._h, ptr(np.asarray(vol_shape, dtype=np.int32)),
                                                int(tiles_per_batch or 0)))
 
-    def auto_tiles_per_batch(self, vol_shape, fraction=0.85):
+    def auto_tiles_per_batch(self, vol_shape, fraction=0.5):
         """All tiles in one batch when the activation workspace fits `fraction` of the free device memory (plus what
-        torch's caching allocator already holds), otherwise the largest even split that does."""
+        torch's caching allocator already holds), otherwise the largest even split that does.  (On a 180 GB B200 the
+        default "mixed" plan runs a 160-tile knee as 2 x 80 tiles, 43 GB; pass tiles_per_batch to override.)"""
         key = tuple(int(v) for v in vol_shape)
         if key in self._auto:   # decided once per shape (also keeps CUDA-graph capture free of memory queries)
             return self._auto[key]
@@ -433,3 +434,47 @@ def intensity_window(vol, perc_lo=0.1, perc_hi=99.9, out_min=0.0, out_max=1.0, o
         check(lib.oai_intensity_window_result(ptr(ws), w, stream_ptr()), "intensity_window_result")
         return out, (w[0], w[1])
     return out
+
+
+# ------------------------------------------------------------------------------------------------ iso-surface extraction
+def mc_table():
+    """The generated marching-cubes polygon table [256, 64, 32] uint8 (host arithmetic in the library)."""
+    t = np.zeros((256, 64, 32), dtype=np.uint8)
+    check(lib.oai_mc_table(ptr(t), c_size(t.size)), "mc_table")
+    return t
+
+
+def marching_cubes(vol, level=0.5, spacing_xyz=(1.0, 1.0, 1.0), gradient_direction="ascent"):
+    """vol: float32 [D,H,W] cuda (z,y,x).  Returns (verts float32 [n,3] (x,y,z) * spacing, faces int32 [m,3]) on the
+    device: skimage.measure.marching_cubes(np.swapaxes(vol, 0, 2), level, spacing=spacing_xyz, step_size=1,
+    gradient_direction=...)[:2] with one vertex per crossed lattice edge."""
+    assert vol.dtype == torch.float32 and vol.is_contiguous() and vol.is_cuda and vol.dim() == 3
+    dims = np.asarray(vol.shape, dtype=np.int32)
+    nbytes = int(lib.oai_mc_workspace_bytes(ptr(dims)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=vol.device)
+    counts = (c_ll * 2)()
+    check(lib.oai_mc_count(ptr(vol), ptr(dims), c_float(level), ptr(ws), c_size(nbytes), counts, stream_ptr()),
+          "mc_count")
+    nv, nf = int(counts[0]), int(counts[1])
+    verts = torch.empty((nv, 3), dtype=torch.float32, device=vol.device)
+    faces = torch.empty((nf, 3), dtype=torch.int32, device=vol.device)
+    if nv and nf:
+        sp = np.asarray(spacing_xyz, dtype=np.float64)
+        check(lib.oai_mc_emit(ptr(vol), ptr(dims), c_float(level), ptr(sp), int(gradient_direction == "ascent"),
+                              ptr(ws), c_size(nbytes), ptr(verts), ptr(faces), stream_ptr()), "mc_emit")
+    return verts, faces
+
+
+def keep_large_regions(verts, faces, min_cells=3000):
+    """get_vtk_mesh's region filter on the device: (verts, faces) of the connected regions with > min_cells faces."""
+    nv, nf = int(verts.shape[0]), int(faces.shape[0])
+    if nv == 0 or nf == 0:
+        return verts[:0], faces[:0]
+    assert verts.dtype == torch.float32 and faces.dtype == torch.int32 and verts.is_contiguous() and faces.is_contiguous()
+    nbytes = int(lib.oai_mesh_regions_workspace_bytes(c_ll(nv), c_ll(nf)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=verts.device)
+    ov, of = torch.empty_like(verts), torch.empty_like(faces)
+    counts = (c_ll * 2)()
+    check(lib.oai_mesh_keep_large_regions(ptr(verts), c_ll(nv), ptr(faces), c_ll(nf), int(min_cells), ptr(ws),
+                                          c_size(nbytes), ptr(ov), ptr(of), counts, stream_ptr()), "keep_large_regions")
+    return ov[:int(counts[0])], of[:int(counts[1])]

@@ -62,6 +62,15 @@ class KneePipeline:
             self._g_out = self.run_device(self._g_vol, geom, self._g_verts)
         return self
 
+    def release_graph(self):
+        """Drop the captured graph, its static buffers and the stream API's staging buffers (tens of GB of private
+        pool memory go back to the allocator)."""
+        for name in ("_graph", "_g_out", "_g_vol", "_g_verts", "_rs"):
+            if hasattr(self, name):
+                delattr(self, name)
+        torch.cuda.synchronize(self.device)
+        torch.cuda.empty_cache()
+
     def _graph_matches(self, vol, geom, vertices):
         return (getattr(self, "_graph", None) is not None and tuple(vol.shape) == tuple(self._g_vol.shape)
                 and geom is self._g_geom

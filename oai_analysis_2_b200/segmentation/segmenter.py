@@ -80,7 +80,8 @@ class Segmenter3DInPatchClassWise(Segmenter3DInPatch):
         arr = np.ascontiguousarray(itk_compat.array_from_image(image), dtype=np.float32)
         vol = torch.from_numpy(arr).to(self.device, non_blocking=True)
         out = self.segment_device(vol, if_output_prob_map, self.config.get("tiles_per_batch"))
-        host = out.cpu().numpy().astype(np.float64)  # the reference assembles into float64 (np.zeros default, :493)
+        # the reference assembles into float64 (np.zeros default, :493); torch's multi-threaded cast beats numpy's astype
+        host = out.cpu().to(torch.float64).numpy()
         if self.model._fmt() == 0 and ops.conv_overflow_count(reset=True):
             raise FloatingPointError("segmentation activations left the fp16 range (|x| > 65504) with this checkpoint; "
                                      "set model.precision = 'bf16' (UNet.precision / OAI_B200_SEG_PRECISION)")

@@ -70,7 +70,7 @@ class CompositeTransform:
     def displacement_field_array(self):
         """float64 [D,H,W,3] like itk.array_from_image(tr.GetDisplacementField()).  Read from the device every time:
         the field buffer may be a CUDA graph's static output that a later replay rewrites."""
-        return self.disp.cpu().numpy().astype(np.float64)
+        return self.disp.cpu().to(torch.float64).numpy()
 
     def transform_points(self, pts_xyz):
         """TransformPoint over an [n,3] array of physical points (float64).  Runs on the GPU."""

@@ -271,3 +271,80 @@ def test_warp_volume_and_points_match_itk_oracle():
     assert np.abs(ref - pts).max() > 0.5
     assert tr.transform_points(np.zeros((0, 3))).shape == (0, 3)
     assert np.allclose(tr.TransformPoint(pts[0]), ref[0], atol=1e-6)
+
+
+def test_isosurface_extraction_matches_oracle():
+    """marching cubes @0.5 with spacing + small-region filter on the device against the (unpinned) numpy
+    oracle: same vertex set, same face set, same regions."""
+    _cuda()
+    from oai_analysis_2_b200 import mesh_processing, ops
+    from oracle import mesh_oracle as mo
+    rng = np.random.default_rng(3)
+    n = (36, 44, 40)
+    z, y, x = np.meshgrid(*(np.arange(m) for m in n), indexing="ij")
+
+    def blob(c, r):
+        return 1.0 / (1.0 + np.exp(np.sqrt((z - c[0]) ** 2 + (y - c[1]) ** 2 + (x - c[2]) ** 2) - r))
+    vol = np.maximum(blob((18.2, 21.7, 19.4), 13.0), blob((4.3, 5.2, 5.9), 2.2)).astype(np.float32)
+    vol += (0.02 * rng.standard_normal(n)).astype(np.float32)          # roughen: ambiguous faces do occur
+    sp = (0.36, 0.37, 0.7)
+    verts, faces = ops.marching_cubes(torch.from_numpy(vol).cuda(), 0.5, sp, "ascent")
+    rv, rf = mo.marching_cubes(np.swapaxes(vol, 0, 2), 0.5, sp, "ascent")   # the reference swaps to x,y,z first
+    v, f = verts.cpu().numpy().astype(np.float64), faces.cpu().numpy().astype(np.int64)
+    assert v.shape == rv.shape and f.shape == rf.shape
+    # same vertices (as a set, the orders differ) ...
+    def order(a):
+        return np.lexsort(np.round(a / 1e-4).astype(np.int64).T[::-1])
+    io, ro = order(v), order(rv)
+    assert np.abs(v[io] - rv[ro]).max() < 2e-5
+    # ... and the same faces once both are re-indexed to the sorted vertex order (rotation-normalised)
+    def canon(faces_, perm):
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(len(perm))
+        g = inv[faces_]
+        k = np.argmin(g, axis=1)
+        g = np.stack([np.roll(row, -kk) for row, kk in zip(g, k)])
+        return g[np.lexsort(g.T[::-1])]
+    assert np.array_equal(canon(f, io), canon(rf, ro))
+    st = mo.mesh_stats(v, f)
+    print(f"iso-surface: {st['n_verts']} vertices, {st['n_faces']} faces, area {st['area']:.1f}, Euler {st['euler']}")
+    # region filter (get_vtk_mesh: > 3000 cells)
+    kv, kf = ops.keep_large_regions(verts, faces, 3000)
+    okv, okf, nreg = mo.keep_large_regions(rv, rf, 3000)
+    assert nreg == 1 and kv.shape[0] == len(okv) and kf.shape[0] == len(okf) and 0 < len(okf) < len(rf)
+    kvn = kv.cpu().numpy().astype(np.float64)
+    assert np.abs(kvn[order(kvn)] - okv[order(okv)]).max() < 2e-5
+    assert mo.mesh_stats(kvn, kf.cpu().numpy().astype(np.int64))["euler"] == 2
+    # drop-in wrapper on an image with metadata
+    from oai_analysis_2_b200 import itk_compat
+    mv, mf = mesh_processing.extract_isosurface(itk_compat.Image(vol, spacing=sp))
+    assert mv.shape == tuple(kv.shape) and mf.shape == tuple(kf.shape)
+    # degenerate inputs: nothing above the level -> empty mesh, not an error
+    ev, ef = ops.marching_cubes(torch.zeros(8, 8, 8, device="cuda"), 0.5)
+    assert ev.shape == (0, 3) and ef.shape == (0, 3)
+
+
+def test_isosurface_full_size_properties():
+    """BASELINE size (160x384x384): closed, oriented surface of a synthetic cartilage-like sheet; timing printed."""
+    _cuda()
+    from oai_analysis_2_b200 import ops, synthetic
+    from oracle import mesh_oracle as mo
+    vol = torch.from_numpy(synthetic.synthetic_knee(synthetic.OAI_SHAPE, seed=3)).cuda()
+    vol[0], vol[-1], vol[:, 0], vol[:, -1], vol[:, :, 0], vol[:, :, -1] = 0, 0, 0, 0, 0, 0
+    ops.marching_cubes(vol, 0.5, synthetic.OAI_SPACING)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    v, f = ops.marching_cubes(vol, 0.5, synthetic.OAI_SPACING)
+    kv, kf = ops.keep_large_regions(v, f, 3000)
+    e1.record()
+    torch.cuda.synchronize()
+    fn = kf.cpu().numpy().astype(np.int64)
+    d = np.concatenate([fn[:, [0, 1]], fn[:, [1, 2]], fn[:, [2, 0]]])
+    key = np.sort(d[:, 0] * (len(kv) + 1) + d[:, 1])
+    rev = np.sort(d[:, 1] * (len(kv) + 1) + d[:, 0])
+    assert np.array_equal(key, rev)                      # watertight + consistently oriented
+    st = mo.mesh_stats(kv.cpu().numpy().astype(np.float64), fn)
+    print(f"full-size iso-surface: {len(v)} -> {st['n_verts']} vertices, {len(f)} -> {st['n_faces']} faces, "
+          f"{e0.elapsed_time(e1):.2f} ms (marching cubes + region filter)")
+    assert st["n_faces"] > 3000 and st["volume"] < 0     # ascent winding: inward normals for a bright object
