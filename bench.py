@@ -245,6 +245,14 @@ def run_full(args):
     vols_pin = [torch.from_numpy(v).pin_memory() for v in vols_h]
     verts_pin = torch.from_numpy(verts_h).pin_memory()
 
+    # the drop-in entry points first, eagerly, while the allocator is still empty (the CUDA graph captured below keeps
+    # its activation workspace in a private pool for as long as the graph lives)
+    e2e_dropin = None
+    if rank == 0 and world == 1 and not args.no_dropin:
+        e2e_dropin = dropin_e2e(pipe, vols_h, geom)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
     launches_per_step = None
     if not args.no_graph:
         # the whole per-knee path is one CUDA graph; the conv profiling events are recorded inside it
@@ -327,12 +335,14 @@ def run_full(args):
     line["config"]["seg_tflop_per_volume"] = SEG_FLOP_PER_VOLUME / 1e12
     if rank == 0:
         if world == 1:
-            del vols_d, verts_d
-            pipe.release_graph()   # the graph's private pool (activation workspace) goes back to the allocator
-            if not args.no_dropin:
-                line["e2e_dropin"] = dropin_e2e(pipe, vols_h, geom)
+            if e2e_dropin is not None:
+                line["e2e_dropin"] = e2e_dropin
             if not args.no_library_bar:
+                import gc
+                del vols_d, verts_d, res
+                pipe.release_graph()   # the graph's private pool (activation workspace) goes back to the allocator
                 del pipe
+                gc.collect()
                 torch.cuda.empty_cache()
                 line["library_bar"] = library_bar(vols_h[0], "full")
             if not args.no_cpu_baseline:

@@ -1335,91 +1335,82 @@ __device__ __forceinline__ TriF trif_setup(const double s[3], const int n[3]) {
   return r;
 }
 
-// Tile = 32 (x) x 8 (y) x kWarpVZ (z) output voxels per block; lane <-> x, so the gathers and stores of a warp fall
-// in a few 128-byte lines and neighbouring warps (rows) share them through L1.  A thread carries kWarpVZ z-adjacent
-// voxels (1 in the shipped instantiation: at 40 registers 6 blocks / SM are resident, which beat carrying 2 or 4
-// voxels per thread at lower occupancy, and staging the tile's field box in shared memory was slower than L1;
-// profiles/r01_warp_variants.txt).  The kernel is issue-bound on the fp64 coordinate math and address arithmetic.  Coordinates stay fp64 (ITK computes in double); interpolation weights and
-// sums are fp32.
-template <int kWarpVZ, int kMinBlocks>
+// Tile = 32 (x) x 8 (y) output voxels of one z-slice per block; lane <-> x, so the gathers and stores of a warp fall in
+// a few 128-byte lines and neighbouring warps (rows) share them through L1.  One voxel per thread.  The kernel is
+// issue-bound, not DRAM-bound (profiles/r01_warp_variants.txt: ~420 instructions per voxel in the first version), so
+// the structure below is about instruction count: the eight neighbour offsets (32-bit, relative to the channel plane)
+// and the eight interpolation weights are computed ONCE per voxel and reused by every channel -- the channel loop is
+// eight loads, eight FMAs and a store -- and the displacement gather uses 32-bit element offsets as well.
+// Coordinates stay fp64 (ITK computes in double); interpolation weights and sums are fp32.
+template <int kMinBlocks>
 __global__ void __launch_bounds__(256, kMinBlocks) warp_volume_kernel(const WarpVolumeParams p) {
   const long long nvox = static_cast<long long>(p.OD) * p.OH * p.OW;
   const size_t splane = static_cast<size_t>(p.SD) * p.SH * p.SW;
   const int nf[3] = {p.FW, p.FH, p.FD}, ns[3] = {p.SW, p.SH, p.SD};
   const int nbx = (p.OW + 31) / 32, nby = (p.OH + 7) / 8;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int tx0 = static_cast<int>(blockIdx.x % nbx) * 32, ty0 = static_cast<int>((blockIdx.x / nbx) % nby) * 8;
-  const int tz0 = static_cast<int>(blockIdx.x / (nbx * nby)) * kWarpVZ;
-  const int x = tx0 + lane, y = ty0 + wrp;
+  const int x = static_cast<int>(blockIdx.x % nbx) * 32 + lane, y = static_cast<int>((blockIdx.x / nbx) % nby) * 8 + wrp;
+  const int z = static_cast<int>(blockIdx.x / (nbx * nby));
   if (x >= p.OW || y >= p.OH) return;
-  // ---- displacement at the kWarpVZ lattice points
-  double q[kWarpVZ][3];
-  float dsp[kWarpVZ][3];
+  // ---- lattice coordinate of the output voxel and the displacement there
+  double q[3];
+  {
+    const double j[3] = {static_cast<double>(x), static_cast<double>(y), static_cast<double>(z)};
+    affine_apply(p.out_index_to_net, j, q);
+  }
+  bool fin = true;
 #pragma unroll
-  for (int i = 0; i < kWarpVZ; ++i) {
-    const double j[3] = {static_cast<double>(x), static_cast<double>(y),
-                         static_cast<double>(min(tz0 + i, p.OD - 1))};
-    affine_apply(p.out_index_to_net, j, q[i]);
-    bool fin = true;
+  for (int a = 0; a < 3; ++a) fin = fin && q[a] >= -0.5 && q[a] < p.fhi[a];
+  float dx = 0.f, dy = 0.f, dz = 0.f;
+  if (fin) {
+    const TriF tf = trif_setup(q, nf);
+    const int r00 = (tf.i0[2] * p.FH + tf.i0[1]) * p.FW, r01 = (tf.i0[2] * p.FH + tf.i1[1]) * p.FW;
+    const int r10 = (tf.i1[2] * p.FH + tf.i0[1]) * p.FW, r11 = (tf.i1[2] * p.FH + tf.i1[1]) * p.FW;
+    const float tx = tf.t[0], ty = tf.t[1], tz = tf.t[2];
+    const float wy0 = (1.f - ty) * (1.f - tz), wy1 = ty * (1.f - tz), wy2 = (1.f - ty) * tz, wy3 = ty * tz;
+    const int rows[4] = {r00, r01, r10, r11};
+    const float wr[4] = {wy0, wy1, wy2, wy3};
 #pragma unroll
-    for (int a = 0; a < 3; ++a) fin = fin && q[i][a] >= -0.5 && q[i][a] < p.fhi[a];
-    dsp[i][0] = dsp[i][1] = dsp[i][2] = 0.f;
-    if (fin) {
-      const TriF tf = trif_setup(q[i], nf);
-      {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int ix = (c & 1) ? tf.i1[0] : tf.i0[0], iy = (c & 2) ? tf.i1[1] : tf.i0[1],
-                    iz = (c & 4) ? tf.i1[2] : tf.i0[2];
-          const float w = ((c & 1) ? tf.t[0] : 1.f - tf.t[0]) * ((c & 2) ? tf.t[1] : 1.f - tf.t[1]) *
-                          ((c & 4) ? tf.t[2] : 1.f - tf.t[2]);
-          const float* e = p.disp + ((static_cast<size_t>(iz) * p.FH + iy) * p.FW + ix) * 3;
-          dsp[i][0] = fmaf(w, __ldg(e), dsp[i][0]);
-          dsp[i][1] = fmaf(w, __ldg(e + 1), dsp[i][1]);
-          dsp[i][2] = fmaf(w, __ldg(e + 2), dsp[i][2]);
-        }
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float* e0 = p.disp + 3 * (rows[k] + tf.i0[0]);
+      const float* e1 = p.disp + 3 * (rows[k] + tf.i1[0]);
+      const float w0 = wr[k] * (1.f - tx), w1 = wr[k] * tx;
+      dx = fmaf(w0, __ldg(e0), dx); dy = fmaf(w0, __ldg(e0 + 1), dy); dz = fmaf(w0, __ldg(e0 + 2), dz);
+      dx = fmaf(w1, __ldg(e1), dx); dy = fmaf(w1, __ldg(e1 + 1), dy); dz = fmaf(w1, __ldg(e1 + 2), dz);
     }
   }
-  // ---- source index, inside test, interpolation set-up
-  TriF ts[kWarpVZ];
-  bool sin[kWarpVZ];
+  // ---- source index, inside test, interpolation set-up (once per voxel, shared by every channel)
+  const double qd[3] = {q[0] + dx, q[1] + dy, q[2] + dz};
+  double sidx[3];
+  affine_apply(p.net_to_src_index, qd, sidx);
+  bool sin = true;
 #pragma unroll
-  for (int i = 0; i < kWarpVZ; ++i) {
-    const double qd[3] = {q[i][0] + dsp[i][0], q[i][1] + dsp[i][1], q[i][2] + dsp[i][2]};
-    double sidx[3];
-    affine_apply(p.net_to_src_index, qd, sidx);
-    sin[i] = true;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) sin[i] = sin[i] && sidx[a] >= -0.5 && sidx[a] < p.shi[a];
-    ts[i] = trif_setup(sidx, ns);
+  for (int a = 0; a < 3; ++a) sin = sin && sidx[a] >= -0.5 && sidx[a] < p.shi[a];
+  const long long v = (static_cast<long long>(z) * p.OH + y) * p.OW + x;
+  if (!sin) {
+    for (int c = 0; c < p.C; ++c) p.out[c * nvox + v] = p.default_value;
+    return;
   }
-  const long long v0 = (static_cast<long long>(tz0) * p.OH + y) * p.OW + x;
-  const long long zstride = static_cast<long long>(p.OH) * p.OW;
-  for (int c = 0; c < p.C; ++c) {
-    const float* src = p.src + c * splane;
-    float o[kWarpVZ];
+  const TriF ts = trif_setup(sidx, ns);
+  int off[8];
+  float w[8];
+  {
+    const int r00 = (ts.i0[2] * p.SH + ts.i0[1]) * p.SW, r01 = (ts.i0[2] * p.SH + ts.i1[1]) * p.SW;
+    const int r10 = (ts.i1[2] * p.SH + ts.i0[1]) * p.SW, r11 = (ts.i1[2] * p.SH + ts.i1[1]) * p.SW;
+    const float tx = ts.t[0], ty = ts.t[1], tz = ts.t[2];
+    const float a0 = (1.f - ty) * (1.f - tz), a1 = ty * (1.f - tz), a2 = (1.f - ty) * tz, a3 = ty * tz;
+    off[0] = r00 + ts.i0[0]; off[1] = r00 + ts.i1[0]; off[2] = r01 + ts.i0[0]; off[3] = r01 + ts.i1[0];
+    off[4] = r10 + ts.i0[0]; off[5] = r10 + ts.i1[0]; off[6] = r11 + ts.i0[0]; off[7] = r11 + ts.i1[0];
+    w[0] = a0 * (1.f - tx); w[1] = a0 * tx; w[2] = a1 * (1.f - tx); w[3] = a1 * tx;
+    w[4] = a2 * (1.f - tx); w[5] = a2 * tx; w[6] = a3 * (1.f - tx); w[7] = a3 * tx;
+  }
+  const float* src = p.src;
+  float* dst = p.out + v;
+  for (int c = 0; c < p.C; ++c, src += splane, dst += nvox) {
+    float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < kWarpVZ; ++i) {
-      float acc = 0.f;
-      if (sin[i]) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int ix = (k & 1) ? ts[i].i1[0] : ts[i].i0[0], iy = (k & 2) ? ts[i].i1[1] : ts[i].i0[1],
-                    iz = (k & 4) ? ts[i].i1[2] : ts[i].i0[2];
-          const float w = ((k & 1) ? ts[i].t[0] : 1.f - ts[i].t[0]) * ((k & 2) ? ts[i].t[1] : 1.f - ts[i].t[1]) *
-                          ((k & 4) ? ts[i].t[2] : 1.f - ts[i].t[2]);
-          acc = fmaf(w, __ldg(src + (static_cast<size_t>(iz) * p.SH + iy) * p.SW + ix), acc);
-        }
-      } else {
-        acc = p.default_value;
-      }
-      o[i] = acc;
-    }
-    float* dst = p.out + c * nvox + v0;
-#pragma unroll
-    for (int i = 0; i < kWarpVZ; ++i)
-      if (tz0 + i < p.OD) dst[i * zstride] = o[i];
+    for (int k = 0; k < 8; ++k) acc = fmaf(w[k], __ldg(src + off[k]), acc);
+    *dst = acc;
   }
 }
 
@@ -1658,13 +1649,14 @@ int disp_field_launch(const float* phi, int D, int H, int W, float* disp, cudaSt
 }
 
 int warp_volume_launch(const WarpVolumeParams& p, cudaStream_t st) {
-  constexpr int vz = 1;
-  const long long tiles = static_cast<long long>((p.OW + 31) / 32) * ((p.OH + 7) / 8) * ((p.OD + vz - 1) / vz);
+  const long long tiles = static_cast<long long>((p.OW + 31) / 32) * ((p.OH + 7) / 8) * p.OD;
   if (tiles <= 0 || tiles > 0x7fffffffLL) return fail("warp_volume: output too large");
+  if (static_cast<long long>(p.SD) * p.SH * p.SW >= (1ll << 31) || 3ll * p.FD * p.FH * p.FW >= (1ll << 31))
+    return fail("warp_volume: source / field planes must stay below 2^31 elements (32-bit gather offsets)");
   WarpVolumeParams q = p;
   const int nf[3] = {p.FW, p.FH, p.FD}, ns[3] = {p.SW, p.SH, p.SD};
   for (int a = 0; a < 3; ++a) { q.fhi[a] = nf[a] - 0.5; q.shi[a] = ns[a] - 0.5; }
-  warp_volume_kernel<vz, 6><<<static_cast<unsigned>(tiles), 256, 0, st>>>(q);
+  warp_volume_kernel<5><<<static_cast<unsigned>(tiles), 256, 0, st>>>(q);
   return launched("warp_volume_kernel");
 }
 

@@ -121,7 +121,7 @@ class SegHandle:
         return int(lib.oai_seg_workspace_bytes(self._h, ptr(np.asarray(vol_shape, dtype=np.int32)),
                                                int(tiles_per_batch or 0)))
 
-    def auto_tiles_per_batch(self, vol_shape, fraction=0.5):
+    def auto_tiles_per_batch(self, vol_shape, fraction=0.4):
         """All tiles in one batch when the activation workspace fits `fraction` of the free device memory (plus what
         torch's caching allocator already holds), otherwise the largest even split that does.  (On a 180 GB B200 the
         default "mixed" plan runs a 160-tile knee as 2 x 80 tiles, 43 GB; pass tiles_per_batch to override.)"""
