@@ -25,17 +25,26 @@ class KneePipeline:
     def run_device(self, vol, geom, vertices=None):
         """vol: float32 [D,H,W] on the device (intensities windowed to [0,1]); vertices: float64 [n,3] physical
         points in the knee's space.  Returns device tensors."""
+        nvtx = torch.cuda.nvtx   # one range per stage (SURVEY §5: the reference has no tracing at all)
+        nvtx.range_push("oai.segmentation")
         prob = self.segmenter.segment_device(vol, if_output_prob_map=True,
                                              tiles_per_batch=self.segmenter.config.get("tiles_per_batch"))
+        nvtx.range_pop()
+        nvtx.range_push("oai.registration")
         phi_AB, phi_BA = itk_wrapper.register_pair_device(self.reg_model, vol, self.atlas)
         tr_AB = CompositeTransform(ops.displacement_field(phi_AB[0]), geom, self.atlas_geom)
         tr_BA = CompositeTransform(ops.displacement_field(phi_BA[0]), self.atlas_geom, geom)
+        nvtx.range_pop()
+        nvtx.range_push("oai.warp_probmaps")
         warped = tr_AB.resample_device(prob, geom, self.atlas_geom)      # FC, TC on the atlas grid
+        nvtx.range_pop()
         out = dict(prob=prob, warped=warped, phi_AB=tr_AB, phi_BA=tr_BA)
         if vertices is not None:
             # ITK resampling transforms map output-space points to input space, so patient -> atlas is phi_BA
+            nvtx.range_push("oai.warp_vertices")
             out["vertices"] = ops.warp_points(vertices, tr_BA.disp, tr_BA.from_network_space_inv,
                                               tr_BA.to_network_space)
+            nvtx.range_pop()
         return out
 
     # -- CUDA graph of the whole per-knee path (about a hundred launches; replaying one graph removes the launch gaps)

@@ -70,7 +70,7 @@ class Segmenter3DInPatchClassWise(Segmenter3DInPatch):
         # the reference batches config['batch_size'] tiles per forward (results do not depend on it: BN is in eval
         # mode); here the whole tile set is one batch unless the workspace would not fit the free device memory
         if tiles_per_batch is None:
-            tiles_per_batch = handle.auto_tiles_per_batch(volume.shape)
+            tiles_per_batch = self.config.get("tiles_per_batch") or handle.auto_tiles_per_batch(volume.shape)
         return handle.forward(volume, out_mode=0 if if_output_prob_map else 1, tiles_per_batch=tiles_per_batch,
                               out=out)
 
