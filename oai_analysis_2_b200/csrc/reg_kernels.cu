@@ -1335,64 +1335,24 @@ __device__ __forceinline__ TriF trif_setup(const double s[3], const int n[3]) {
   return r;
 }
 
-// Tile = 32 (x) x 8 (y) output voxels of one z-slice per block; lane <-> x, one voxel per thread.
-//
-// The kernel is bound by L1 gather wavefronts and instruction issue, not DRAM (profiles/r01_warp_variants.txt,
-// profiles/r02_warp_sweep.json).  Two things keep both down:
-//   * the displacement field of the tile is staged in shared memory: the tile's footprint in the field lattice is the
-//     bounding box of its four corners under the (affine) index -> lattice map, a few hundred [x,y,z] points that the
-//     block fetches with coalesced loads once; the 8 x 3 per-voxel gathers then hit shared memory, where the 12-byte
-//     point stride is bank-conflict free, instead of 3-4 L1 lines per warp load.  Footprints beyond kFieldBoxPts
-//     points (strongly magnifying maps) and stray points outside the box fall back to global loads;
-//   * the eight neighbour offsets (32-bit, relative to the channel plane) and the eight interpolation weights of the
-//     image gather are computed once per voxel; the channel loop is eight loads, eight FMAs and a store.
+// Tile = 32 (x) x 8 (y) output voxels of one z-slice per block; lane <-> x, so the gathers and stores of a warp fall in
+// a few 128-byte lines and neighbouring warps (rows) share them through L1.  One voxel per thread.  The kernel is
+// issue-bound, not DRAM-bound (profiles/r01_warp_variants.txt: ~420 instructions per voxel in the first version), so
+// the structure below is about instruction count: the eight neighbour offsets (32-bit, relative to the channel plane)
+// and the eight interpolation weights are computed ONCE per voxel and reused by every channel -- the channel loop is
+// eight loads, eight FMAs and a store -- and the displacement gather uses 32-bit element offsets as well.  Staging the
+// tile's field footprint in shared memory was measured again in round 2 and is slower (the cooperative copy costs more
+// than the L1 gathers it replaces): profiles/r02_warp_variants.json.
 // Coordinates stay fp64 (ITK computes in double); interpolation weights and sums are fp32.
-constexpr int kFieldBoxPts = 1536;
-
 template <int kMinBlocks>
 __global__ void __launch_bounds__(256, kMinBlocks) warp_volume_kernel(const WarpVolumeParams p) {
-  __shared__ float s_field[3 * kFieldBoxPts];
   const long long nvox = static_cast<long long>(p.OD) * p.OH * p.OW;
   const size_t splane = static_cast<size_t>(p.SD) * p.SH * p.SW;
   const int nf[3] = {p.FW, p.FH, p.FD}, ns[3] = {p.SW, p.SH, p.SD};
   const int nbx = (p.OW + 31) / 32, nby = (p.OH + 7) / 8;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int x0 = static_cast<int>(blockIdx.x % nbx) * 32, y0 = static_cast<int>((blockIdx.x / nbx) % nby) * 8;
-  const int x = x0 + lane, y = y0 + wrp;
+  const int x = static_cast<int>(blockIdx.x % nbx) * 32 + lane, y = static_cast<int>((blockIdx.x / nbx) % nby) * 8 + wrp;
   const int z = static_cast<int>(blockIdx.x / (nbx * nby));
-  // ---- the tile's footprint in the field lattice (fp32 is plenty: the box carries a one-point safety margin)
-  int blo[3], bdim[3];
-  bool staged = true;
-  {
-    const float xa = static_cast<float>(x0), xb = static_cast<float>(min(x0 + 31, p.OW - 1));
-    const float ya = static_cast<float>(y0), yb = static_cast<float>(min(y0 + 7, p.OH - 1));
-    const float zf = static_cast<float>(z);
-    int npts = 1;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float m0 = static_cast<float>(p.out_index_to_net.m[3 * a]), m1 = static_cast<float>(p.out_index_to_net.m[3 * a + 1]);
-      const float base = static_cast<float>(p.out_index_to_net.m[3 * a + 2]) * zf + static_cast<float>(p.out_index_to_net.t[a]);
-      const float c0 = base + m0 * xa + m1 * ya, c1 = base + m0 * xb + m1 * ya;
-      const float c2 = base + m0 * xa + m1 * yb, c3 = base + m0 * xb + m1 * yb;
-      const float lo = fminf(fminf(c0, c1), fminf(c2, c3)), hi = fmaxf(fmaxf(c0, c1), fmaxf(c2, c3));
-      // clamp in float first: far-away tiles must not overflow the integer conversion
-      const int ilo = static_cast<int>(floorf(fminf(fmaxf(lo, -2.f), static_cast<float>(nf[a])))) - 1;
-      const int ihi = static_cast<int>(floorf(fminf(fmaxf(hi, -2.f), static_cast<float>(nf[a])))) + 2;
-      blo[a] = min(max(ilo, 0), nf[a] - 1);
-      bdim[a] = min(max(ihi, 0), nf[a] - 1) - blo[a] + 1;
-      npts *= bdim[a];
-      staged = staged && npts <= kFieldBoxPts;   // (checked per axis so the product cannot overflow)
-    }
-    if (staged) {
-      const int rowf = 3 * bdim[0], nfl = rowf * bdim[1] * bdim[2];
-      for (int i = threadIdx.x; i < nfl; i += 256) {
-        const int row = i / rowf, col = i - row * rowf;
-        const int rz = row / bdim[1], ry = row - rz * bdim[1];
-        s_field[i] = __ldg(p.disp + 3 * (((blo[2] + rz) * p.FH + blo[1] + ry) * p.FW + blo[0]) + col);
-      }
-    }
-    __syncthreads();
-  }
   if (x >= p.OW || y >= p.OH) return;
   // ---- lattice coordinate of the output voxel and the displacement there
   double q[3];
@@ -1406,33 +1366,19 @@ __global__ void __launch_bounds__(256, kMinBlocks) warp_volume_kernel(const Warp
   float dx = 0.f, dy = 0.f, dz = 0.f;
   if (fin) {
     const TriF tf = trif_setup(q, nf);
+    const int r00 = (tf.i0[2] * p.FH + tf.i0[1]) * p.FW, r01 = (tf.i0[2] * p.FH + tf.i1[1]) * p.FW;
+    const int r10 = (tf.i1[2] * p.FH + tf.i0[1]) * p.FW, r11 = (tf.i1[2] * p.FH + tf.i1[1]) * p.FW;
     const float tx = tf.t[0], ty = tf.t[1], tz = tf.t[2];
-    const float wr[4] = {(1.f - ty) * (1.f - tz), ty * (1.f - tz), (1.f - ty) * tz, ty * tz};
-    const int ax0 = tf.i0[0] - blo[0], ax1 = tf.i1[0] - blo[0], ay0 = tf.i0[1] - blo[1], ay1 = tf.i1[1] - blo[1];
-    const int az0 = tf.i0[2] - blo[2], az1 = tf.i1[2] - blo[2];
-    const bool inbox = staged && ax0 >= 0 && ax1 < bdim[0] && ay0 >= 0 && ay1 < bdim[1] && az0 >= 0 && az1 < bdim[2];
-    if (inbox) {
-      const int rows[4] = {(az0 * bdim[1] + ay0) * bdim[0], (az0 * bdim[1] + ay1) * bdim[0],
-                           (az1 * bdim[1] + ay0) * bdim[0], (az1 * bdim[1] + ay1) * bdim[0]};
+    const float wy0 = (1.f - ty) * (1.f - tz), wy1 = ty * (1.f - tz), wy2 = (1.f - ty) * tz, wy3 = ty * tz;
+    const int rows[4] = {r00, r01, r10, r11};
+    const float wr[4] = {wy0, wy1, wy2, wy3};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float* e0 = s_field + 3 * (rows[k] + ax0);
-        const float* e1 = s_field + 3 * (rows[k] + ax1);
-        const float w0 = wr[k] * (1.f - tx), w1 = wr[k] * tx;
-        dx = fmaf(w0, e0[0], dx); dy = fmaf(w0, e0[1], dy); dz = fmaf(w0, e0[2], dz);
-        dx = fmaf(w1, e1[0], dx); dy = fmaf(w1, e1[1], dy); dz = fmaf(w1, e1[2], dz);
-      }
-    } else {
-      const int rows[4] = {(tf.i0[2] * p.FH + tf.i0[1]) * p.FW, (tf.i0[2] * p.FH + tf.i1[1]) * p.FW,
-                           (tf.i1[2] * p.FH + tf.i0[1]) * p.FW, (tf.i1[2] * p.FH + tf.i1[1]) * p.FW};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float* e0 = p.disp + 3 * (rows[k] + tf.i0[0]);
-        const float* e1 = p.disp + 3 * (rows[k] + tf.i1[0]);
-        const float w0 = wr[k] * (1.f - tx), w1 = wr[k] * tx;
-        dx = fmaf(w0, __ldg(e0), dx); dy = fmaf(w0, __ldg(e0 + 1), dy); dz = fmaf(w0, __ldg(e0 + 2), dz);
-        dx = fmaf(w1, __ldg(e1), dx); dy = fmaf(w1, __ldg(e1 + 1), dy); dz = fmaf(w1, __ldg(e1 + 2), dz);
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float* e0 = p.disp + 3 * (rows[k] + tf.i0[0]);
+      const float* e1 = p.disp + 3 * (rows[k] + tf.i1[0]);
+      const float w0 = wr[k] * (1.f - tx), w1 = wr[k] * tx;
+      dx = fmaf(w0, __ldg(e0), dx); dy = fmaf(w0, __ldg(e0 + 1), dy); dz = fmaf(w0, __ldg(e0 + 2), dz);
+      dx = fmaf(w1, __ldg(e1), dx); dy = fmaf(w1, __ldg(e1 + 1), dy); dz = fmaf(w1, __ldg(e1 + 2), dz);
     }
   }
   // ---- source index, inside test, interpolation set-up (once per voxel, shared by every channel)
