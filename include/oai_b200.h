@@ -339,6 +339,32 @@ OAI_API int oai_mesh_keep_large_regions(const float* verts, long long n_verts, c
                                         int min_cells, void* workspace, size_t workspace_bytes, float* out_verts,
                                         int* out_faces, long long* counts_host, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Mesh post-processing (oai_analysis/mesh_processing.py).  Meshes are (verts float32 [n][3], faces int32
+ * [m][3]) on the device; workspaces are caller-owned, 256-byte aligned.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* smooth_mesh (mesh_processing.py:298-306): vtkSmoothPolyDataFilter(NumberOfIterations, RelaxationFactor = 0.01 by
+ * default, feature-edge smoothing off): x <- x + f * (mean(unique edge neighbours) - x), positions float32 between
+ * iterations.  Jacobi sweeps (VTK sweeps in place); vertices on open boundary edges stay fixed. */
+OAI_API size_t oai_mesh_smooth_workspace_bytes(long long n_verts, long long n_faces);
+OAI_API int oai_mesh_smooth(const float* verts, long long n_verts, const int* faces, long long n_faces, int iterations,
+                            float relaxation, void* workspace, size_t workspace_bytes, float* out_verts, void* stream);
+/* get_cell_normals / get_cell_centroid (mesh_processing.py:25-47): unit face normals (right-hand rule, zero for a
+ * degenerate face) and face centroids, float32 [m][3] each. */
+OAI_API int oai_mesh_face_features(const float* verts, const int* faces, long long n_faces, float* normals,
+                                   float* centroids, void* stream);
+/* get_distance (mesh_processing.py:310-321, vtkDistancePolyDataFilter, unsigned): for every point the distance to the
+ * closest point ON the target mesh's triangles. */
+OAI_API int oai_mesh_distance(const float* points, long long n_points, const float* verts, const int* faces,
+                              long long n_faces, float* dist, void* stream);
+/* KMeans(n_clusters = 2, algorithm = "lloyd") of split_*_cartilage_surface (mesh_processing.py:197-294) on float32
+ * features [n][dim], dim <= 16: Lloyd iterations from a deterministic farthest-point initialisation until no label
+ * changes (or max_iter).  labels int32 [n] in {0, 1}; which cluster is 0 is arbitrary, as with sklearn (the callers
+ * re-orient by the normals).  Synchronises the stream; iterations_host (may be NULL) receives the sweeps done. */
+OAI_API size_t oai_kmeans2_workspace_bytes(int dim);
+OAI_API int oai_kmeans2(const float* features, long long n, int dim, int max_iter, int* labels, void* workspace,
+                        size_t workspace_bytes, int* iterations_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

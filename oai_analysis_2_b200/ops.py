@@ -478,3 +478,49 @@ def keep_large_regions(verts, faces, min_cells=3000):
     check(lib.oai_mesh_keep_large_regions(ptr(verts), c_ll(nv), ptr(faces), c_ll(nf), int(min_cells), ptr(ws),
                                           c_size(nbytes), ptr(ov), ptr(of), counts, stream_ptr()), "keep_large_regions")
     return ov[:int(counts[0])], of[:int(counts[1])]
+
+
+# ------------------------------------------------------------------------------------------------ mesh post-processing
+def smooth_mesh(verts, faces, iterations=150, relaxation=0.01):
+    nv, nf = int(verts.shape[0]), int(faces.shape[0])
+    out = torch.empty_like(verts)
+    if nv == 0:
+        return out
+    assert verts.dtype == torch.float32 and faces.dtype == torch.int32 and verts.is_contiguous() and faces.is_contiguous()
+    nbytes = int(lib.oai_mesh_smooth_workspace_bytes(c_ll(nv), c_ll(nf)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=verts.device)
+    check(lib.oai_mesh_smooth(ptr(verts), c_ll(nv), ptr(faces), c_ll(nf), int(iterations), c_float(relaxation), ptr(ws),
+                              c_size(nbytes), ptr(out), stream_ptr()), "mesh_smooth")
+    return out
+
+
+def face_features(verts, faces):
+    nf = int(faces.shape[0])
+    normals = torch.empty((nf, 3), dtype=torch.float32, device=verts.device)
+    cent = torch.empty((nf, 3), dtype=torch.float32, device=verts.device)
+    check(lib.oai_mesh_face_features(ptr(verts), ptr(faces), c_ll(nf), ptr(normals), ptr(cent), stream_ptr()),
+          "mesh_face_features")
+    return normals, cent
+
+
+def mesh_distance(points, verts, faces):
+    """Unsigned distance of every point [n,3] float32 to the closest point on the triangles of (verts, faces)."""
+    n = int(points.shape[0])
+    out = torch.empty(n, dtype=torch.float32, device=points.device)
+    assert points.is_contiguous() and verts.is_contiguous() and faces.is_contiguous()
+    check(lib.oai_mesh_distance(ptr(points), c_ll(n), ptr(verts), ptr(faces), c_ll(int(faces.shape[0])), ptr(out),
+                                stream_ptr()), "mesh_distance")
+    return out
+
+
+def kmeans2(features, max_iter=300):
+    """labels int32 [n] of a 2-cluster Lloyd KMeans on float32 features [n, dim <= 16]; returns (labels, sweeps)."""
+    x = features.contiguous().float()
+    n, dim = x.shape
+    labels = torch.empty(n, dtype=torch.int32, device=x.device)
+    nbytes = int(lib.oai_kmeans2_workspace_bytes(int(dim)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    it = c_int(0)
+    check(lib.oai_kmeans2(ptr(x), c_ll(n), int(dim), int(max_iter), ptr(labels), ptr(ws), c_size(nbytes),
+                          ctypes.byref(it), stream_ptr()), "kmeans2")
+    return labels, int(it.value)

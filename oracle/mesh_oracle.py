@@ -245,3 +245,115 @@ def mesh_stats(verts, faces):
     n_edges = len(np.unique(e, axis=0))
     return dict(area=float(area), volume=float(vol), euler=int(len(verts) - n_edges + len(faces)),
                 n_verts=int(len(verts)), n_faces=int(len(faces)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Mesh post-processing (reference oai_analysis/mesh_processing.py:197-321) -- ** parity unpinned **
+# except KMeans, which is the real sklearn call the reference makes.
+# ---------------------------------------------------------------------------------------------------------------
+def vertex_neighbours(n_verts, faces):
+    """unique edge neighbours per vertex + flag of vertices on an open boundary edge (an edge used by one face)"""
+    nbr = [set() for _ in range(n_verts)]
+    edge_use = {}
+    for a, b, c in faces:
+        for u, v in ((a, b), (b, c), (c, a)):
+            nbr[u].add(v)
+            nbr[v].add(u)
+            key = (min(u, v), max(u, v))
+            edge_use[key] = edge_use.get(key, 0) + 1
+    fixed = np.zeros(n_verts, dtype=bool)
+    for (u, v), k in edge_use.items():
+        if k == 1:
+            fixed[u] = fixed[v] = True
+    return [sorted(s) for s in nbr], fixed
+
+
+def smooth_mesh(verts, faces, iterations=150, relaxation=0.01, in_place=True):
+    """vtkSmoothPolyDataFilter with the defaults smooth_mesh leaves (mesh_processing.py:298-306): Laplacian relaxation
+    towards the mean of the edge neighbours, points stored as float32 after every update.  in_place=True sweeps the
+    vertices in index order reusing already-updated neighbours (VTK's loop); False is the Jacobi form the GPU runs.
+    Open-boundary vertices are held fixed (closed iso-surfaces have none)."""
+    nbr, fixed = vertex_neighbours(len(verts), faces)
+    x = np.asarray(verts, dtype=np.float32).copy()
+    for _ in range(iterations):
+        src = x if in_place else x.copy()
+        for i in range(len(x)):
+            if fixed[i] or not nbr[i]:
+                continue
+            xi = src[i].astype(np.float64)
+            d = np.zeros(3)
+            for j in nbr[i]:
+                d += (src[j].astype(np.float64) - xi) / len(nbr[i])
+            x[i] = (xi + relaxation * d).astype(np.float32)
+    return x
+
+
+def face_normals_centroids(verts, faces):
+    """trimesh face_normals (unit (b-a)x(c-a)) and get_cell_centroid (mesh_processing.py:25-47)."""
+    v = np.asarray(verts, dtype=np.float64)
+    a, b, c = v[faces[:, 0]], v[faces[:, 1]], v[faces[:, 2]]
+    n = np.cross(b - a, c - a)
+    ln = np.linalg.norm(n, axis=1, keepdims=True)
+    n = np.divide(n, ln, out=np.zeros_like(n), where=ln > 0)
+    return n, (a + b + c) / 3.0
+
+
+def point_mesh_distance(points, verts, faces, chunk=256):
+    """vtkDistancePolyDataFilter (unsigned): distance from each point to the closest point on any triangle."""
+    v = np.asarray(verts, dtype=np.float64)
+    A, B, C = v[faces[:, 0]], v[faces[:, 1]], v[faces[:, 2]]
+    out = np.empty(len(points))
+    P = np.asarray(points, dtype=np.float64)
+    for s in range(0, len(P), chunk):
+        p = P[s:s + chunk, None, :]
+        ab, ac, ap = B - A, C - A, p - A
+        d1, d2 = (ab * ap).sum(-1), (ac * ap).sum(-1)
+        bp = p - B
+        d3, d4 = (ab * bp).sum(-1), (ac * bp).sum(-1)
+        cp = p - C
+        d5, d6 = (ab * cp).sum(-1), (ac * cp).sum(-1)
+        va, vb, vc = d3 * d6 - d5 * d4, d5 * d2 - d1 * d6, d1 * d4 - d3 * d2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            den = 1.0 / (va + vb + vc)
+            q = A + ab * (vb * den)[..., None] + ac * (vc * den)[..., None]                    # interior
+            t = (d4 - d3) / ((d4 - d3) + (d5 - d6))
+            q = np.where(((va <= 0) & (d4 - d3 >= 0) & (d5 - d6 >= 0))[..., None], B + (C - B) * t[..., None], q)
+            t = d2 / (d2 - d6)
+            q = np.where(((vb <= 0) & (d2 >= 0) & (d6 <= 0))[..., None], A + ac * t[..., None], q)
+            q = np.where(((d6 >= 0) & (d5 <= d6))[..., None], C, q)
+            t = d1 / (d1 - d3)
+            q = np.where(((vc <= 0) & (d1 >= 0) & (d3 <= 0))[..., None], A + ab * t[..., None], q)
+            q = np.where(((d3 >= 0) & (d4 <= d3))[..., None], B, q)
+            q = np.where(((d1 <= 0) & (d2 <= 0))[..., None], A, q)
+        out[s:s + chunk] = np.sqrt(((p - q) ** 2).sum(-1).min(axis=1))
+    return out
+
+
+def split_tibial(normals, centroids):
+    """split_tibial_cartilage_surface (mesh_processing.py:197-222) with the reference's own sklearn KMeans call."""
+    from sklearn.cluster import KMeans
+    cn = (centroids - centroids.mean(0)) / (centroids.max(0) - centroids.min(0))
+    feats = np.concatenate((cn * 1, normals * 10), axis=1)
+    labels = KMeans(n_clusters=2, algorithm="lloyd", random_state=5).fit(feats).labels_ * 2 - 1
+    if normals[labels == -1, 1].mean() < 0:
+        labels = -labels
+    return labels, feats
+
+
+def split_femoral(normals, centroids, bounds_min, bounds_max, num_divisions=3):
+    """split_femoral_cartilage_surface (mesh_processing.py:243-294), sklearn KMeans(n_init=5, random_state=5)."""
+    from sklearn.cluster import KMeans
+    cn = (centroids - centroids.mean(0)) / (centroids.max(0) - centroids.min(0))
+    center = (np.asarray(bounds_min) + np.asarray(bounds_max)) / 2
+    dot = (center - centroids) * normals
+    x = cn[:, 0]
+    lo, step = x.min(), (x.max() - x.min()) / num_divisions
+    out = np.zeros(len(cn))
+    for i in range(num_divisions):
+        idx = np.where((x >= lo + step * i) & (x < lo + step * i + step))[0]
+        feats = np.concatenate((cn[idx], normals[idx], dot[idx]), axis=1)
+        lab = KMeans(n_clusters=2, algorithm="lloyd", n_init=5, random_state=5).fit(feats).labels_ * 2 - 1
+        if normals[idx][lab == -1, 1].mean() < 0:
+            lab = -lab
+        out[idx] = lab
+    return out
