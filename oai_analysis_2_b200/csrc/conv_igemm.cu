@@ -27,7 +27,8 @@ namespace oai {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;   // warps 0-2: producers + MMA issuer, 3: idle, 4-11: two epilogue groups
+constexpr int kEpiGroups = 2;  // epilogue group g (warps 4+4g .. 7+4g) drains the accumulators a = g, g+2, ...
 constexpr int kTmemCols = 512;
 
 // activations that left the fp16 range (|x| > 65504 before rounding) since the last reset: a real checkpoint with large
@@ -100,8 +101,9 @@ __device__ __forceinline__ UnitInfo decode_unit(const ConvIgemmParams& p, int u)
   return ui;
 }
 
-__device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
-  if (fmt == 0) {
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (FMT == 0) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
   }
@@ -117,34 +119,97 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
 }
 
 // rn16(x - hi) for the pair whose rounded hi halves are already packed in `hi`
-__device__ __forceinline__ uint32_t pack2_residual(float a, float b, uint32_t hi, int fmt) {
-  if (fmt == 0) {
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2_residual(float a, float b, uint32_t hi) {
+  if (FMT == 0) {
     const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-    return pack2(a - h.x, b - h.y, fmt);
+    return pack2<FMT>(a - h.x, b - h.y);
   }
   const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi));
-  return pack2(a - h.x, b - h.y, fmt);
+  return pack2<FMT>(a - h.x, b - h.y);
 }
 
-// acc[k] += sum_i relu(v[i] + bias[i]) * w[k][i] over one 32-column chunk (w rows are 64 floats apart)
-template <int NC>
-__device__ __forceinline__ void head_dot(const uint32_t (&v)[32], const float* __restrict__ bias,
-                                         const float* __restrict__ w, float (&acc)[8], int ncls = NC) {
+// Epilogue of one 32-column chunk held in registers: + bias (from shared memory), ReLU, 16-bit rounding, two 32-byte
+// stores per thread (a thread owns one voxel's channel row, so every L2 sector is written whole by one instruction);
+// SPLIT also writes the rounding residual lo = rn16(x - hi) lo_off elements further, so hi + lo carries ~22 bits.
+template <int FMT, bool RELU, bool SPLIT>
+__device__ __forceinline__ void epi_store_chunk(uint32_t (&v)[32], uint32_t sbias, uint16_t* dst, long long lo_off,
+                                                float& amax) {
+  uint32_t o[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float f = fmaxf(__uint_as_float(v[i]) + __ldg(bias + i), 0.f);
+  for (int i = 0; i < 8; ++i) {
+    const float4 b4 = lds_f4(sbias + 16 * i);
+    float x0 = __uint_as_float(v[4 * i]) + b4.x, x1 = __uint_as_float(v[4 * i + 1]) + b4.y;
+    float x2 = __uint_as_float(v[4 * i + 2]) + b4.z, x3 = __uint_as_float(v[4 * i + 3]) + b4.w;
+    if (RELU) {
+      x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+    }
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fmaxf(fabsf(x2), fabsf(x3))));
+    o[2 * i] = pack2<FMT>(x0, x1);
+    o[2 * i + 1] = pack2<FMT>(x2, x3);
+    if (SPLIT) {
+      v[4 * i] = __float_as_uint(x0); v[4 * i + 1] = __float_as_uint(x1);
+      v[4 * i + 2] = __float_as_uint(x2); v[4 * i + 3] = __float_as_uint(x3);
+    }
+  }
+  st_global_256(dst, o);
+  st_global_256(dst + 16, o + 8);
+  if (SPLIT) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      o[i] = pack2_residual<FMT>(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]), o[i]);
+    st_global_256(dst + lo_off, o);
+    st_global_256(dst + lo_off + 16, o + 8);
+  }
+}
+
+// All 32-column chunks of one accumulator (this warp's 32 TMEM lanes).  The accumulator is handed back to the MMA warp
+// as soon as its last columns sit in registers, before the conversion and the global stores of that batch.
+template <int FMT, bool RELU, bool SPLIT>
+__device__ __forceinline__ void epi_store_acc(uint32_t t_acc, int nb, uint32_t sbias, uint16_t* dst, long long lo_off,
+                                              uint64_t* acc_empty_bar, int lane, float& amax) {
+  for (int j = 0; j < nb; ++j) {
+    uint32_t v[32];
+    tmem_ld_32x32(t_acc + j * 32, v);
+    tmem_ld_wait();
+    if (j + 1 == nb) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty_bar);
+    }
+    epi_store_chunk<FMT, RELU, SPLIT>(v, sbias + j * 128, dst + j * 32, lo_off, amax);
+  }
+}
+
+// acc[k] += sum_i relu(v[i] + bias[i]) * w[k][i] over one 32-column chunk; bias and the head filter (rows 64 floats
+// apart) are read from shared memory, four columns per load
+template <int NC>
+__device__ __forceinline__ void head_dot(const uint32_t (&v)[32], uint32_t sbias, uint32_t sw, float (&acc)[8],
+                                         int ncls = NC) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b4 = lds_f4(sbias + 16 * i);
+    const float f0 = fmaxf(__uint_as_float(v[4 * i]) + b4.x, 0.f), f1 = fmaxf(__uint_as_float(v[4 * i + 1]) + b4.y, 0.f);
+    const float f2 = fmaxf(__uint_as_float(v[4 * i + 2]) + b4.z, 0.f), f3 = fmaxf(__uint_as_float(v[4 * i + 3]) + b4.w, 0.f);
 #pragma unroll
     for (int k = 0; k < NC; ++k)
-      if (k < ncls) acc[k] = fmaf(f, w[k * 64 + i], acc[k]);
+      if (k < ncls) {
+        const float4 w4 = lds_f4(sw + k * 256 + 16 * i);
+        acc[k] = fmaf(f3, w4.w, fmaf(f2, w4.z, fmaf(f1, w4.y, fmaf(f0, w4.x, acc[k]))));
+      }
   }
 }
 
 
-// The MMA-issuing warp's whole loop.  NKW / K16N > 0: compile-time (kw taps per A stage, K=16 steps per chunk) fast
-// path; <0, 0>: the general path (debug / A-B flags, uncommon shapes) with run-time trip counts and descriptors rebuilt
-// per MMA.  The whole warp walks the (warp-uniform) schedule so the compiler keeps the descriptor arithmetic in uniform
-// registers; one lane, elected once, issues every tcgen05.mma / tcgen05.commit.
-template <int NKW, int K16N>
+// The MMA-issuing warp's whole loop.  NKW / K16N / PER > 0: compile-time (kw taps per A stage, K=16 steps per chunk,
+// accumulators one MMA may span = 256 / cout) fast path; <0, 0, 0>: the general path (debug / A-B flags, uncommon
+// shapes) with run-time trip counts and descriptors rebuilt per MMA.  The whole warp walks the (warp-uniform) schedule so
+// the compiler keeps the descriptor arithmetic in uniform registers; one lane, elected once, issues every tcgen05.mma /
+// tcgen05.commit.  The single thread that feeds the tensor pipe is the critical resource of the kernel (ncu source
+// counters, profiles/r02_ncu_ec1_issuer.txt: ~150 instructions per A stage outside the polling loops against 6 x 96
+// clocks of MMAs for a 32-channel stage), so the steady state -- every accumulator of the unit already holds partial
+// sums, which is every stage after the unit's first weight block -- is a separate loop body of descriptor adds only.
+template <int NKW, int K16N, int PER>
 __device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint32_t tmem_base, uint8_t* abuf,
                                            uint8_t* wbuf, const uint32_t wstride, uint64_t* full_a, uint64_t* empty_a,
                                            uint64_t* full_w, uint64_t* empty_w, uint64_t* acc_full,
@@ -161,10 +226,12 @@ __device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint3
   const uint32_t desc_hi32 = (sbo >> 4) | (1u << 14) | (lay << 29);  // SBO, version = 1, swizzle mode
   const uint32_t a_lo0 = ((smem_u32(abuf) & 0x3FFFF) >> 4) | (1u << 16), a_step = p.astage_stride >> 4;
   const uint32_t w_lo0 = ((smem_u32(wbuf) & 0x3FFFF) >> 4) | (1u << 16), w_step = wstride >> 4;
-  const int per = max(1, 256 / cout);
+  const int per = kFast ? PER : max(1, 256 / cout);
   const uint32_t idesc_1 = umma_idesc_f16(128, static_cast<uint32_t>(cout), p.ab_format);
   const uint32_t idesc_step = static_cast<uint32_t>(cout >> 3) << 17;  // +1 tap in the N field
   const bool up2 = mode == kModeUp2;
+  const bool one_kd = mode == kModePointwise || up2;
+  const bool kd_cycle = mode == kModePerTap && kpb == 1;
   const bool leader = elect_one();
   int stage = 0, wb = 0;
   uint32_t aphase = 0, wphase = 0, use_bits = 0;  // use_bits: per-accumulator mbarrier phase (flips per use)
@@ -178,8 +245,8 @@ __device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint3
     for (int b = 0; b < nblk; ++b) {
       // taps stacked in this block and the input slices it walks (same arithmetic as decode_block, by counters)
       int kdlo = 0, nkd = 3;
-      if (mode == kModePointwise || up2) { kdlo = 1; nkd = 1; }
-      else if (mode == kModePerTap && kpb == 1) { kdlo = kd_it; nkd = 1; kd_it = kd_it == 2 ? 0 : kd_it + 1; }
+      if (one_kd) { kdlo = 1; nkd = 1; }
+      else if (kd_cycle) { kdlo = kd_it; nkd = 1; kd_it = kd_it == 2 ? 0 : kd_it + 1; }
       const int ns = up2 ? R_acc : nkd;
       const int kdhi = kdlo + nkd - 1;
       const int dlo = max(0, d0 + kdlo - 1);
@@ -195,22 +262,31 @@ __device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint3
         const int acc0 = max(a_first, 0);
         const int ti_lo = acc0 - a_first;
         const int nt = min(ns - 1, ra - 1 - a_first) - ti_lo + 1;
-        const uint32_t span = ((1u << nt) - 1u) << acc0;
-        const uint32_t fresh = span & ~touched;
+        uint32_t fresh = 0;
+        if (touched != all_acc) {
+          const uint32_t span = ((1u << nt) - 1u) << acc0;
+          fresh = span & ~touched;
+          touched |= span;
+        }
         if (kFast && fresh == 0) {
           // steady state: every accumulator of the span already holds partial sums
-          for (int g0 = 0; g0 < nt; g0 += per) {
-            const int ng = min(per, nt - g0);
-            const uint32_t idesc = idesc_1 + static_cast<uint32_t>(ng - 1) * idesc_step;
-            const uint32_t d_addr = tmem_base + static_cast<uint32_t>((acc0 + g0) * cout);
-            const uint32_t b_lo = w_lo + static_cast<uint32_t>(ti_lo + g0) * tap16;
-            if (leader) {
+          const uint32_t d_addr0 = tmem_base + static_cast<uint32_t>(acc0 * cout);
+          const uint32_t b_lo0 = w_lo + static_cast<uint32_t>(ti_lo) * tap16;
+          if (leader) {
 #pragma unroll
-              for (int kw = 0; kw < (kFast ? NKW : 1); ++kw)
+            for (int g0 = 0; g0 < 8; g0 += (kFast ? PER : 1)) {
+              if (g0 < nt) {
+                const int ng = min(kFast ? PER : 1, nt - g0);
+                const uint32_t idesc = idesc_1 + static_cast<uint32_t>(ng - 1) * idesc_step;
+                const uint32_t d_addr = d_addr0 + static_cast<uint32_t>(g0 * cout);
+                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g0) * tap16;
 #pragma unroll
-                for (int k16 = 0; k16 < (kFast ? K16N : 1); ++k16)
-                  umma_f16_ss_lohi(d_addr, a_lo + kw * kw_step + k16 * 2, b_lo + kw * b_kw + k16 * 2, desc_hi32, idesc,
-                                   1u);
+                for (int kw = 0; kw < (kFast ? NKW : 1); ++kw)
+#pragma unroll
+                  for (int k16 = 0; k16 < (kFast ? K16N : 1); ++k16)
+                    umma_f16_ss_lohi(d_addr, a_lo + kw * kw_step + k16 * 2, b_lo + kw * b_kw + k16 * 2, desc_hi32,
+                                     idesc, 1u);
+              }
             }
           }
         } else if (kFast) {
@@ -247,7 +323,6 @@ __device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint3
                                      idesc, 1u);
             }
           }
-          touched |= span;
         } else {
           // general path: one group per run of equal accumulator state, descriptors rebuilt per MMA
           const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
@@ -257,9 +332,9 @@ __device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint3
             int ti = ti_lo;
             while (ti <= ti_hi) {
               const int a0 = a_first + ti;
-              const uint32_t f = (touched >> a0) & 1u;
+              const uint32_t f = ((fresh >> a0) & 1u) ^ 1u;   // 1: holds partial sums (of this unit) already
               int len = 1;
-              while (ti + len <= ti_hi && ((touched >> (a0 + len)) & 1u) == f && (len + 1) * cout <= 256) ++len;
+              while (ti + len <= ti_hi && ((((fresh >> (a0 + len)) & 1u) ^ 1u) == f) && (len + 1) * cout <= 256) ++len;
               if (!f) {
                 for (int j = 0; j < len; ++j)
                   mbar_wait(&acc_empty[a0 + j], ((use_bits >> (a0 + j)) & 1u) ^ 1u, 500 + a0 + j);
@@ -277,9 +352,9 @@ __device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint3
                   umma_f16_ss(d_addr, adesc, bdesc, idesc, (f | (k16 > 0)) ? 1u : 0u);
                 }
               }
-              touched |= ((1u << len) - 1u) << a0;
               ti += len;
             }
+            fresh = 0;  // after kw = 0 every accumulator of the span accumulates
           }
         }
         // release the A stage; the last block's last tap of an accumulator also publishes it to the epilogue
@@ -422,14 +497,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     // specialised at compile time on (kw taps per stage, K=16 steps per chunk) and kept to descriptor adds.
     const bool general = p.base_off_mode || p.no_fast_path;
     const int nkw_rt = (p.mode == kModeRowShared) ? 3 : 1;
-    if (general) mma_issuer<0, 0>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
-    else if (nkw_rt == 3 && p.k16_steps == 4) mma_issuer<3, 4>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
-    else if (nkw_rt == 3 && p.k16_steps == 2) mma_issuer<3, 2>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
-    else if (nkw_rt == 1 && p.k16_steps == 4) mma_issuer<1, 4>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
-    else mma_issuer<0, 0>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
+    const int per_rt = max(1, 256 / p.cout);
+#define OAI_ISSUE(NKW, K16N, PER) \
+  mma_issuer<NKW, K16N, PER>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty)
+    if (general) OAI_ISSUE(0, 0, 0);
+    else if (nkw_rt == 3 && p.k16_steps == 4 && per_rt == 4) OAI_ISSUE(3, 4, 4);
+    else if (nkw_rt == 3 && p.k16_steps == 2 && per_rt == 4) OAI_ISSUE(3, 2, 4);
+    else if (nkw_rt == 1 && p.k16_steps == 4 && per_rt == 4) OAI_ISSUE(1, 4, 4);
+    else if (nkw_rt == 1 && p.k16_steps == 4 && per_rt == 2) OAI_ISSUE(1, 4, 2);
+    else if (nkw_rt == 1 && p.k16_steps == 4 && per_rt == 1) OAI_ISSUE(1, 4, 1);
+    else OAI_ISSUE(0, 0, 0);
+#undef OAI_ISSUE
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int eg = (warp - 4) >> 2;         // epilogue group: drains the accumulators a = eg, eg + kEpiGroups, ...
+    const int epi_variant = (p.ab_format ? 4 : 0) + (p.out_split ? 2 : 0) + (p.relu ? 1 : 0);
+    const uint32_t s_bias_addr = smem_u32(s_bias), s_head_addr = smem_u32(s_head);
     const int m = q * 32 + lane;
     const int th = m / p.TW, tw = m % p.TW;
     uint32_t use_bits = 0;
@@ -439,8 +523,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
       const UnitInfo ui = decode_unit(p, u);
       const long long off0 = p.obase + ui.n * p.osN + (ui.h0 + th) * p.osH + (ui.w0 + tw) * p.osW +
                              static_cast<long long>(ui.nh) * p.cout;
-      const float* bias = p.bias + ui.nh * p.cout;
-      for (int a = 0; a < ui.ra; ++a) {
+      for (int a = eg; a < ui.ra; a += kEpiGroups) {
         mbar_wait(&acc_full[a], (use_bits >> a) & 1u, 600 + a);
         tc_fence_after();
         if (p.head.enabled) {
@@ -458,12 +541,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                 static_cast<uint32_t>(a * p.cout + j * 32), v);
               tmem_ld_wait();
+              const uint32_t sbj = s_bias_addr + static_cast<uint32_t>(ui.nh * p.cout + j * 32) * 4u;
+              const uint32_t swj = s_head_addr + static_cast<uint32_t>(j * 32) * 4u;
               switch (hd.ncls) {
-                case 1: head_dot<1>(v, bias + j * 32, s_head + j * 32, acc); break;
-                case 2: head_dot<2>(v, bias + j * 32, s_head + j * 32, acc); break;
-                case 3: head_dot<3>(v, bias + j * 32, s_head + j * 32, acc); break;
-                case 4: head_dot<4>(v, bias + j * 32, s_head + j * 32, acc); break;
-                default: head_dot<8>(v, bias + j * 32, s_head + j * 32, acc, hd.ncls); break;
+                case 1: head_dot<1>(v, sbj, swj, acc); break;
+                case 2: head_dot<2>(v, sbj, swj, acc); break;
+                case 3: head_dot<3>(v, sbj, swj, acc); break;
+                case 4: head_dot<4>(v, sbj, swj, acc); break;
+                default: head_dot<8>(v, sbj, swj, acc, hd.ncls); break;
               }
             }
             if (mine) {
@@ -490,62 +575,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             }
           }
         } else {
-        uint16_t* dst = (p.mode == kModeUp2) ? out + off0 + ui.d0 * p.osD + p.tap_off[ui.tg * p.R + a]
-                                             : out + off0 + (ui.d0 + a) * p.osD;
-        const float* sb = s_bias + ui.nh * p.cout;
-        const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a * p.cout);
-        const int nb = p.cout / 32;
-        // 64 columns per TMEM round trip; the accumulator is handed back to the MMA warp as soon as its last
-        // columns sit in registers, before the conversion and the global stores of that batch
-        for (int j = 0; j < nb; j += 2) {
-          uint32_t v[2][32];
-          tmem_ld_32x32(t_acc + j * 32, v[0]);
-          if (j + 1 < nb) tmem_ld_32x32(t_acc + (j + 1) * 32, v[1]);
-          tmem_ld_wait();
-          if (j + 2 >= nb) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[a]);
+          uint16_t* dst = (p.mode == kModeUp2) ? out + off0 + ui.d0 * p.osD + p.tap_off[ui.tg * p.R + a]
+                                               : out + off0 + (ui.d0 + a) * p.osD;
+          const uint32_t sb = s_bias_addr + static_cast<uint32_t>(ui.nh * p.cout) * 4u;
+          const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(a * p.cout);
+          const int nb = p.cout / 32;
+          switch (epi_variant) {
+            case 0: epi_store_acc<0, false, false>(t_acc, nb, sb, dst, p.out_lo_off, &acc_empty[a], lane, amax); break;
+            case 1: epi_store_acc<0, true, false>(t_acc, nb, sb, dst, p.out_lo_off, &acc_empty[a], lane, amax); break;
+            case 2: epi_store_acc<0, false, true>(t_acc, nb, sb, dst, p.out_lo_off, &acc_empty[a], lane, amax); break;
+            case 3: epi_store_acc<0, true, true>(t_acc, nb, sb, dst, p.out_lo_off, &acc_empty[a], lane, amax); break;
+            case 4: epi_store_acc<1, false, false>(t_acc, nb, sb, dst, p.out_lo_off, &acc_empty[a], lane, amax); break;
+            case 5: epi_store_acc<1, true, false>(t_acc, nb, sb, dst, p.out_lo_off, &acc_empty[a], lane, amax); break;
+            case 6: epi_store_acc<1, false, true>(t_acc, nb, sb, dst, p.out_lo_off, &acc_empty[a], lane, amax); break;
+            default: epi_store_acc<1, true, true>(t_acc, nb, sb, dst, p.out_lo_off, &acc_empty[a], lane, amax); break;
           }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (j + h >= nb) break;
-            uint32_t o[16];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sb + (j + h) * 32 + 4 * i);
-              float x0 = __uint_as_float(v[h][4 * i]) + b4.x, x1 = __uint_as_float(v[h][4 * i + 1]) + b4.y;
-              float x2 = __uint_as_float(v[h][4 * i + 2]) + b4.z, x3 = __uint_as_float(v[h][4 * i + 3]) + b4.w;
-              if (p.relu) {
-                x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
-              }
-              amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fmaxf(fabsf(x2), fabsf(x3))));
-              o[2 * i] = pack2(x0, x1, p.ab_format);
-              o[2 * i + 1] = pack2(x2, x3, p.ab_format);
-            }
-            // 32-byte stores: every L2 sector is written whole by one instruction (a thread owns a voxel's channel row, so
-            // the lanes of a warp never share a line -- half as many store instructions is half the LSU line traffic)
-            st_global_256(dst + (j + h) * 32, o);
-            st_global_256(dst + (j + h) * 32 + 16, o + 8);
-            if (p.out_split) {
-              // lo plane: the rounding residual of the hi plane, so hi + lo carries ~22 mantissa bits
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 b4 = *reinterpret_cast<const float4*>(sb + (j + h) * 32 + 4 * i);
-                float x0 = __uint_as_float(v[h][4 * i]) + b4.x, x1 = __uint_as_float(v[h][4 * i + 1]) + b4.y;
-                float x2 = __uint_as_float(v[h][4 * i + 2]) + b4.z, x3 = __uint_as_float(v[h][4 * i + 3]) + b4.w;
-                if (p.relu) {
-                  x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
-                }
-                o[2 * i] = pack2_residual(x0, x1, o[2 * i], p.ab_format);
-                o[2 * i + 1] = pack2_residual(x2, x3, o[2 * i + 1], p.ab_format);
-              }
-              st_global_256(dst + p.out_lo_off + (j + h) * 32, o);
-              st_global_256(dst + p.out_lo_off + (j + h) * 32 + 16, o + 8);
-            }
-          }
-        }
-        continue;  // accumulator already released
+          continue;  // accumulator already released
         }
         tc_fence_before();
         __syncwarp();

@@ -65,14 +65,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  // the clock is read only once per 2^16 failed polls, so the polling loop of the single-warp roles stays at a handful
+  // of instructions (each try_wait already suspends the thread for a hardware-defined interval)
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > OAI_MBAR_TIMEOUT_NS) {
-      printf("[oai] mbarrier timeout: block %d thread %d tag %d parity %u\n", blockIdx.x, threadIdx.x, tag, parity);
-      __trap();
+    if ((++spins & 0xffff) == 0) {
+      const uint64_t t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > OAI_MBAR_TIMEOUT_NS) {
+        printf("[oai] mbarrier timeout: block %d thread %d tag %d parity %u\n", blockIdx.x, threadIdx.x, tag, parity);
+        __trap();
+      }
     }
   }
+}
+
+// 16-byte shared-memory load through the shared window (an LDS, not a generic LD): the compiler may schedule it freely
+// against global stores
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
 }
 
 // ---------------------------------------------------------------- TMA
