@@ -164,7 +164,7 @@ OAI_API int oai_seg_head(const void* act, int C, int ncls, const float* w, const
  * ------------------------------------------------------------------------------------------------------------ */
 enum {
   OAI_SEG_PRECISION_FP16 = 0,    /* 16-bit operands everywhere (TF32-class mantissa, the reference's cuDNN default) */
-  OAI_SEG_PRECISION_MIXED = 1,   /* default: the two full-resolution decoder layers (dc2, dc1) read fp16 hi+lo inputs */
+  OAI_SEG_PRECISION_MIXED = 1,   /* default: dc2 (the full-resolution 192->64 decoder layer) reads fp16 hi+lo inputs */
   OAI_SEG_PRECISION_FP16X2 = 2,  /* every layer reads fp16 hi+lo activations (terms 2) */
   OAI_SEG_PRECISION_FP16X3 = 3,  /* fp32-faithful: activations and weights both hi+lo (terms 3) */
   OAI_SEG_PRECISION_CUSTOM = 4   /* layer_terms[] below */
@@ -176,7 +176,9 @@ typedef struct {
   int overlap_xyz[3];                     /* segmenter_config "overlap_size" (x,y,z; analysis_object.py:23) */
   int ab_format;                          /* 0 fp16, 1 bf16 */
   int precision;                          /* OAI_SEG_PRECISION_* */
-  int layer_terms[17];                    /* CUSTOM only: terms (1..3) of ec0..ec7, dc9..dc1 (ec0 is always exact) */
+  int layer_terms[17];                    /* CUSTOM only: terms of ec0..ec7, dc9..dc1 (ec0 is always exact): 1..3 as above;
+                                           * 4 / 5 on a concatenating layer (dc8, dc5, dc2): only the skip / only the
+                                           * upsampled source is read as hi+lo */
 } oai_seg_config;
 
 /* one entry of the reference's state_dict: float32, contiguous, host memory, torch layout */
@@ -364,6 +366,36 @@ OAI_API int oai_mesh_distance(const float* points, long long n_points, const flo
 OAI_API size_t oai_kmeans2_workspace_bytes(int dim);
 OAI_API int oai_kmeans2(const float* features, long long n, int dim, int max_iter, int* labels, void* workspace,
                         size_t workspace_bytes, int* iterations_host, void* stream);
+
+/* ---- atlas attribute mapping and 2-D projection of the thickness maps ------------------------------------ */
+/* map_attributes (mesh_processing.py:398-406): vtkPointInterpolator with its default vtkLinearKernel (footprint RADIUS,
+ * radius 1.0 in the reference) and SetNullPointsStrategyToClosestPoint: out[t] = mean of source_attr over the source
+ * points within `radius` of target point t (distance <= radius), or the attribute of the closest source point when
+ * none is in range.  source_attr / out are float32 [n][n_attr], n_attr <= 4. */
+OAI_API int oai_mesh_map_attributes(const float* source_points, const float* source_attr, long long n_source,
+                                    int n_attr, const float* target_points, long long n_target, float radius,
+                                    float* out, void* stream);
+/* 256-byte device scratch (256-byte aligned) of the two projection helpers below. */
+OAI_API size_t oai_mesh_project_workspace_bytes(void);
+/* compute_least_square_circle (mesh_processing.py:409-443, scipy.optimize.leastsq from the centroid): least-squares
+ * circle through coordinates (coord_x, coord_y) of the float32 points [.,3] selected by `index` (int32 [n], or NULL for
+ * the first n points).  Gauss-Newton on the same residual and Jacobian; the sums run on the device, the 2x2 solves on
+ * the host, so the call synchronises the stream.  center_host[2], radius_host / iterations_host (may be NULL). */
+OAI_API int oai_circle_fit(const float* points, const int* index, long long n, int coord_x, int coord_y,
+                           double* center_host, double* radius_host, int* iterations_host, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* get_projection_from_circle_and_vertice (mesh_processing.py:455-476): angle[i] = atan2(p[coord_y] - center_y,
+ * p[coord_x] - center_x), height[i] = p[coord_z]; float64 [n] device outputs. */
+OAI_API int oai_cylinder_project(const float* points, long long n, int coord_x, int coord_y, int coord_z,
+                                 double center_x, double center_y, double* angle, double* height, void* stream);
+/* The tibial branch of project_thickness (mesh_processing.py:497-534) for one plateau: sklearn KernelPCA(n_components=2)
+ * with its default linear kernel = the first two principal-component scores of the selected points (each column signed
+ * so its largest-magnitude entry is positive), then rotate_embedded(rotate_deg), optional x mirror, offset.  float64 [n]
+ * device outputs in the order of `index` (NULL: the first n points).  Synchronises the stream (3x3 eigenproblem on the
+ * host). */
+OAI_API int oai_pca2_project(const float* points, const int* index, long long n, double rotate_deg, int mirror_x,
+                             double offset_x, double offset_y, double* out_x, double* out_y, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,7 @@ lib.oai_mc_workspace_bytes.restype = ctypes.c_size_t
 lib.oai_mesh_regions_workspace_bytes.restype = ctypes.c_size_t
 lib.oai_mesh_smooth_workspace_bytes.restype = ctypes.c_size_t
 lib.oai_kmeans2_workspace_bytes.restype = ctypes.c_size_t
+lib.oai_mesh_project_workspace_bytes.restype = ctypes.c_size_t
 
 c_int, c_ll, c_size, c_void, c_float, c_double = (ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t, ctypes.c_void_p,
                                                    ctypes.c_float, ctypes.c_double)

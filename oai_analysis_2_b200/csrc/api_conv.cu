@@ -40,16 +40,23 @@ struct Plan {
   Chunk chunks[kMaxChunks];
 };
 
+// which sources a term code reads as fp16 hi + lo pairs: 2 / 3 both, 4 the second (the decoder's skip connection) only,
+// 5 the first only
+inline bool split_src(int terms, int src) {
+  return terms == 2 || terms == 3 || (terms == 4 && src == 1) || (terms == 5 && src == 0);
+}
+
 int build_chunks(const ConvSpec& s, Plan* pl) {
   int n = 0;
   const int cs[2] = {s.c0, s.c1};
   for (int src = 0; src < 2; ++src) {
     const int c = cs[src];
     if (c == 0) continue;
-    const int wide = s.terms >= 2 ? 2 * c : c;
+    const bool spl = split_src(s.terms, src);
+    const int wide = spl ? 2 * c : c;
     for (int j = 0; j * 64 < wide; ++j) {
       OAI_REQUIRE(n < kMaxChunks, "conv plan: more than %d K chunks", kMaxChunks);
-      pl->chunks[n++] = Chunk{src, j * 64, s.terms == 3 ? 1 : 0, s.terms >= 2 ? 1 : 0};
+      pl->chunks[n++] = Chunk{src, j * 64, s.terms == 3 ? 1 : 0, spl ? 1 : 0};
     }
     if (s.terms == 3)
       for (int j = 0; j * 64 < c; ++j) {
@@ -65,10 +72,12 @@ int make_plan(const ConvSpec& s, Plan* pl, int d_cnt = 0) {
   const int D = s.D, H = s.H, W = s.W, c0 = s.c0, c1 = s.c1, cout = s.cout, pointwise = s.kind, flags = s.flags;
   OAI_REQUIRE(D > 0 && H > 0 && W > 0 && c0 > 0 && c1 >= 0 && cout > 0, "conv plan: bad dims");
   OAI_REQUIRE(c0 % 8 == 0 && c1 % 8 == 0, "conv plan: channel counts must be multiples of 8 (got %d,%d)", c0, c1);
-  OAI_REQUIRE(s.terms >= 1 && s.terms <= 3, "conv plan: terms=%d (1 = 16-bit, 2 = split activations, 3 = split both)",
-              s.terms);
-  OAI_REQUIRE(s.terms == 1 || (s.split0 && (c1 == 0 || s.split1)),
-              "conv plan: terms=%d needs sources stored as [hi | lo] planes", s.terms);
+  OAI_REQUIRE(s.terms >= 1 && s.terms <= 5,
+              "conv plan: terms=%d (1 = 16-bit, 2 = split activations, 3 = split both, 4 / 5 = split the second / first "
+              "source's activations only)", s.terms);
+  OAI_REQUIRE((!split_src(s.terms, 0) || s.split0) && (!split_src(s.terms, 1) || c1 == 0 || s.split1),
+              "conv plan: terms=%d needs the split sources stored as [hi | lo] planes", s.terms);
+  OAI_REQUIRE(s.terms < 4 || c1 > 0, "conv plan: terms=%d is for two-source layers", s.terms);
   OAI_REQUIRE((!s.split0 || c0 % 32 == 0) && (!s.split1 || c1 % 64 == 0) && (c1 == 0 || c0 % 64 == 0),
               "conv plan: split / concatenated sources need 64-channel multiples (got %d,%d)", c0, c1);
   pl->TW = W < 128 ? W : 128;
@@ -92,7 +101,7 @@ int make_plan(const ConvSpec& s, Plan* pl, int d_cnt = 0) {
   pl->Rd = R;
   pl->up_groups = 1;
   if (build_chunks(s, pl)) return 1;
-  const int c0v = s.terms >= 2 ? 2 * c0 : c0;  // channels the first source's chunks run over
+  const int c0v = split_src(s.terms, 0) ? 2 * c0 : c0;  // channels the first source's chunks run over
   pl->k16 = (c1 == 0 && c0v <= 32) ? (c0v <= 16 ? 1 : 2) : 4;
   // a single 32-channel source keeps 64-byte rows (SWIZZLE_64B): half the TMA / shared-memory bytes per voxel
   pl->row_bytes = (c1 == 0 && c0v == 32 && !(flags & kFlagWideRows)) ? 64 : 128;

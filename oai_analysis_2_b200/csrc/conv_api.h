@@ -15,6 +15,7 @@ struct ConvSpec {
   int cout;
   int kind;            // 0 = 3x3x3 p1, 1 = 1x1x1, 2 = ConvTranspose3d(k2,s2)
   int terms;           // 1: a*w (16-bit operands) | 2: (a_hi + a_lo)*w | 3: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+                       // 4 / 5: as 2, but only source 1 / only source 0 is read as hi + lo
   int fmt;             // 0 fp16, 1 bf16
   int flags;
 };

@@ -201,37 +201,86 @@ __device__ __forceinline__ void head_dot(const uint32_t (&v)[32], uint32_t sbias
 }
 
 
-// The MMA-issuing warp's whole loop.  NKW / K16N / PER > 0: compile-time (kw taps per A stage, K=16 steps per chunk,
-// accumulators one MMA may span = 256 / cout) fast path; <0, 0, 0>: the general path (debug / A-B flags, uncommon
-// shapes) with run-time trip counts and descriptors rebuilt per MMA.  The whole warp walks the (warp-uniform) schedule so
-// the compiler keeps the descriptor arithmetic in uniform registers; one lane, elected once, issues every tcgen05.mma /
-// tcgen05.commit.  The single thread that feeds the tensor pipe is the critical resource of the kernel (ncu source
-// counters, profiles/r02_ncu_ec1_issuer.txt: ~150 instructions per A stage outside the polling loops against 6 x 96
-// clocks of MMAs for a 32-channel stage), so the steady state -- every accumulator of the unit already holds partial
-// sums, which is every stage after the unit's first weight block -- is a separate loop body of descriptor adds only.
+// ---------------------------------------------------------------------------------------------- MMA issue
+// The single thread that feeds the tensor pipe is the critical resource of the kernel: a lone warp retires one
+// instruction every ~7 clocks (dependent integer chains, branch resolution; ncu source counters of the ec1 launch,
+// profiles/r02_ncu_ec1_issuer.txt), so every instruction of the per-stage loop costs more than one K=16 step of a
+// small MMA is worth.  Two loops therefore exist:
+//   * mma_issuer_fast<NKW, K16N, PER>: compile-time (kw taps per A stage, K=16 steps per chunk, accumulators one MMA may
+//     span = 256 / cout); per stage it does one mbarrier poll, five integer ops for the accumulator span, descriptor
+//     adds and the MMAs; accumulators seeing their first MMA of the unit (first weight block) take a short side path;
+//   * mma_issuer_general: run-time trip counts and descriptors rebuilt per MMA (debug / A-B flags, uncommon shapes).
+// The whole warp walks the (warp-uniform) schedule so the compiler keeps the descriptor arithmetic in uniform
+// registers; one lane, elected once, issues every tcgen05.mma / tcgen05.commit.
+struct IssueConsts {
+  uint32_t kw_step, b_kw, desc_hi32, idesc_1, idesc_step, tap16, cout;
+};
+
+// every (kw, k16) step of one A stage onto the accumulators [d_addr, +nt*cout), all accumulating; skip_first leaves out
+// the (0, 0) step (already issued by issue_first with per-accumulator overwrite flags)
 template <int NKW, int K16N, int PER>
-__device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint32_t tmem_base, uint8_t* abuf,
-                                           uint8_t* wbuf, const uint32_t wstride, uint64_t* full_a, uint64_t* empty_a,
-                                           uint64_t* full_w, uint64_t* empty_w, uint64_t* acc_full,
-                                           uint64_t* acc_empty) {
-  constexpr bool kFast = NKW > 0;
-  const int mode = p.mode, R_acc = p.R, cout = p.cout, nblk = p.nblk, nst = p.n_astage, nwb = p.n_wbuf, Dm1 = p.D - 1,
-            kpb = p.kd_per_block;
-  const int nkw = kFast ? NKW : ((mode == kModeRowShared) ? 3 : 1);
-  const int k16n = kFast ? K16N : p.k16_steps;
+__device__ __forceinline__ void issue_stage(const IssueConsts& c, uint32_t d_addr, uint32_t a_lo, uint32_t b_lo, int nt,
+                                            bool skip_first) {
+  for (int g0 = 0; g0 < nt; g0 += PER) {
+    const int ng = min(PER, nt - g0);
+    const uint32_t idesc = c.idesc_1 + static_cast<uint32_t>(ng - 1) * c.idesc_step;
+    const uint32_t d = d_addr + static_cast<uint32_t>(g0) * c.cout;
+    const uint32_t bl = b_lo + static_cast<uint32_t>(g0) * c.tap16;
+#pragma unroll
+    for (int kw = 0; kw < NKW; ++kw)
+#pragma unroll
+      for (int k16 = 0; k16 < K16N; ++k16) {
+        if (kw == 0 && k16 == 0) {
+          if (!skip_first) umma_f16_ss_lohi(d, a_lo, bl, c.desc_hi32, idesc, 1u);
+        } else {
+          umma_f16_ss_lohi(d, a_lo + kw * c.kw_step + k16 * 2, bl + kw * c.b_kw + k16 * 2, c.desc_hi32, idesc, 1u);
+        }
+      }
+  }
+}
+
+// the (kw = 0, k16 = 0) step of a stage whose span [acc0, acc0 + nt) holds partial sums below accumulator f0 and is
+// fresh (first MMA of the unit: overwrite) from f0 on
+template <int PER>
+__device__ __forceinline__ void issue_first(const IssueConsts& c, uint32_t tmem_base, int acc0, int nt, int f0,
+                                            uint32_t a_lo, uint32_t b_lo) {
+  for (int g0 = 0; g0 < nt; g0 += PER) {
+    const int ng = min(PER, nt - g0);
+    const int ag = acc0 + g0;
+    const int keep = min(max(f0 - ag, 0), ng);  // leading accumulators of the group that accumulate
+    const uint32_t bl = b_lo + static_cast<uint32_t>(g0) * c.tap16;
+    if (keep > 0)
+      umma_f16_ss_lohi(tmem_base + static_cast<uint32_t>(ag) * c.cout, a_lo, bl, c.desc_hi32,
+                       c.idesc_1 + static_cast<uint32_t>(keep - 1) * c.idesc_step, 1u);
+    if (keep < ng)
+      umma_f16_ss_lohi(tmem_base + static_cast<uint32_t>(ag + keep) * c.cout, a_lo,
+                       bl + static_cast<uint32_t>(keep) * c.tap16, c.desc_hi32,
+                       c.idesc_1 + static_cast<uint32_t>(ng - keep - 1) * c.idesc_step, 0u);
+  }
+}
+
+template <int NKW, int K16N, int PER>
+__device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const uint32_t tmem_base, uint8_t* abuf,
+                                                uint8_t* wbuf, const uint32_t wstride, uint64_t* full_a,
+                                                uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
+                                                uint64_t* acc_full, uint64_t* acc_empty) {
+  const int mode = p.mode, R_acc = p.R, nblk = p.nblk, nst = p.n_astage, nwb = p.n_wbuf, Dm1 = p.D - 1;
   const uint32_t rowb = static_cast<uint32_t>(p.row_bytes), sbo = 8u * rowb, lay = rowb == 128u ? 2u : 4u;
-  const uint32_t cout128 = static_cast<uint32_t>(cout) * rowb;    // bytes of one tap's weight rows
-  const uint32_t tap16 = cout128 >> 4;                             // ... in descriptor units
-  const uint32_t kw_step = rowb >> 4;                              // descriptor units per one-voxel row shift
-  const uint32_t desc_hi32 = (sbo >> 4) | (1u << 14) | (lay << 29);  // SBO, version = 1, swizzle mode
+  IssueConsts c;
+  c.cout = static_cast<uint32_t>(p.cout);
+  c.tap16 = (c.cout * rowb) >> 4;                               // one tap's weight rows, in descriptor units
+  c.kw_step = rowb >> 4;                                        // descriptor units per one-voxel row shift
+  c.desc_hi32 = (sbo >> 4) | (1u << 14) | (lay << 29);          // SBO, version = 1, swizzle mode
+  c.idesc_1 = umma_idesc_f16(128, c.cout, p.ab_format);
+  c.idesc_step = (c.cout >> 3) << 17;                           // +1 tap in the N field
   const uint32_t a_lo0 = ((smem_u32(abuf) & 0x3FFFF) >> 4) | (1u << 16), a_step = p.astage_stride >> 4;
   const uint32_t w_lo0 = ((smem_u32(wbuf) & 0x3FFFF) >> 4) | (1u << 16), w_step = wstride >> 4;
-  const int per = kFast ? PER : max(1, 256 / cout);
-  const uint32_t idesc_1 = umma_idesc_f16(128, static_cast<uint32_t>(cout), p.ab_format);
-  const uint32_t idesc_step = static_cast<uint32_t>(cout >> 3) << 17;  // +1 tap in the N field
   const bool up2 = mode == kModeUp2;
   const bool one_kd = mode == kModePointwise || up2;
-  const bool kd_cycle = mode == kModePerTap && kpb == 1;
+  const bool kd_cycle = mode == kModePerTap && p.kd_per_block == 1;
+  const int ns = up2 ? R_acc : ((one_kd || kd_cycle) ? 1 : 3);  // taps stacked along N in every weight block
+  const int a_inc = up2 ? 0 : 1;
+  c.b_kw = static_cast<uint32_t>(ns) * c.tap16;
   const bool leader = elect_one();
   int stage = 0, wb = 0;
   uint32_t aphase = 0, wphase = 0, use_bits = 0;  // use_bits: per-accumulator mbarrier phase (flips per use)
@@ -243,123 +292,41 @@ __device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint3
     uint32_t touched = 0, signaled = 0;
     int kd_it = 0;  // kd counter of the one-kd-per-block schedule (fastest block index there)
     for (int b = 0; b < nblk; ++b) {
-      // taps stacked in this block and the input slices it walks (same arithmetic as decode_block, by counters)
-      int kdlo = 0, nkd = 3;
-      if (one_kd) { kdlo = 1; nkd = 1; }
-      else if (kd_cycle) { kdlo = kd_it; nkd = 1; kd_it = kd_it == 2 ? 0 : kd_it + 1; }
-      const int ns = up2 ? R_acc : nkd;
-      const int kdhi = kdlo + nkd - 1;
+      int kdlo = 0, kdhi = 2;
+      if (one_kd) { kdlo = 1; kdhi = 1; }
+      else if (kd_cycle) { kdlo = kdhi = kd_it; kd_it = kd_it == 2 ? 0 : kd_it + 1; }
       const int dlo = max(0, d0 + kdlo - 1);
       const int dhi = min(Dm1, d0 + rd - 1 + kdhi - 1);
       const bool last_blk = b == nblk - 1;
       mbar_wait(&full_w[wb], wphase, 300 + wb);
       const uint32_t w_lo = w_lo0 + static_cast<uint32_t>(wb) * w_step;
-      const uint32_t b_kw = static_cast<uint32_t>(ns) * tap16;
       int a_first = up2 ? 0 : dlo - kdhi + 1 - d0;  // accumulator hit by the first stacked tap
-      for (int dp = dlo; dp <= dhi; ++dp, a_first += (up2 ? 0 : 1)) {
+      for (int dp = dlo; dp <= dhi; ++dp, a_first += a_inc) {
         mbar_wait(&full_a[stage], aphase, 400 + stage);
         tc_fence_after();
         const int acc0 = max(a_first, 0);
-        const int ti_lo = acc0 - a_first;
-        const int nt = min(ns - 1, ra - 1 - a_first) - ti_lo + 1;
-        uint32_t fresh = 0;
+        const int acc1 = min(a_first + ns - 1, ra - 1);
+        const int nt = acc1 - acc0 + 1;
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc0) * c.cout;
+        const uint32_t b_lo = w_lo + static_cast<uint32_t>(acc0 - a_first) * c.tap16;
+        int f0 = -1;
         if (touched != all_acc) {
-          const uint32_t span = ((1u << nt) - 1u) << acc0;
-          fresh = span & ~touched;
+          // first weight block of the unit (and, in the one-kd schedule at the volume's first slice, the second):
+          // accumulators seeing their first MMA wait until the epilogue has drained their previous contents
+          const uint32_t span = ((2u << (acc1 - acc0)) - 1u) << acc0;
+          const uint32_t fresh = span & ~touched;
           touched |= span;
-        }
-        if (kFast && fresh == 0) {
-          // steady state: every accumulator of the span already holds partial sums
-          const uint32_t d_addr0 = tmem_base + static_cast<uint32_t>(acc0 * cout);
-          const uint32_t b_lo0 = w_lo + static_cast<uint32_t>(ti_lo) * tap16;
-          if (leader) {
-#pragma unroll
-            for (int g0 = 0; g0 < 8; g0 += (kFast ? PER : 1)) {
-              if (g0 < nt) {
-                const int ng = min(kFast ? PER : 1, nt - g0);
-                const uint32_t idesc = idesc_1 + static_cast<uint32_t>(ng - 1) * idesc_step;
-                const uint32_t d_addr = d_addr0 + static_cast<uint32_t>(g0 * cout);
-                const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g0) * tap16;
-#pragma unroll
-                for (int kw = 0; kw < (kFast ? NKW : 1); ++kw)
-#pragma unroll
-                  for (int k16 = 0; k16 < (kFast ? K16N : 1); ++k16)
-                    umma_f16_ss_lohi(d_addr, a_lo + kw * kw_step + k16 * 2, b_lo + kw * b_kw + k16 * 2, desc_hi32,
-                                     idesc, 1u);
-              }
-            }
-          }
-        } else if (kFast) {
-          // accumulators seeing their first MMA of the unit: wait until the epilogue has drained their previous
-          // contents; their very first issue (kw = 0, k16 = 0) overwrites instead of accumulating
-          for (int a = acc0; a < acc0 + nt; ++a)
-            if ((fresh >> a) & 1u) mbar_wait(&acc_empty[a], ((use_bits >> a) & 1u) ^ 1u, 500 + a);
-          tc_fence_after();
-          for (int g0 = 0; g0 < nt; g0 += per) {
-            const int ng = min(per, nt - g0);
-            const uint32_t idesc = idesc_1 + static_cast<uint32_t>(ng - 1) * idesc_step;
-            const uint32_t d_addr = tmem_base + static_cast<uint32_t>((acc0 + g0) * cout);
-            const uint32_t b_lo = w_lo + static_cast<uint32_t>(ti_lo + g0) * tap16;
-            const uint32_t gfresh = (fresh >> (acc0 + g0)) & ((1u << ng) - 1u);
-            if (leader) {
-              if (gfresh) {
-                int j = 0;  // first issue of the group, split into runs of equal state
-                while (j < ng) {
-                  const uint32_t f = (gfresh >> j) & 1u;
-                  int len = 1;
-                  while (j + len < ng && ((gfresh >> (j + len)) & 1u) == f) ++len;
-                  umma_f16_ss_lohi(d_addr + static_cast<uint32_t>(j * cout), a_lo,
-                                   b_lo + static_cast<uint32_t>(j) * tap16, desc_hi32,
-                                   idesc_1 + static_cast<uint32_t>(len - 1) * idesc_step, f ? 0u : 1u);
-                  j += len;
-                }
-              }
-#pragma unroll
-              for (int kw = 0; kw < (kFast ? NKW : 1); ++kw)
-#pragma unroll
-                for (int k16 = 0; k16 < (kFast ? K16N : 1); ++k16)
-                  if (!(gfresh && kw == 0 && k16 == 0))
-                    umma_f16_ss_lohi(d_addr, a_lo + kw * kw_step + k16 * 2, b_lo + kw * b_kw + k16 * 2, desc_hi32,
-                                     idesc, 1u);
-            }
-          }
-        } else {
-          // general path: one group per run of equal accumulator state, descriptors rebuilt per MMA
-          const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
-          const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
-          const int ti_hi = ti_lo + nt - 1;
-          for (int kw = 0; kw < nkw; ++kw) {
-            int ti = ti_lo;
-            while (ti <= ti_hi) {
-              const int a0 = a_first + ti;
-              const uint32_t f = ((fresh >> a0) & 1u) ^ 1u;   // 1: holds partial sums (of this unit) already
-              int len = 1;
-              while (ti + len <= ti_hi && ((((fresh >> (a0 + len)) & 1u) ^ 1u) == f) && (len + 1) * cout <= 256) ++len;
-              if (!f) {
-                for (int j = 0; j < len; ++j)
-                  mbar_wait(&acc_empty[a0 + j], ((use_bits >> (a0 + j)) & 1u) ^ 1u, 500 + a0 + j);
-                tc_fence_after();
-              }
-              const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * cout), p.ab_format);
-              const uint32_t a_addr = a_base + static_cast<uint32_t>(kw) * rowb;
-              const uint32_t b_addr = w_base + static_cast<uint32_t>(kw * ns + ti) * cout128;
-              const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
-              const uint32_t d_addr = tmem_base + static_cast<uint32_t>(a0 * cout);
-              if (leader) {
-                for (int k16 = 0; k16 < k16n; ++k16) {
-                  const uint64_t adesc = umma_desc_kmajor(a_addr + k16 * 32, sbo, boff, lay);
-                  const uint64_t bdesc = umma_desc_kmajor(b_addr + k16 * 32, sbo, 0, lay);
-                  umma_f16_ss(d_addr, adesc, bdesc, idesc, (f | (k16 > 0)) ? 1u : 0u);
-                }
-              }
-              ti += len;
-            }
-            fresh = 0;  // after kw = 0 every accumulator of the span accumulates
+          if (fresh) {
+            f0 = __ffs(fresh) - 1;  // the fresh accumulators are always the top of the span
+            for (int a = f0; a <= acc1; ++a) mbar_wait(&acc_empty[a], ((use_bits >> a) & 1u) ^ 1u, 500 + a);
+            tc_fence_after();
           }
         }
-        // release the A stage; the last block's last tap of an accumulator also publishes it to the epilogue
         const bool publish = last_blk && a_first >= 0 && a_first < ra;
         if (leader) {
+          if (f0 >= 0) issue_first<PER>(c, tmem_base, acc0, nt, f0, a_lo, b_lo);
+          issue_stage<NKW, K16N, PER>(c, d_addr, a_lo, b_lo, nt, f0 >= 0);
+          // release the A stage; the last block's last tap of an accumulator also publishes it to the epilogue
           umma_commit(&empty_a[stage]);
           if (publish) umma_commit(&acc_full[a_first]);
         }
@@ -369,6 +336,103 @@ __device__ __forceinline__ void mma_issuer(const ConvIgemmParams& p, const uint3
           stage = 0;
           aphase ^= 1u;
           a_lo = a_lo0;
+        }
+      }
+      if (leader) umma_commit(&empty_w[wb]);
+      if (++wb == nwb) {
+        wb = 0;
+        wphase ^= 1u;
+      }
+    }
+    if (leader && signaled != all_acc) {
+      for (int a = 0; a < ra; ++a)
+        if (!((signaled >> a) & 1u)) umma_commit(&acc_full[a]);
+    }
+    use_bits ^= all_acc;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void mma_issuer_general(const ConvIgemmParams& p, const uint32_t tmem_base, uint8_t* abuf,
+                                                   uint8_t* wbuf, const uint32_t wstride, uint64_t* full_a,
+                                                   uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
+                                                   uint64_t* acc_full, uint64_t* acc_empty) {
+  const int mode = p.mode, R_acc = p.R, cout = p.cout, nblk = p.nblk, nst = p.n_astage, nwb = p.n_wbuf, Dm1 = p.D - 1,
+            kpb = p.kd_per_block;
+  const int nkw = (mode == kModeRowShared) ? 3 : 1;
+  const int k16n = p.k16_steps;
+  const uint32_t rowb = static_cast<uint32_t>(p.row_bytes), sbo = 8u * rowb, lay = rowb == 128u ? 2u : 4u;
+  const uint32_t cout128 = static_cast<uint32_t>(cout) * rowb;    // bytes of one tap's weight rows
+  const bool up2 = mode == kModeUp2;
+  const bool leader = elect_one();
+  int stage = 0, wb = 0;
+  uint32_t aphase = 0, wphase = 0, use_bits = 0;  // use_bits: per-accumulator mbarrier phase (flips per use)
+  for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+    const UnitInfo ui = decode_unit(p, u);
+    const int d0 = ui.d0, ra = ui.ra, rd = ui.rd;
+    const uint32_t all_acc = (1u << ra) - 1u;
+    uint32_t touched = 0, signaled = 0;
+    int kd_it = 0;  // kd counter of the one-kd-per-block schedule (fastest block index there)
+    for (int b = 0; b < nblk; ++b) {
+      // taps stacked in this block and the input slices it walks (same arithmetic as decode_block, by counters)
+      int kdlo = 0, nkd = 3;
+      if (mode == kModePointwise || up2) { kdlo = 1; nkd = 1; }
+      else if (mode == kModePerTap && kpb == 1) { kdlo = kd_it; nkd = 1; kd_it = kd_it == 2 ? 0 : kd_it + 1; }
+      const int ns = up2 ? R_acc : nkd;
+      const int kdhi = kdlo + nkd - 1;
+      const int dlo = max(0, d0 + kdlo - 1);
+      const int dhi = min(Dm1, d0 + rd - 1 + kdhi - 1);
+      const bool last_blk = b == nblk - 1;
+      mbar_wait(&full_w[wb], wphase, 300 + wb);
+      int a_first = up2 ? 0 : dlo - kdhi + 1 - d0;  // accumulator hit by the first stacked tap
+      for (int dp = dlo; dp <= dhi; ++dp, a_first += (up2 ? 0 : 1)) {
+        mbar_wait(&full_a[stage], aphase, 400 + stage);
+        tc_fence_after();
+        const int acc0 = max(a_first, 0);
+        const int ti_lo = acc0 - a_first;
+        const int nt = min(ns - 1, ra - 1 - a_first) - ti_lo + 1;
+        // one group per run of equal accumulator state, descriptors rebuilt per MMA
+        const uint32_t a_base = smem_u32(abuf + static_cast<size_t>(stage) * p.astage_stride);
+        const uint32_t w_base = smem_u32(wbuf + static_cast<size_t>(wb) * wstride);
+        const int ti_hi = ti_lo + nt - 1;
+        for (int kw = 0; kw < nkw; ++kw) {
+          int ti = ti_lo;
+          while (ti <= ti_hi) {
+            const int a0 = a_first + ti;
+            const uint32_t f = (touched >> a0) & 1u;
+            int len = 1;
+            while (ti + len <= ti_hi && ((touched >> (a0 + len)) & 1u) == f && (len + 1) * cout <= 256) ++len;
+            if (!f) {
+              for (int j = 0; j < len; ++j)
+                mbar_wait(&acc_empty[a0 + j], ((use_bits >> (a0 + j)) & 1u) ^ 1u, 500 + a0 + j);
+              tc_fence_after();
+            }
+            const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(len * cout), p.ab_format);
+            const uint32_t a_addr = a_base + static_cast<uint32_t>(kw) * rowb;
+            const uint32_t b_addr = w_base + static_cast<uint32_t>(kw * ns + ti) * cout128;
+            const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
+            const uint32_t d_addr = tmem_base + static_cast<uint32_t>(a0 * cout);
+            if (leader) {
+              for (int k16 = 0; k16 < k16n; ++k16) {
+                const uint64_t adesc = umma_desc_kmajor(a_addr + k16 * 32, sbo, boff, lay);
+                const uint64_t bdesc = umma_desc_kmajor(b_addr + k16 * 32, sbo, 0, lay);
+                umma_f16_ss(d_addr, adesc, bdesc, idesc, (f | (k16 > 0)) ? 1u : 0u);
+              }
+            }
+            touched |= ((1u << len) - 1u) << a0;
+            ti += len;
+          }
+        }
+        // release the A stage; the last block's last tap of an accumulator also publishes it to the epilogue
+        const bool publish = last_blk && a_first >= 0 && a_first < ra;
+        if (leader) {
+          umma_commit(&empty_a[stage]);
+          if (publish) umma_commit(&acc_full[a_first]);
+        }
+        if (publish) signaled |= 1u << a_first;
+        if (++stage == nst) {
+          stage = 0;
+          aphase ^= 1u;
         }
       }
       if (leader) umma_commit(&empty_w[wb]);
@@ -439,8 +503,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int nkw = (p.mode == kModeRowShared) ? 3 : 1;
-
   if (warp == 0) {
     // ------------------------------------------------------------ activation producer
     if (lane == 0) {
@@ -499,14 +561,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     const int nkw_rt = (p.mode == kModeRowShared) ? 3 : 1;
     const int per_rt = max(1, 256 / p.cout);
 #define OAI_ISSUE(NKW, K16N, PER) \
-  mma_issuer<NKW, K16N, PER>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty)
-    if (general) OAI_ISSUE(0, 0, 0);
+  mma_issuer_fast<NKW, K16N, PER>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty)
+#define OAI_ISSUE_GENERAL() \
+  mma_issuer_general(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty)
+    if (general) OAI_ISSUE_GENERAL();
     else if (nkw_rt == 3 && p.k16_steps == 4 && per_rt == 4) OAI_ISSUE(3, 4, 4);
     else if (nkw_rt == 3 && p.k16_steps == 2 && per_rt == 4) OAI_ISSUE(3, 2, 4);
     else if (nkw_rt == 1 && p.k16_steps == 4 && per_rt == 4) OAI_ISSUE(1, 4, 4);
     else if (nkw_rt == 1 && p.k16_steps == 4 && per_rt == 2) OAI_ISSUE(1, 4, 2);
     else if (nkw_rt == 1 && p.k16_steps == 4 && per_rt == 1) OAI_ISSUE(1, 4, 1);
-    else OAI_ISSUE(0, 0, 0);
+    else OAI_ISSUE_GENERAL();
+#undef OAI_ISSUE_GENERAL
 #undef OAI_ISSUE
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue

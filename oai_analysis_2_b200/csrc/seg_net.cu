@@ -203,10 +203,11 @@ extern "C" int oai_seg_layer_terms(int precision, int* terms17) {
               "seg_layer_terms: unknown precision %d", precision);
   for (int l = 0; l < kNumLayers; ++l) terms17[l] = 1;
   if (precision == OAI_SEG_PRECISION_MIXED) {
-    // the two full-resolution decoder layers read their inputs as fp16 hi + lo pairs: their activation rounding is what
-    // reaches the logits undamped (scripts/sim_precision.py); everything upstream keeps 16-bit operands
+    // dc2 (192 -> 64 at full resolution, 31 % of the network's MACs) reads both its inputs as fp16 hi + lo pairs: the
+    // rounding of its input activations is the largest single contribution to the logit error (scripts/dice_plans.py
+    // on the golden fixtures, profiles/r02_dice_plans.jsonl: mask flips 28 -> 12 over the three fixtures, minimum Dice
+    // 0.99881 -> 0.99965; splitting dc1 as well changes no Dice on the hardest fixture and costs 5 ms per knee)
     terms17[DC2] = 2;
-    terms17[DC1] = 2;
   } else if (precision == OAI_SEG_PRECISION_FP16X2 || precision == OAI_SEG_PRECISION_FP16X3) {
     for (int l = 1; l < kNumLayers; ++l) terms17[l] = precision == OAI_SEG_PRECISION_FP16X2 ? 2 : 3;
   }
@@ -248,14 +249,19 @@ extern "C" int oai_seg_create(const oai_seg_config* cfg, const oai_tensor* state
   if (cfg->precision == OAI_SEG_PRECISION_CUSTOM) {
     for (int l = 0; l < kNumLayers; ++l) {
       h->terms[l] = l == 0 ? 1 : cfg->layer_terms[l];
-      OAI_REQUIRE(h->terms[l] >= 1 && h->terms[l] <= 3, "seg_create: layer_terms[%d]=%d", l, h->terms[l]);
+      OAI_REQUIRE(h->terms[l] >= 1 && h->terms[l] <= 5 && (h->terms[l] < 4 || kLayers[l].c_first > 0),
+                  "seg_create: layer_terms[%d]=%d", l, h->terms[l]);
     }
   } else if (oai_seg_layer_terms(cfg->precision, h->terms)) {
     return 1;
   }
   for (int t = 0; t < kNumTensors; ++t) {
+    // a tensor carries [hi | lo] planes when the layer reading it splits that source (terms 4 / 5: only the skip / only
+    // the upsampled source of a concatenating layer)
     const int c = kTensors[t].consumers[0];
-    h->split[t] = c >= 0 && h->terms[c] >= 2;
+    const bool is_skip = t == T_SYN0 || t == T_SYN1 || t == T_SYN2;
+    const int tm = c >= 0 ? h->terms[c] : 1;
+    h->split[t] = tm == 2 || tm == 3 || (tm == 4 && is_skip) || (tm == 5 && !is_skip);
   }
   for (int i = 0; i < 3; ++i)   // a skip tensor must also carry both planes when its pooled consumer wants them
     if (h->split[kPoolOf[i][1]]) h->split[kPoolOf[i][0]] = 1;
@@ -331,8 +337,8 @@ extern "C" int oai_seg_create(const oai_seg_config* cfg, const oai_tensor* state
     s.flags = 0;
     s.split0 = s.split1 = 0;   // filled per launch from the tensors actually bound
     ConvSpec ps = s;            // the packer only needs the terms' split pattern
-    ps.split0 = s.terms > 1;
-    ps.split1 = s.terms > 1 && s.c1 > 0;
+    ps.split0 = s.terms == 2 || s.terms == 3 || s.terms == 5;
+    ps.split1 = (s.terms == 2 || s.terms == 3 || s.terms == 4) && s.c1 > 0;
     P.w_bytes = conv_wpack_bytes(ps);
     OAI_REQUIRE(P.w_bytes > 0, "seg_create: layer %s: %s", L.name, oai_last_error());
     std::vector<uint8_t> img(P.w_bytes);

@@ -8,8 +8,11 @@ inner / outer cartilage surfaces and their thickness, without the host round tri
     get_thickness_mesh     the three above
 
 Meshes are (verts float32 [n,3] x,y,z * spacing, faces int32 [m,3]) device tensors.  The arithmetic runs in
-liboai_b200 (csrc/mesh.cu, csrc/mesh_post.cu); this file is the reference's control flow around it.  Not built:
-atlas attribute mapping / 2-D projection / mesh IO (§8f-4)."""
+liboai_b200 (csrc/mesh.cu, csrc/mesh_post.cu, csrc/mesh_map.cu); this file is the reference's control flow around it.
+
+    map_attributes         thickness of a subject's mesh -> the atlas mesh's vertices (§8f-4)
+    project_thickness      2-D unrolling of the mapped thickness (femoral: cylinder; tibial: per-plateau PCA)
+Mesh / image file formats: oai_analysis_2_b200/io.py."""
 import numpy as np
 import torch
 
@@ -134,3 +137,49 @@ def get_thickness_mesh(itk_image, mesh_type="FC", num_iterations=150, device="cu
     inner, outer = split_mesh(verts, faces, mesh_type)
     d_in, d_out = get_distance(inner, outer)
     return dict(inner=(inner[0], inner[1], d_in), outer=(outer[0], outer[1], d_out))
+
+
+# ---------------------------------------------------------------------------------------------- §8f-4
+MAP_RADIUS = 1.0   # vtkPointInterpolator's default vtkLinearKernel: footprint RADIUS, Radius = 1.0
+
+
+def map_attributes(source_mesh, target_mesh, radius=MAP_RADIUS):
+    """mesh_processing.py:398-406.  source_mesh = (verts, faces, attr) with attr float32 [n] or [n,k]; target_mesh =
+    (verts, faces[, ...]).  Returns (target verts, target faces, mapped attr): the atlas geometry carrying, at every
+    vertex, the mean of the source attribute within `radius` (the closest source vertex's where none is in range)."""
+    sv, sa = source_mesh[0], source_mesh[2]
+    tv, tf = target_mesh[0], target_mesh[1]
+    return tv, tf, ops.map_attributes(sv, sa, tv, radius)
+
+
+def compute_least_square_circle(x, y):
+    """mesh_processing.py:409-443 on device coordinates x, y [n]: ((xc, yc), R)."""
+    pts = torch.stack((x.float(), y.float(), torch.zeros_like(x, dtype=torch.float32)), dim=1)
+    center, radius, _ = ops.circle_fit(pts, 0, 1)
+    return center, radius
+
+
+def get_cylinder(verts):
+    """mesh_processing.py:447-451: ((center, r), (z_min, z_max)) of a cylinder along z through the vertices' x,y."""
+    center, radius, _ = ops.circle_fit(verts, 0, 1)
+    return (center, radius), (float(verts[:, 2].min()), float(verts[:, 2].max()))
+
+
+def project_thickness(mapped_mesh, mesh_type="FC"):
+    """mesh_processing.py:481-534 -> (x, y, thickness) device tensors (float64 coordinates like the reference's numpy).
+
+    FC: the reference swaps the vertices' x and y, fits a circle to them and returns (polar angle, z, thickness).
+    TC: vertices are split at z = 50 into the two plateaus, each flattened by a linear KernelPCA to 2-D, rotated by
+    -50 / -160 degrees, the right one mirrored in x and lifted by 50; output order [right plateau; left plateau]."""
+    verts, attr = mapped_mesh[0].contiguous().float(), mapped_mesh[2]
+    if mesh_type == "FC":
+        # after the swap the circle is fitted to (old y, old x): coordinate selectors instead of a copy
+        center, _, _ = ops.circle_fit(verts, 1, 0)
+        angle, height = ops.cylinder_project(verts, 1, 0, 2, center)
+        return angle, height, attr
+    z = verts[:, 2]
+    left = torch.nonzero(z < 50).flatten().to(torch.int32)
+    right = torch.nonzero(z >= 50).flatten().to(torch.int32)
+    lx, ly = ops.pca2_project(verts, left, -50.0, False, (0.0, 0.0))
+    rx, ry = ops.pca2_project(verts, right, -160.0, True, (0.0, 50.0))
+    return (torch.cat((rx, lx)), torch.cat((ry, ly)), torch.cat((attr[right.long()], attr[left.long()])))

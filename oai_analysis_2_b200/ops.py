@@ -5,7 +5,7 @@ import math
 import numpy as np
 import torch
 
-from ._lib import c_float, c_int, c_ll, c_size, check, lib, ptr, stream_ptr
+from ._lib import c_double, c_float, c_int, c_ll, c_size, check, lib, ptr, stream_ptr
 
 FLAG_FORCE_PER_TAP = 1
 FLAG_BASE_OFF_FORMULA = 2
@@ -524,3 +524,56 @@ def kmeans2(features, max_iter=300):
     check(lib.oai_kmeans2(ptr(x), c_ll(n), int(dim), int(max_iter), ptr(labels), ptr(ws), c_size(nbytes),
                           ctypes.byref(it), stream_ptr()), "kmeans2")
     return labels, int(it.value)
+
+
+def map_attributes(source_points, source_attr, target_points, radius=1.0):
+    """vtkPointInterpolator(linear kernel, radius) + closest-point null strategy: float32 [n_target(, k)]."""
+    sp, tp = source_points.contiguous().float(), target_points.contiguous().float()
+    a = source_attr.contiguous().float()
+    k = 1 if a.dim() == 1 else int(a.shape[1])
+    out = torch.empty((tp.shape[0],) + tuple(a.shape[1:]), dtype=torch.float32, device=tp.device)
+    check(lib.oai_mesh_map_attributes(ptr(sp), ptr(a), c_ll(int(sp.shape[0])), k, ptr(tp), c_ll(int(tp.shape[0])),
+                                      c_float(float(radius)), ptr(out), stream_ptr()), "mesh_map_attributes")
+    return out
+
+
+def _project_ws(device):
+    return torch.empty(int(lib.oai_mesh_project_workspace_bytes()), dtype=torch.uint8, device=device)
+
+
+def circle_fit(points, coord_x, coord_y, index=None):
+    """Least-squares circle through coordinates (coord_x, coord_y) of points [n,3]: ((xc, yc), radius, iterations)."""
+    p = points.contiguous().float()
+    idx = None if index is None else index.contiguous().to(torch.int32)
+    n = int(p.shape[0] if idx is None else idx.shape[0])
+    center = (c_double * 2)()
+    radius, it = c_double(0.0), c_int(0)
+    ws = _project_ws(p.device)
+    check(lib.oai_circle_fit(ptr(p), ptr(idx), c_ll(n), int(coord_x), int(coord_y), center, ctypes.byref(radius),
+                             ctypes.byref(it), ptr(ws), c_size(ws.numel()), stream_ptr()), "circle_fit")
+    return (float(center[0]), float(center[1])), float(radius.value), int(it.value)
+
+
+def cylinder_project(points, coord_x, coord_y, coord_z, center):
+    """(angle, height) float64 [n]: polar angle of (p[coord_x], p[coord_y]) around center, and p[coord_z]."""
+    p = points.contiguous().float()
+    n = int(p.shape[0])
+    angle = torch.empty(n, dtype=torch.float64, device=p.device)
+    height = torch.empty(n, dtype=torch.float64, device=p.device)
+    check(lib.oai_cylinder_project(ptr(p), c_ll(n), int(coord_x), int(coord_y), int(coord_z), c_double(center[0]),
+                                   c_double(center[1]), ptr(angle), ptr(height), stream_ptr()), "cylinder_project")
+    return angle, height
+
+
+def pca2_project(points, index=None, rotate_deg=0.0, mirror_x=False, offset=(0.0, 0.0)):
+    """Linear KernelPCA(2) scores of the selected points, rotated / mirrored / offset: (x, y) float64 [n]."""
+    p = points.contiguous().float()
+    idx = None if index is None else index.contiguous().to(torch.int32)
+    n = int(p.shape[0] if idx is None else idx.shape[0])
+    ox = torch.empty(n, dtype=torch.float64, device=p.device)
+    oy = torch.empty(n, dtype=torch.float64, device=p.device)
+    ws = _project_ws(p.device)
+    check(lib.oai_pca2_project(ptr(p), ptr(idx), c_ll(n), c_double(float(rotate_deg)), int(bool(mirror_x)),
+                               c_double(float(offset[0])), c_double(float(offset[1])), ptr(ox), ptr(oy), ptr(ws),
+                               c_size(ws.numel()), stream_ptr()), "pca2_project")
+    return ox, oy

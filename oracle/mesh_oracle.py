@@ -357,3 +357,99 @@ def split_femoral(normals, centroids, bounds_min, bounds_max, num_divisions=3):
             lab = -lab
         out[idx] = lab
     return out
+
+
+# ------------------------------------------------------------------------------------------------ §8f-4
+def map_attributes(source_pts, source_attr, target_pts, radius=1.0):
+    """mesh_processing.py:398-406: vtkPointInterpolator(source -> target points) with its DEFAULT kernel and
+    SetNullPointsStrategyToClosestPoint().  vtk is not installable here; restated from the VTK sources as published:
+    the default kernel is vtkLinearKernel (a vtkGeneralizedKernel with footprint RADIUS, Radius = 1.0): the value at a
+    target point is the plain average of the source attributes at the source points within `radius` (distance <=
+    radius); a target point with no source point in range is a "null point" and takes the attribute of the closest
+    source point.  ** parity unpinned ** (no reference test holds a mapped value).  float64, brute force."""
+    s = np.asarray(source_pts, dtype=np.float64)
+    a = np.asarray(source_attr, dtype=np.float64)
+    t = np.asarray(target_pts, dtype=np.float64)
+    a2 = a.reshape(len(s), -1)
+    out = np.empty((len(t), a2.shape[1]))
+    for i0 in range(0, len(t), 512):
+        d2 = ((t[i0:i0 + 512, None, :] - s[None, :, :]) ** 2).sum(-1)
+        inside = d2 <= radius * radius
+        cnt = inside.sum(1)
+        sums = inside.astype(np.float64) @ a2
+        near = a2[d2.argmin(1)]
+        out[i0:i0 + 512] = np.where(cnt[:, None] > 0, sums / np.maximum(cnt, 1)[:, None], near)
+    return out.reshape((len(t),) + a.shape[1:])
+
+
+def compute_least_square_circle(x, y):
+    """mesh_processing.py:409-443 verbatim in behaviour: scipy.optimize.leastsq (the reference's own call; scipy is
+    installed here, so this half IS the reference's arithmetic) on the algebraic distance to the mean circle, started
+    at the centroid, with the analytic Jacobian."""
+    from scipy import optimize
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+
+    def calc_r(xc, yc):
+        return np.sqrt((x - xc) ** 2 + (y - yc) ** 2)
+
+    def f(c):
+        r = calc_r(*c)
+        return r - r.mean()
+
+    def df(c):
+        xc, yc = c
+        r = calc_r(xc, yc)
+        d = np.empty((2, x.size))
+        d[0] = (xc - x) / r
+        d[1] = (yc - y) / r
+        return d - d.mean(axis=1)[:, None]
+
+    center, _ = optimize.leastsq(f, (x.mean(), y.mean()), Dfun=df, col_deriv=True)
+    return center, calc_r(*center).mean()
+
+
+def project_thickness_fc(verts, thickness):
+    """mesh_processing.py:489-496 (mesh_type == "FC"): swap x and y, fit the cylinder, unroll by the polar angle."""
+    v = np.array(verts, dtype=np.float32)
+    v[:, [1, 0]] = v[:, [0, 1]]
+    center, _ = compute_least_square_circle(v[:, 0], v[:, 1])
+    angle = np.arctan2(v[:, 1] - center[1], v[:, 0] - center[0])
+    return angle, v[:, 2].astype(np.float64), np.asarray(thickness), center
+
+
+def linear_kernel_pca2(points):
+    """sklearn.decomposition.KernelPCA(n_components=2, degree=3.0) as the reference calls it (mesh_processing.py:472-
+    477): the kernel defaults to "linear" (degree is ignored), so fit_transform returns the first two principal-component
+    scores of the centred points, each column signed so that its entry of largest magnitude is positive (sklearn's
+    svd_flip on the Gram matrix's eigenvectors).  Restated through the 3x3 covariance (an n x n Gram matrix of a 20 k
+    vertex half-mesh does not fit a test); tests/test_mesh_oracle.py checks it against sklearn itself on small inputs."""
+    x = np.asarray(points, dtype=np.float64)
+    xc = x - x.mean(0)
+    w, v = np.linalg.eigh(xc.T @ xc)
+    order = np.argsort(w)[::-1][:2]
+    scores = xc @ v[:, order]
+    for k in range(2):
+        j = np.argmax(np.abs(scores[:, k]))
+        if scores[j, k] < 0:
+            scores[:, k] = -scores[:, k]
+    return scores
+
+
+def _rotate_embedded(embedded, angle):
+    theta = (angle / 180.0) * np.pi
+    rot = np.array([[np.cos(theta), -np.sin(theta)], [np.sin(theta), np.cos(theta)]])
+    return np.dot(embedded, rot)
+
+
+def project_thickness_tc(verts, thickness):
+    """mesh_processing.py:497-534 (tibial): split at z = 50, PCA-flatten each plateau, rotate (-50 / -160 degrees), mirror
+    the right one, stack [right; left] with the right one lifted by 50."""
+    v = np.asarray(verts)
+    t = np.asarray(thickness)
+    left, right = np.where(v[:, 2] < 50)[0], np.where(v[:, 2] >= 50)[0]
+    el = _rotate_embedded(linear_kernel_pca2(v[left]), -50)
+    er = _rotate_embedded(linear_kernel_pca2(v[right]), -160)
+    er[:, 0] = -er[:, 0]
+    return (np.concatenate([er[:, 0], el[:, 0]]), np.concatenate([er[:, 1] + 50, el[:, 1]]),
+            np.concatenate([t[right], t[left]]))

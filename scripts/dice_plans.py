@@ -18,7 +18,7 @@ def main():
     names = ["ec0", "ec1", "ec2", "ec3", "ec4", "ec5", "ec6", "ec7", "dc9", "dc8", "dc7", "dc6", "dc5", "dc4", "dc3",
              "dc2", "dc1"]
     plans = {"fp16": {}, "dc1": {"dc1": 2}, "dc2": {"dc2": 2}, "dc1+dc2 (mixed)": {"dc1": 2, "dc2": 2},
-             "dc1 x3": {"dc1": 3}, "dc1+dc2+ec1": {"dc1": 2, "dc2": 2, "ec1": 2}, "fp16x2": {n: 2 for n in names[1:]},
+             "dc2 skip only": {"dc2": 4}, "dc2 skip + dc1": {"dc2": 4, "dc1": 2}, "dc2 up only": {"dc2": 5}, "dc1+dc2+ec1": {"dc1": 2, "dc2": 2, "ec1": 2}, "fp16x2": {n: 2 for n in names[1:]},
              "fp16x3": {n: 3 for n in names[1:]}}
     for fx in ("seg_small_pertap", "seg_small_nobn", "seg_prod_tile"):
         z, m = load_golden(fx)
