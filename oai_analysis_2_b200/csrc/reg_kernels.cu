@@ -19,6 +19,9 @@
 #include "ptx.cuh"
 #include "reg_kernels.cuh"
 
+#include <cmath>
+#include <cstdlib>
+
 namespace oai {
 
 namespace {
@@ -1281,6 +1284,19 @@ __device__ __forceinline__ void affine_apply(const Affine3& a, const double in[3
 #pragma unroll
   for (int r = 0; r < 3; ++r) out[r] = a.m[3 * r] * in[0] + a.m[3 * r + 1] * in[1] + a.m[3 * r + 2] * in[2] + a.t[r];
 }
+__device__ __forceinline__ bool affine_is_diagonal(const Affine3& a) {
+  return a.m[1] == 0.0 && a.m[2] == 0.0 && a.m[3] == 0.0 && a.m[5] == 0.0 && a.m[6] == 0.0 && a.m[7] == 0.0;
+}
+// the same map with the axis-aligned case (a third of the fp64 work) as one fused multiply-add per axis; both volume
+// warp kernels go through this function so that they round identically
+__device__ __forceinline__ void affine_apply_fast(const Affine3& a, bool diagonal, const double in[3], double out[3]) {
+  if (diagonal) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) out[r] = fma(a.m[4 * r], in[r], a.t[r]);
+  } else {
+    affine_apply(a, in, out);
+  }
+}
 
 // q (x,y,z lattice coordinate) += trilinear(disp, q) when q is inside the field buffer [-0.5, n-0.5)
 __device__ __forceinline__ void displace(const float* __restrict__ disp, int FD, int FH, int FW, double q[3]) {
@@ -1342,7 +1358,9 @@ __device__ __forceinline__ TriF trif_setup(const double s[3], const int n[3]) {
 // and the eight interpolation weights are computed ONCE per voxel and reused by every channel -- the channel loop is
 // eight loads, eight FMAs and a store -- and the displacement gather uses 32-bit element offsets as well.  Staging the
 // tile's field footprint in shared memory was measured again in round 2 and is slower (the cooperative copy costs more
-// than the L1 gathers it replaces): profiles/r02_warp_variants.json.
+// than the L1 gathers it replaces), and so are two further variants built on an axis-aligned output grid -- a block-wide
+// staged field box with threads walking z columns, and a warp-cooperative coalesced fetch of the four field rows a
+// 32-voxel row touches (fewer L1 wavefronts, but more integer instructions): profiles/r02_warp_variants.json.
 // Coordinates stay fp64 (ITK computes in double); interpolation weights and sums are fp32.
 template <int kMinBlocks>
 __global__ void __launch_bounds__(256, kMinBlocks) warp_volume_kernel(const WarpVolumeParams p) {
@@ -1358,7 +1376,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) warp_volume_kernel(const Warp
   double q[3];
   {
     const double j[3] = {static_cast<double>(x), static_cast<double>(y), static_cast<double>(z)};
-    affine_apply(p.out_index_to_net, j, q);
+    affine_apply_fast(p.out_index_to_net, affine_is_diagonal(p.out_index_to_net), j, q);
   }
   bool fin = true;
 #pragma unroll
@@ -1384,7 +1402,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) warp_volume_kernel(const Warp
   // ---- source index, inside test, interpolation set-up (once per voxel, shared by every channel)
   const double qd[3] = {q[0] + dx, q[1] + dy, q[2] + dz};
   double sidx[3];
-  affine_apply(p.net_to_src_index, qd, sidx);
+  affine_apply_fast(p.net_to_src_index, affine_is_diagonal(p.net_to_src_index), qd, sidx);
   bool sin = true;
 #pragma unroll
   for (int a = 0; a < 3; ++a) sin = sin && sidx[a] >= -0.5 && sidx[a] < p.shi[a];
