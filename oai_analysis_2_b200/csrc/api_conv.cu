@@ -24,6 +24,7 @@ constexpr int kFlagForceKd1 = 4;
 constexpr int kFlagNoFastPath = 8;
 constexpr int kFlagWideN = 16;     // A/B: keep 256-wide N tiles for 3x3x3 layers with cout >= 256 (one kd per weight block)
 constexpr int kFlagWideRows = 32;  // A/B: keep 128-byte rows (zero-filled upper half) for a 32-channel source
+constexpr int kFlagOneKhRow = 64;  // A/B: one kh row per A stage even where the three-row stage applies
 constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8 - 2112 - 2048;  // 227 KB minus alignment slack, barriers, head weights, bias
 
 // One K chunk of the implicit GEMM: a TMA box of 64 (32) channels starting at channel cc of source `src`.
@@ -36,6 +37,7 @@ struct Chunk {
 
 struct Plan {
   int mode, kd_per_block, R, Rd, up_groups, nhalf, cph, nblk, nch, k16, row_bytes, TW, TH, n_wbuf, n_astage;
+  int nkh;   // kh rows per A stage at launch (the packed image is the same: three consecutive kh blocks form one)
   uint32_t wblock_bytes, astage_bytes, astage_stride;
   Chunk chunks[kMaxChunks];
 };
@@ -136,9 +138,18 @@ int make_plan(const ConvSpec& s, Plan* pl, int d_cnt = 0) {
     pl->nblk = nch * (pl->kd_per_block == 3 ? 9 : 27);
     pl->n_wbuf = pl->kd_per_block == 3 ? 2 : 3;
   }
-  pl->astage_bytes = (pl->mode == kModeRowShared ? 130 : 128) * rb;
+  // A 32-channel row-shared layer (ec1) issues only six MMAs per one-row stage, fewer tensor clocks than the issuing
+  // thread needs instructions: there the stage holds the three kh rows of a slice (18 MMAs) and the whole
+  // 27-tap weight image (three consecutive kh blocks of the packed layout, 110 KB) stays resident in shared memory.
+  pl->nkh = 1;
+  if (pl->mode == kModeRowShared && rb == 64 && nch == 1 &&
+      !(flags & (kFlagOneKhRow | kFlagNoFastPath | kFlagBaseOffFormula))) {
+    pl->nkh = 3;
+    pl->n_wbuf = 1;
+  }
+  pl->astage_bytes = (pl->mode == kModeRowShared ? 130 : 128) * rb * pl->nkh;
   pl->astage_stride = (pl->astage_bytes + 1023u) & ~1023u;
-  const size_t wstride = (pl->wblock_bytes + 1023u) & ~size_t(1023);
+  const size_t wstride = (static_cast<size_t>(pl->wblock_bytes) * pl->nkh + 1023u) & ~size_t(1023);
   const size_t left = kSmemBudget - pl->n_wbuf * wstride;
   int ns = static_cast<int>(left / pl->astage_stride);
   if (ns > 8) ns = 8;
@@ -357,8 +368,10 @@ int conv_run(const ConvSpec& s, const ConvLaunch& a, cudaStream_t st) {
     p.chunk_src[c] = static_cast<uint8_t>(pl.chunks[c].src);
     p.chunk_cc[c] = static_cast<uint16_t>(pl.chunks[c].cc);
   }
-  p.mode = pl.mode; p.kd_per_block = pl.kd_per_block; p.nblk = pl.nblk;
-  p.wblock_bytes = pl.wblock_bytes; p.n_wbuf = pl.n_wbuf; p.n_astage = pl.n_astage;
+  p.mode = pl.mode; p.kd_per_block = pl.kd_per_block; p.nblk = pl.nblk / pl.nkh;
+  p.wblock_bytes = pl.wblock_bytes * pl.nkh; p.n_wbuf = pl.n_wbuf; p.n_astage = pl.n_astage;
+  p.nkh = pl.nkh;
+  p.w_resident = (p.nblk == 1 && pl.nhalf == 1 && pl.up_groups == 1 && pl.n_wbuf == 1) ? 1 : 0;
   p.astage_bytes = pl.astage_bytes; p.astage_stride = pl.astage_stride;
   p.ab_format = s.fmt; p.relu = a.relu;
   p.base_off_mode = (s.flags & kFlagBaseOffFormula) ? 1 : 0;
@@ -381,7 +394,7 @@ int conv_run(const ConvSpec& s, const ConvLaunch& a, cudaStream_t st) {
 
   OAI_REQUIRE(pl.mode != kModeUp2 || (c1 == 0 && !head), "conv: up2 mode takes one source and no fused head");
   const int bw = pl.mode == kModeRowShared ? 130 : pl.TW;
-  const int bh = pl.TH;
+  const int bh = pl.TH * pl.nkh;
   CUtensorMap tm0, tm1;
   if (make_act_tmap(&tm0, a.src0, s.split0 ? 2 * c0 : c0, W, H, D, a.NT, bw, bh, s.fmt, pl.row_bytes)) return 1;
   if (a.src1) {

@@ -43,8 +43,8 @@ struct BlockInfo {
 __device__ __forceinline__ BlockInfo decode_block(const ConvIgemmParams& p, int b) {
   BlockInfo bi;
   if (p.mode == kModeRowShared) {
-    bi.c = b / 3;
-    bi.kh = b % 3;
+    bi.c = p.nkh == 3 ? b : b / 3;
+    bi.kh = p.nkh == 3 ? 0 : b % 3;   // three-row stages start at row h - 1 and hold kh = 0, 1, 2
     bi.kw = 0;
     bi.kdlo = 0;
     bi.nkd = 3;
@@ -214,11 +214,12 @@ __device__ __forceinline__ void head_dot(const uint32_t (&v)[32], uint32_t sbias
 // registers; one lane, elected once, issues every tcgen05.mma / tcgen05.commit.
 struct IssueConsts {
   uint32_t kw_step, b_kw, desc_hi32, idesc_1, idesc_step, tap16, cout;
+  uint32_t kh_a, kh_b;   // three-row stages: descriptor units between the kh rows of the A stage / the kh sub-blocks of B
 };
 
 // every (kw, k16) step of one A stage onto the accumulators [d_addr, +nt*cout), all accumulating; skip_first leaves out
 // the (0, 0) step (already issued by issue_first with per-accumulator overwrite flags)
-template <int NKW, int K16N, int PER>
+template <int NKW, int K16N, int PER, int NKH>
 __device__ __forceinline__ void issue_stage(const IssueConsts& c, uint32_t d_addr, uint32_t a_lo, uint32_t b_lo, int nt,
                                             bool skip_first) {
   for (int g0 = 0; g0 < nt; g0 += PER) {
@@ -227,15 +228,18 @@ __device__ __forceinline__ void issue_stage(const IssueConsts& c, uint32_t d_add
     const uint32_t d = d_addr + static_cast<uint32_t>(g0) * c.cout;
     const uint32_t bl = b_lo + static_cast<uint32_t>(g0) * c.tap16;
 #pragma unroll
-    for (int kw = 0; kw < NKW; ++kw)
+    for (int kh = 0; kh < NKH; ++kh)
 #pragma unroll
-      for (int k16 = 0; k16 < K16N; ++k16) {
-        if (kw == 0 && k16 == 0) {
-          if (!skip_first) umma_f16_ss_lohi(d, a_lo, bl, c.desc_hi32, idesc, 1u);
-        } else {
-          umma_f16_ss_lohi(d, a_lo + kw * c.kw_step + k16 * 2, bl + kw * c.b_kw + k16 * 2, c.desc_hi32, idesc, 1u);
+      for (int kw = 0; kw < NKW; ++kw)
+#pragma unroll
+        for (int k16 = 0; k16 < K16N; ++k16) {
+          if (kh == 0 && kw == 0 && k16 == 0) {
+            if (!skip_first) umma_f16_ss_lohi(d, a_lo, bl, c.desc_hi32, idesc, 1u);
+          } else {
+            umma_f16_ss_lohi(d, a_lo + kh * c.kh_a + kw * c.kw_step + k16 * 2,
+                             bl + kh * c.kh_b + kw * c.b_kw + k16 * 2, c.desc_hi32, idesc, 1u);
+          }
         }
-      }
   }
 }
 
@@ -259,7 +263,7 @@ __device__ __forceinline__ void issue_first(const IssueConsts& c, uint32_t tmem_
   }
 }
 
-template <int NKW, int K16N, int PER>
+template <int NKW, int K16N, int PER, int NKH>
 __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const uint32_t tmem_base, uint8_t* abuf,
                                                 uint8_t* wbuf, const uint32_t wstride, uint64_t* full_a,
                                                 uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
@@ -281,6 +285,10 @@ __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const 
   const int ns = up2 ? R_acc : ((one_kd || kd_cycle) ? 1 : 3);  // taps stacked along N in every weight block
   const int a_inc = up2 ? 0 : 1;
   c.b_kw = static_cast<uint32_t>(ns) * c.tap16;
+  c.kh_a = (130u * rowb) >> 4;
+  c.kh_b = 3u * c.b_kw;
+  const bool resident = p.w_resident != 0;
+  bool have_w = false;
   const bool leader = elect_one();
   int stage = 0, wb = 0;
   uint32_t aphase = 0, wphase = 0, use_bits = 0;  // use_bits: per-accumulator mbarrier phase (flips per use)
@@ -298,7 +306,8 @@ __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const 
       const int dlo = max(0, d0 + kdlo - 1);
       const int dhi = min(Dm1, d0 + rd - 1 + kdhi - 1);
       const bool last_blk = b == nblk - 1;
-      mbar_wait(&full_w[wb], wphase, 300 + wb);
+      if (!(resident && have_w)) mbar_wait(&full_w[wb], wphase, 300 + wb);
+      have_w = true;
       const uint32_t w_lo = w_lo0 + static_cast<uint32_t>(wb) * w_step;
       int a_first = up2 ? 0 : dlo - kdhi + 1 - d0;  // accumulator hit by the first stacked tap
       for (int dp = dlo; dp <= dhi; ++dp, a_first += a_inc) {
@@ -325,7 +334,7 @@ __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const 
         const bool publish = last_blk && a_first >= 0 && a_first < ra;
         if (leader) {
           if (f0 >= 0) issue_first<PER>(c, tmem_base, acc0, nt, f0, a_lo, b_lo);
-          issue_stage<NKW, K16N, PER>(c, d_addr, a_lo, b_lo, nt, f0 >= 0);
+          issue_stage<NKW, K16N, PER, NKH>(c, d_addr, a_lo, b_lo, nt, f0 >= 0);
           // release the A stage; the last block's last tap of an accumulator also publishes it to the epilogue
           umma_commit(&empty_a[stage]);
           if (publish) umma_commit(&acc_full[a_first]);
@@ -338,10 +347,12 @@ __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const 
           a_lo = a_lo0;
         }
       }
-      if (leader) umma_commit(&empty_w[wb]);
-      if (++wb == nwb) {
-        wb = 0;
-        wphase ^= 1u;
+      if (!resident) {
+        if (leader) umma_commit(&empty_w[wb]);
+        if (++wb == nwb) {
+          wb = 0;
+          wphase ^= 1u;
+        }
       }
     }
     if (leader && signaled != all_acc) {
@@ -539,6 +550,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
         const UnitInfo ui = decode_unit(p, u);
         const uint8_t* src = p.wpack + static_cast<size_t>(ui.nh * p.up_groups + ui.tg) * p.nblk * p.wblock_bytes;
+        if (p.w_resident && u != static_cast<int>(blockIdx.x)) break;   // the single block stays in shared memory
         for (int b = 0; b < p.nblk; ++b) {
           mbar_wait(&empty_w[wb], phase ^ 1u, 200 + wb);
           mbar_arrive_expect_tx(&full_w[wb], p.wblock_bytes);
@@ -561,11 +573,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     const int nkw_rt = (p.mode == kModeRowShared) ? 3 : 1;
     const int per_rt = max(1, 256 / p.cout);
 #define OAI_ISSUE(NKW, K16N, PER) \
-  mma_issuer_fast<NKW, K16N, PER>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty)
+  mma_issuer_fast<NKW, K16N, PER, 1>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty)
 #define OAI_ISSUE_GENERAL() \
   mma_issuer_general(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty)
     if (general) OAI_ISSUE_GENERAL();
     else if (nkw_rt == 3 && p.k16_steps == 4 && per_rt == 4) OAI_ISSUE(3, 4, 4);
+    else if (nkw_rt == 3 && p.k16_steps == 2 && per_rt == 4 && p.nkh == 3)
+      mma_issuer_fast<3, 2, 4, 3>(p, tmem_base, abuf, wbuf, wstride, full_a, empty_a, full_w, empty_w, acc_full, acc_empty);
     else if (nkw_rt == 3 && p.k16_steps == 2 && per_rt == 4) OAI_ISSUE(3, 2, 4);
     else if (nkw_rt == 1 && p.k16_steps == 4 && per_rt == 4) OAI_ISSUE(1, 4, 4);
     else if (nkw_rt == 1 && p.k16_steps == 4 && per_rt == 2) OAI_ISSUE(1, 4, 2);

@@ -30,10 +30,10 @@ def main():
         xs = torch.cat((x, torch.zeros_like(x)), -1).contiguous()
         w = torch.randn(cout, c0, 3, 3, 3) * 0.05
         b = torch.zeros(cout, device="cuda")
-        for name, flags, terms, split_out in (("default", 0, 1, False), ("wide rows (128 B)", 32, 1, False),
+        for name, flags, terms, split_out in (("default", 0, 1, False), ("one kh row per stage", 64, 1, False), ("wide rows (128 B)", 32, 1, False),
                                               ("per-tap", 1, 1, False), ("terms 2", 0, 2, False),
                                               ("default, split out", 0, 1, True)):
-            if flags == 32 and c0 != 32:
+            if flags in (32, 64) and c0 != 32:
                 continue
             wp = ops.pack_conv_weights_ex(w, c0, 0, D, H, W, 0, terms, 0, flags)
             src = xs if terms > 1 else x
