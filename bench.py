@@ -262,7 +262,7 @@ def run_full(args):
             _lib.lib.oai_profile_begin()
             mark["n0"] = _lib.launch_count()
 
-        pipe.capture(vols_d[0].shape, geom, verts_d.shape[0], on_record)
+        pipe.capture(vols_d[0].shape, geom, verts_d.shape[0], on_record, overlap_registration=args.overlap_registration)
         launches_per_step = _lib.launch_count() - mark["n0"]   # kernels recorded into the graph = launches per replay
 
     def step_device(i):
@@ -932,6 +932,8 @@ def main():
     ap.add_argument("--no-library-bar", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the CUDA graph")
+    ap.add_argument("--overlap-registration", action="store_true",
+                    help="A/B: record the registration as a parallel branch of the per-knee graph")
     args = ap.parse_args()
     if args.precision:
         os.environ["OAI_B200_SEG_PRECISION"] = args.precision

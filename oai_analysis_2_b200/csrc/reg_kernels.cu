@@ -1116,32 +1116,49 @@ __global__ void __launch_bounds__(256) deep_reduce_convt4_kernel(const ConvT4Par
 
 // ------------------------------------------------------------------------------------------------ sampling helpers
 // F.grid_sample(bilinear, border, align_corners=True) at normalised coordinate g = 2c-1 along each axis.
+// The neighbour pair of every axis is (b, b + 1) with b <= n - 2: at the clamped upper border (pix == n - 1, where
+// grid_sample reads v[n-1] twice with weights 1 and 0) the base steps back to n - 2 and the fraction becomes 1 -- the
+// same value -- so the eight corners of every sample sit at fixed offsets {0,1} + {0,W} + {0,HW} from one base
+// pointer and the loads take immediate / row-pointer offsets instead of eight separate 64-bit address computations.
+// An axis of extent 1 keeps b = 0, t = 0 and a zero stride.
 struct Tri {
-  int i0[3], i1[3];
+  long long base;   // element offset of corner (b_z, b_y, b_x) inside one component plane
   float t[3];
 };
 __device__ __forceinline__ Tri tri_setup(float cz, float cy, float cx, int D, int H, int W) {
   Tri r;
   const float c[3] = {cz, cy, cx};
   const int n[3] = {D, H, W};
+  int b[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const float g = c[a] * 2.f - 1.f;
     float pix = ((g + 1.f) / 2.f) * static_cast<float>(n[a] - 1);
     pix = fminf(fmaxf(pix, 0.f), static_cast<float>(n[a] - 1));
     const float f = floorf(pix);
-    r.i0[a] = static_cast<int>(f);
-    r.i1[a] = min(r.i0[a] + 1, n[a] - 1);
-    r.t[a] = pix - f;
+    int i0 = static_cast<int>(f);
+    float t = pix - f;
+    if (i0 > n[a] - 2) {   // pix == n - 1 exactly (t == 0): read (n-2, n-1) with weights (0, 1)
+      i0 = max(n[a] - 2, 0);
+      t = n[a] > 1 ? 1.f : 0.f;
+    }
+    b[a] = i0;
+    r.t[a] = t;
   }
+  r.base = (static_cast<long long>(b[0]) * H + b[1]) * W + b[2];
   return r;
 }
-__device__ __forceinline__ float tri_sample(const float* __restrict__ v, const Tri& q, int H, int W) {
-  const size_t z0 = static_cast<size_t>(q.i0[0]) * H, z1 = static_cast<size_t>(q.i1[0]) * H;
-  const float v000 = __ldg(v + (z0 + q.i0[1]) * W + q.i0[2]), v001 = __ldg(v + (z0 + q.i0[1]) * W + q.i1[2]);
-  const float v010 = __ldg(v + (z0 + q.i1[1]) * W + q.i0[2]), v011 = __ldg(v + (z0 + q.i1[1]) * W + q.i1[2]);
-  const float v100 = __ldg(v + (z1 + q.i0[1]) * W + q.i0[2]), v101 = __ldg(v + (z1 + q.i0[1]) * W + q.i1[2]);
-  const float v110 = __ldg(v + (z1 + q.i1[1]) * W + q.i0[2]), v111 = __ldg(v + (z1 + q.i1[1]) * W + q.i1[2]);
+// sx / sy / sz: element strides of the three axes (0 for an axis of extent 1)
+__device__ __forceinline__ float tri_sample(const float* __restrict__ v, const Tri& q, long long sy, long long sz,
+                                            int sx) {
+  const float* r00 = v + q.base;
+  const float* r01 = r00 + sy;
+  const float* r10 = r00 + sz;
+  const float* r11 = r10 + sy;
+  const float v000 = __ldg(r00), v001 = __ldg(r00 + sx);
+  const float v010 = __ldg(r01), v011 = __ldg(r01 + sx);
+  const float v100 = __ldg(r10), v101 = __ldg(r10 + sx);
+  const float v110 = __ldg(r11), v111 = __ldg(r11 + sx);
   const float tz = q.t[0], ty = q.t[1], tx = q.t[2];
   return (1.f - tz) * ((1.f - ty) * ((1.f - tx) * v000 + tx * v001) + ty * ((1.f - tx) * v010 + tx * v011)) +
          tz * ((1.f - ty) * ((1.f - tx) * v100 + tx * v101) + ty * ((1.f - tx) * v110 + tx * v111));
@@ -1183,13 +1200,16 @@ __global__ void __launch_bounds__(256, kMinBlocks) chain_kernel(const ChainParam
         }
       } else {
         Tri q[kChainVZ];
+        const int fsx = p.uw[f] > 1 ? 1 : 0;
+        const long long fsy = p.uh[f] > 1 ? p.uw[f] : 0;
+        const long long fsz = p.ud[f] > 1 ? static_cast<long long>(p.uh[f]) * p.uw[f] : 0;
 #pragma unroll
         for (int i = 0; i < kChainVZ; ++i) q[i] = tri_setup(cz[i], cy[i], cx[i], p.ud[f], p.uh[f], p.uw[f]);
 #pragma unroll
         for (int i = 0; i < kChainVZ; ++i) {
-          const float dz = tri_sample(u, q[i], p.uh[f], p.uw[f]);
-          const float dy = tri_sample(u + plane, q[i], p.uh[f], p.uw[f]);
-          const float dx = tri_sample(u + 2 * plane, q[i], p.uh[f], p.uw[f]);
+          const float dz = tri_sample(u, q[i], fsy, fsz, fsx);
+          const float dy = tri_sample(u + plane, q[i], fsy, fsz, fsx);
+          const float dx = tri_sample(u + 2 * plane, q[i], fsy, fsz, fsx);
           cz[i] += dz; cy[i] += dy; cx[i] += dx;
         }
       }
@@ -1199,7 +1219,8 @@ __global__ void __launch_bounds__(256, kMinBlocks) chain_kernel(const ChainParam
 #pragma unroll
       for (int i = 0; i < kChainVZ; ++i) {
         const Tri q = tri_setup(cz[i], cy[i], cx[i], p.id, p.ih, p.iw);
-        img[i] = tri_sample(p.img, q, p.ih, p.iw);
+        img[i] = tri_sample(p.img, q, p.ih > 1 ? p.iw : 0, p.id > 1 ? static_cast<long long>(p.ih) * p.iw : 0,
+                            p.iw > 1 ? 1 : 0);
       }
     }
 #pragma unroll
@@ -1431,6 +1452,123 @@ __global__ void __launch_bounds__(256, kMinBlocks) warp_volume_kernel(const Warp
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc = fmaf(w[k], __ldg(src + off[k]), acc);
     *dst = acc;
+  }
+}
+
+// ---- the same resampling with neighbours at fixed strides
+// The gather kernel above spends most of its ~380 (C = 1) to ~550 (C = 8) instructions per voxel on address arithmetic:
+// every one of its 24 + 8 C loads carries its own clamped 32-bit offset and a three- or four-instruction 64-bit address
+// (profiles/r02_warp_sass_notes.txt).  Here the clamping is folded into the interpolation fraction instead: a lattice
+// coordinate whose lower / upper neighbour would be clamped (s in [-0.5, 0) or [n-1, n-0.5)) takes the base index 0 /
+// n-2 with fraction 0 / 1 -- the same value, v[0] or v[n-1] -- so the eight corners of EVERY voxel sit at the same
+// offsets {0, 1} + {0, W} + {0, H W} from one base pointer.  Per voxel and channel that is one 64-bit pointer bump,
+// three row pointers and eight loads with immediate offsets.  Needs every lattice dimension >= 2 (else the gather kernel).
+struct Tri1 {
+  int b[3];
+  float t[3];
+};
+__device__ __forceinline__ Tri1 tri1_setup(const double s[3], const int n[3]) {
+  Tri1 r;
+  const double magic = 6755399441055744.0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double m = s[a] + magic;
+    int b = __double2loint(m);
+    float d = static_cast<float>(s[a] - (m - magic));
+    if (d < 0.f) { d += 1.f; b -= 1; }
+    if (b < 0) { b = 0; d = 0.f; }
+    if (b > n[a] - 2) { b = n[a] - 2; d = 1.f; }
+    r.b[a] = b;
+    r.t[a] = d;
+  }
+  return r;
+}
+
+// A block owns a 32 (x) x 8 (y) tile over kWarpZ consecutive output slices and walks them in order: the upper
+// neighbour planes (field and source) of slice z are the lower ones of slice z + 1 and are still in L1.  With one slice
+// per block every corner plane came from L2 twice; the sweep was bound by L2 -> SM traffic (~24 B per voxel and channel
+// against 8 B algorithmic), which is why trimming instructions alone did not move it.
+constexpr int kWarpZ = 4;
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) warp_volume_fast_kernel(const WarpVolumeParams p) {
+  const long long nvox = static_cast<long long>(p.OD) * p.OH * p.OW;
+  const long long splane = static_cast<long long>(p.SD) * p.SH * p.SW;
+  const int nf[3] = {p.FW, p.FH, p.FD}, ns[3] = {p.SW, p.SH, p.SD};
+  const int nbx = (p.OW + 31) / 32, nby = (p.OH + 7) / 8;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int x = static_cast<int>(blockIdx.x % nbx) * 32 + lane, y = static_cast<int>((blockIdx.x / nbx) % nby) * 8 + wrp;
+  const int z0 = static_cast<int>(blockIdx.x / (nbx * nby)) * kWarpZ;
+  if (x >= p.OW || y >= p.OH) return;
+  const bool diag1 = affine_is_diagonal(p.out_index_to_net), diag2 = affine_is_diagonal(p.net_to_src_index);
+  const long long frow = 3ll * p.FW, fslice = frow * p.FH;
+  const long long srow = p.SW, sslice = static_cast<long long>(p.SW) * p.SH;
+  const int z1 = min(z0 + kWarpZ, p.OD);
+  for (int z = z0; z < z1; ++z) {
+    double q[3];
+    {
+      const double j[3] = {static_cast<double>(x), static_cast<double>(y), static_cast<double>(z)};
+      affine_apply_fast(p.out_index_to_net, diag1, j, q);
+    }
+    bool fin = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) fin = fin && q[a] >= -0.5 && q[a] < p.fhi[a];
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (fin) {
+      const Tri1 tf = tri1_setup(q, nf);
+      const float* e00 = p.disp + 3 * ((tf.b[2] * p.FH + tf.b[1]) * p.FW + tf.b[0]);
+      const float* e01 = e00 + frow;
+      const float* e10 = e00 + fslice;
+      const float* e11 = e10 + frow;
+      const float tx = tf.t[0], ty = tf.t[1], tz = tf.t[2];
+      const float wr[4] = {(1.f - ty) * (1.f - tz), ty * (1.f - tz), (1.f - ty) * tz, ty * tz};
+      const float* rows[4] = {e00, e01, e10, e11};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* e = rows[k];
+        const float w0 = wr[k] * (1.f - tx), w1 = wr[k] * tx;
+        dx = fmaf(w0, __ldg(e), dx); dy = fmaf(w0, __ldg(e + 1), dy); dz = fmaf(w0, __ldg(e + 2), dz);
+        dx = fmaf(w1, __ldg(e + 3), dx); dy = fmaf(w1, __ldg(e + 4), dy); dz = fmaf(w1, __ldg(e + 5), dz);
+      }
+    }
+    const double qd[3] = {q[0] + dx, q[1] + dy, q[2] + dz};
+    double sidx[3];
+    affine_apply_fast(p.net_to_src_index, diag2, qd, sidx);
+    bool sin = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sin = sin && sidx[a] >= -0.5 && sidx[a] < p.shi[a];
+    float* dst = p.out + (static_cast<long long>(z) * p.OH + y) * p.OW + x;
+    if (!sin) {
+      for (int c = 0; c < p.C; ++c, dst += nvox) *dst = p.default_value;
+      continue;
+    }
+    const Tri1 ts = tri1_setup(sidx, ns);
+    float w[8];
+    {
+      const float tx = ts.t[0], ty = ts.t[1], tz = ts.t[2];
+      const float a0 = (1.f - ty) * (1.f - tz), a1 = ty * (1.f - tz), a2 = (1.f - ty) * tz, a3 = ty * tz;
+      w[0] = a0 * (1.f - tx); w[1] = a0 * tx; w[2] = a1 * (1.f - tx); w[3] = a1 * tx;
+      w[4] = a2 * (1.f - tx); w[5] = a2 * tx; w[6] = a3 * (1.f - tx); w[7] = a3 * tx;
+    }
+    const float* s00 = p.src + (ts.b[2] * p.SH + ts.b[1]) * p.SW + ts.b[0];
+    // one channel per trip: the eight loads are issued back to back, then consumed (an unrolled loop at this register
+    // budget interleaves each load with its use and serialises on the load latency: 2x slower for C >= 4)
+#pragma unroll 1
+    for (int c = 0; c < p.C; ++c, s00 += splane, dst += nvox) {
+      const float* s01 = s00 + srow;
+      const float* s10 = s00 + sslice;
+      const float* s11 = s10 + srow;
+      const float v0 = __ldg(s00), v1 = __ldg(s00 + 1), v2 = __ldg(s01), v3 = __ldg(s01 + 1);
+      const float v4 = __ldg(s10), v5 = __ldg(s10 + 1), v6 = __ldg(s11), v7 = __ldg(s11 + 1);
+      float acc = w[0] * v0;
+      acc = fmaf(w[1], v1, acc);
+      acc = fmaf(w[2], v2, acc);
+      acc = fmaf(w[3], v3, acc);
+      acc = fmaf(w[4], v4, acc);
+      acc = fmaf(w[5], v5, acc);
+      acc = fmaf(w[6], v6, acc);
+      acc = fmaf(w[7], v7, acc);
+      *dst = acc;
+    }
   }
 }
 
@@ -1668,6 +1806,12 @@ int disp_field_launch(const float* phi, int D, int H, int W, float* disp, cudaSt
   return launched("disp_field_kernel");
 }
 
+// A/B and test switch: OAI_B200_WARP_GATHER=1 forces the general gather kernel
+static bool warp_force_gather() {
+  const char* e = getenv("OAI_B200_WARP_GATHER");
+  return e && e[0] == '1';
+}
+
 int warp_volume_launch(const WarpVolumeParams& p, cudaStream_t st) {
   const long long tiles = static_cast<long long>((p.OW + 31) / 32) * ((p.OH + 7) / 8) * p.OD;
   if (tiles <= 0 || tiles > 0x7fffffffLL) return fail("warp_volume: output too large");
@@ -1676,6 +1820,11 @@ int warp_volume_launch(const WarpVolumeParams& p, cudaStream_t st) {
   WarpVolumeParams q = p;
   const int nf[3] = {p.FW, p.FH, p.FD}, ns[3] = {p.SW, p.SH, p.SD};
   for (int a = 0; a < 3; ++a) { q.fhi[a] = nf[a] - 0.5; q.shi[a] = ns[a] - 0.5; }
+  if (p.FW >= 2 && p.FH >= 2 && p.FD >= 2 && p.SW >= 2 && p.SH >= 2 && p.SD >= 2 && !warp_force_gather()) {
+    const long long ftiles = static_cast<long long>((p.OW + 31) / 32) * ((p.OH + 7) / 8) * ((p.OD + kWarpZ - 1) / kWarpZ);
+    warp_volume_fast_kernel<5><<<static_cast<unsigned>(ftiles), 256, 0, st>>>(q);
+    return launched("warp_volume_fast_kernel");
+  }
   warp_volume_kernel<5><<<static_cast<unsigned>(tiles), 256, 0, st>>>(q);
   return launched("warp_volume_kernel");
 }

@@ -22,19 +22,44 @@ class KneePipeline:
         self.atlas_geom = atlas_geom or Geometry(atlas_array.shape[::-1])
         self._pinned = {}
 
-    def run_device(self, vol, geom, vertices=None):
+    def run_device(self, vol, geom, vertices=None, overlap_registration=False):
         """vol: float32 [D,H,W] on the device (intensities windowed to [0,1]); vertices: float64 [n,3] physical
-        points in the knee's space.  Returns device tensors."""
+        points in the knee's space.  Returns device tensors.
+
+        overlap_registration: registration needs only the volume and the atlas, so it can run as a parallel branch
+        beside the segmentation (a second stream; inside capture() a second branch of the graph).  The persistent conv
+        kernel owns every SM's register file while it runs, so the branch only fills the HBM-bound phases (stem, pools)
+        and the tails of the conv launches.  Used by capture() only: in eager mode the caching allocator would need
+        record_stream bookkeeping for the tensors that cross streams."""
         nvtx = torch.cuda.nvtx   # one range per stage (SURVEY §5: the reference has no tracing at all)
-        nvtx.range_push("oai.segmentation")
-        prob = self.segmenter.segment_device(vol, if_output_prob_map=True,
-                                             tiles_per_batch=self.segmenter.config.get("tiles_per_batch"))
-        nvtx.range_pop()
-        nvtx.range_push("oai.registration")
-        phi_AB, phi_BA = itk_wrapper.register_pair_device(self.reg_model, vol, self.atlas)
-        tr_AB = CompositeTransform(ops.displacement_field(phi_AB[0]), geom, self.atlas_geom)
-        tr_BA = CompositeTransform(ops.displacement_field(phi_BA[0]), self.atlas_geom, geom)
-        nvtx.range_pop()
+
+        def register():
+            nvtx.range_push("oai.registration")
+            phi_AB, phi_BA = itk_wrapper.register_pair_device(self.reg_model, vol, self.atlas)
+            a = CompositeTransform(ops.displacement_field(phi_AB[0]), geom, self.atlas_geom)
+            b = CompositeTransform(ops.displacement_field(phi_BA[0]), self.atlas_geom, geom)
+            nvtx.range_pop()
+            return a, b
+
+        def segment():
+            nvtx.range_push("oai.segmentation")
+            p = self.segmenter.segment_device(vol, if_output_prob_map=True,
+                                              tiles_per_batch=self.segmenter.config.get("tiles_per_batch"))
+            nvtx.range_pop()
+            return p
+
+        if overlap_registration:
+            cur = torch.cuda.current_stream(self.device)
+            if not hasattr(self, "_reg_stream"):
+                self._reg_stream = torch.cuda.Stream(device=self.device)
+            self._reg_stream.wait_stream(cur)
+            with torch.cuda.stream(self._reg_stream):
+                tr_AB, tr_BA = register()
+            prob = segment()
+            cur.wait_stream(self._reg_stream)
+        else:
+            prob = segment()
+            tr_AB, tr_BA = register()
         nvtx.range_push("oai.warp_probmaps")
         warped = tr_AB.resample_device(prob, geom, self.atlas_geom)      # FC, TC on the atlas grid
         nvtx.range_pop()
@@ -48,7 +73,7 @@ class KneePipeline:
         return out
 
     # -- CUDA graph of the whole per-knee path (about a hundred launches; replaying one graph removes the launch gaps)
-    def capture(self, vol_shape, geom, n_vertices=None, on_record=None):
+    def capture(self, vol_shape, geom, n_vertices=None, on_record=None, overlap_registration=False):
         """Record run_device for volumes of `vol_shape` (and `n_vertices` mesh vertices) into a CUDA graph with static
         input / output buffers.  Afterwards run_device_graph / run replay it.  The graph holds the addresses of the
         models' cached buffers (packed weights, the registration nets' concatenation buffers), so after capture this
@@ -68,7 +93,7 @@ class KneePipeline:
         if on_record is not None:
             on_record()   # e.g. switch the library's per-launch profiling events on for the recorded pass only
         with torch.cuda.graph(self._graph):
-            self._g_out = self.run_device(self._g_vol, geom, self._g_verts)
+            self._g_out = self.run_device(self._g_vol, geom, self._g_verts, overlap_registration=overlap_registration)
         return self
 
     def release_graph(self):

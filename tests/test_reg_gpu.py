@@ -348,3 +348,46 @@ def test_isosurface_full_size_properties():
     print(f"full-size iso-surface: {len(v)} -> {st['n_verts']} vertices, {len(f)} -> {st['n_faces']} faces, "
           f"{e0.elapsed_time(e1):.2f} ms (marching cubes + region filter)")
     assert st["n_faces"] > 3000 and st["volume"] < 0     # ascent winding: inward normals for a bright object
+
+
+@pytest.mark.parametrize("case", ["same_res_identity", "half_res_field", "fine_field_offset", "oblique_both"])
+def test_fixed_stride_warp_kernel_matches_the_gather_kernel(case):
+    """warp_volume_fast_kernel (neighbour clamping folded into the interpolation fraction, corners at fixed strides)
+    against warp_volume_kernel (clamped per-corner offsets) on the same inputs: partial tiles, voxels outside the field
+    buffer (no displacement) and outside the source (default value), both edge bands of every axis, oblique maps.
+    The two differ only where a neighbour is clamped: v*(1-t) + v*t there against v*1 + w*0 here."""
+    _cuda()
+    import os
+    from oai_analysis_2_b200 import ops
+    rng = np.random.default_rng(11)
+    out_dims = (19, 37, 70)                      # z,y,x: partial tiles in every direction
+    eye = np.eye(3)
+    th = 0.2
+    rot = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    src_dims = (21, 33, 64)
+    if case == "same_res_identity":
+        fdims, a1 = out_dims, (eye, np.zeros(3))
+    elif case == "half_res_field":              # q runs from -0.25 to n - 0.75: both clamped edge bands are sampled
+        fdims, a1 = (10, 19, 35), (np.diag([0.5, 0.5, 0.5]), np.array([-0.25, -0.25, -0.25]))
+    elif case == "fine_field_offset":           # field finer than the output and not covering it
+        fdims, a1 = (24, 40, 90), (np.diag([1.7, 1.3, 1.5]), np.array([-6.3, 2.2, -1.4]))
+    else:
+        fdims, a1 = (12, 20, 40), (rot * 0.55, np.array([3.0, -2.0, 0.1]))
+    a2m = rot * 0.9 if case == "oblique_both" else np.diag([src_dims[2] / fdims[2], src_dims[1] / fdims[1],
+                                                            src_dims[0] / fdims[0]])
+    a2 = (a2m, np.array([0.4, -0.2, 0.3]))
+    disp = torch.from_numpy((rng.normal(size=fdims + (3,)) * 1.5).astype(np.float32)).cuda()
+    src = torch.from_numpy(rng.random((3,) + src_dims).astype(np.float32)).cuda()
+    outs = {}
+    for mode in ("0", "1"):
+        os.environ["OAI_B200_WARP_GATHER"] = mode
+        try:
+            outs[mode] = ops.warp_volume(src, disp, a1, a2, out_dims, default_value=-7.0).cpu().numpy()
+        finally:
+            os.environ.pop("OAI_B200_WARP_GATHER", None)
+    frac_default = (outs["1"] == -7.0).mean()
+    diff = np.abs(outs["0"] - outs["1"])
+    print(f"{case}: {frac_default:.2f} of the output outside the source; max |diff| {diff.max():.2e}")
+    # a displacement that moves by one fp32 ulp can push a voxel across the source's edge: allow two such voxels
+    assert (diff > 2e-5).sum() <= 2, (diff > 2e-5).sum()
+    assert 0.0 <= frac_default < 0.95
