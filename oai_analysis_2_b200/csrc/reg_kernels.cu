@@ -1496,9 +1496,11 @@ __global__ void __launch_bounds__(256, kMinBlocks) warp_volume_fast_kernel(const
   const int nf[3] = {p.FW, p.FH, p.FD}, ns[3] = {p.SW, p.SH, p.SD};
   const int nbx = (p.OW + 31) / 32, nby = (p.OH + 7) / 8;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int x = static_cast<int>(blockIdx.x % nbx) * 32 + lane, y = static_cast<int>((blockIdx.x / nbx) % nby) * 8 + wrp;
+  const int xl = static_cast<int>(blockIdx.x % nbx) * 32 + lane, y = static_cast<int>((blockIdx.x / nbx) % nby) * 8 + wrp;
   const int z0 = static_cast<int>(blockIdx.x / (nbx * nby)) * kWarpZ;
-  if (x >= p.OW || y >= p.OH) return;
+  if (y >= p.OH) return;                 // whole warp
+  const bool live = xl < p.OW;           // lanes past the row's end shadow its last voxel and store nothing
+  const int x = min(xl, p.OW - 1);
   const bool diag1 = affine_is_diagonal(p.out_index_to_net), diag2 = affine_is_diagonal(p.net_to_src_index);
   const long long frow = 3ll * p.FW, fslice = frow * p.FH;
   const long long srow = p.SW, sslice = static_cast<long long>(p.SW) * p.SH;
@@ -1538,7 +1540,8 @@ __global__ void __launch_bounds__(256, kMinBlocks) warp_volume_fast_kernel(const
     for (int a = 0; a < 3; ++a) sin = sin && sidx[a] >= -0.5 && sidx[a] < p.shi[a];
     float* dst = p.out + (static_cast<long long>(z) * p.OH + y) * p.OW + x;
     if (!sin) {
-      for (int c = 0; c < p.C; ++c, dst += nvox) *dst = p.default_value;
+      if (live)
+        for (int c = 0; c < p.C; ++c, dst += nvox) *dst = p.default_value;
       continue;
     }
     const Tri1 ts = tri1_setup(sidx, ns);
@@ -1549,25 +1552,28 @@ __global__ void __launch_bounds__(256, kMinBlocks) warp_volume_fast_kernel(const
       w[0] = a0 * (1.f - tx); w[1] = a0 * tx; w[2] = a1 * (1.f - tx); w[3] = a1 * tx;
       w[4] = a2 * (1.f - tx); w[5] = a2 * tx; w[6] = a3 * (1.f - tx); w[7] = a3 * tx;
     }
-    const float* s00 = p.src + (ts.b[2] * p.SH + ts.b[1]) * p.SW + ts.b[0];
-    // one channel per trip: the eight loads are issued back to back, then consumed (an unrolled loop at this register
-    // budget interleaves each load with its use and serialises on the load latency: 2x slower for C >= 4)
+    const int sbase = (ts.b[2] * p.SH + ts.b[1]) * p.SW + ts.b[0];
+    {
+      const float* s00 = p.src + sbase;
+      // one channel per trip: the eight loads are issued back to back, then consumed (an unrolled loop at this register
+      // budget interleaves each load with its use and serialises on the load latency: 2x slower for C >= 4)
 #pragma unroll 1
-    for (int c = 0; c < p.C; ++c, s00 += splane, dst += nvox) {
-      const float* s01 = s00 + srow;
-      const float* s10 = s00 + sslice;
-      const float* s11 = s10 + srow;
-      const float v0 = __ldg(s00), v1 = __ldg(s00 + 1), v2 = __ldg(s01), v3 = __ldg(s01 + 1);
-      const float v4 = __ldg(s10), v5 = __ldg(s10 + 1), v6 = __ldg(s11), v7 = __ldg(s11 + 1);
-      float acc = w[0] * v0;
-      acc = fmaf(w[1], v1, acc);
-      acc = fmaf(w[2], v2, acc);
-      acc = fmaf(w[3], v3, acc);
-      acc = fmaf(w[4], v4, acc);
-      acc = fmaf(w[5], v5, acc);
-      acc = fmaf(w[6], v6, acc);
-      acc = fmaf(w[7], v7, acc);
-      *dst = acc;
+      for (int c = 0; c < p.C; ++c, s00 += splane, dst += nvox) {
+        const float* s01 = s00 + srow;
+        const float* s10 = s00 + sslice;
+        const float* s11 = s10 + srow;
+        const float v0 = __ldg(s00), v1 = __ldg(s00 + 1), v2 = __ldg(s01), v3 = __ldg(s01 + 1);
+        const float v4 = __ldg(s10), v5 = __ldg(s10 + 1), v6 = __ldg(s11), v7 = __ldg(s11 + 1);
+        float acc = w[0] * v0;
+        acc = fmaf(w[1], v1, acc);
+        acc = fmaf(w[2], v2, acc);
+        acc = fmaf(w[3], v3, acc);
+        acc = fmaf(w[4], v4, acc);
+        acc = fmaf(w[5], v5, acc);
+        acc = fmaf(w[6], v6, acc);
+        acc = fmaf(w[7], v7, acc);
+        if (live) *dst = acc;
+      }
     }
   }
 }
