@@ -220,8 +220,8 @@ def base_line(args, world, config, value, unit, ms_per_step, dtype, **extra):
     return line
 
 
-SEG_DTYPE = {"mixed": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), the full-resolution decoder layer dc2 reads "
-                      "fp16 hi+lo activations",
+SEG_DTYPE = {"mixed": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), the full-resolution decoder layers read fp16 "
+                      "hi+lo activations (dc2: skip input only; dc1)",
              "fp16": "fp16 operands / fp32 accumulate (tcgen05 kind::f16)", "bf16": "bf16 operands / fp32 accumulate",
              "fp16x2": "fp16 hi+lo activations x fp16 weights / fp32 accumulate",
              "fp16x3": "fp16 hi+lo activations x fp16 hi+lo weights / fp32 accumulate (fp32-faithful)"}

@@ -164,7 +164,7 @@ OAI_API int oai_seg_head(const void* act, int C, int ncls, const float* w, const
  * ------------------------------------------------------------------------------------------------------------ */
 enum {
   OAI_SEG_PRECISION_FP16 = 0,    /* 16-bit operands everywhere (TF32-class mantissa, the reference's cuDNN default) */
-  OAI_SEG_PRECISION_MIXED = 1,   /* default: dc2 (the full-resolution 192->64 decoder layer) reads fp16 hi+lo inputs */
+  OAI_SEG_PRECISION_MIXED = 1,   /* default: dc2's skip input (ec1's output) and dc1's input are read as fp16 hi+lo */
   OAI_SEG_PRECISION_FP16X2 = 2,  /* every layer reads fp16 hi+lo activations (terms 2) */
   OAI_SEG_PRECISION_FP16X3 = 3,  /* fp32-faithful: activations and weights both hi+lo (terms 3) */
   OAI_SEG_PRECISION_CUSTOM = 4   /* layer_terms[] below */

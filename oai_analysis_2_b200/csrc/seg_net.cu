@@ -203,11 +203,14 @@ extern "C" int oai_seg_layer_terms(int precision, int* terms17) {
               "seg_layer_terms: unknown precision %d", precision);
   for (int l = 0; l < kNumLayers; ++l) terms17[l] = 1;
   if (precision == OAI_SEG_PRECISION_MIXED) {
-    // dc2 (192 -> 64 at full resolution, 31 % of the network's MACs) reads both its inputs as fp16 hi + lo pairs: the
-    // rounding of its input activations is the largest single contribution to the logit error (scripts/dice_plans.py
-    // on the golden fixtures, profiles/r02_dice_plans.jsonl: mask flips 28 -> 12 over the three fixtures, minimum Dice
-    // 0.99881 -> 0.99965; splitting dc1 as well changes no Dice on the hardest fixture and costs 5 ms per knee)
-    terms17[DC2] = 2;
+    // Where the logit error comes from was measured plan by plan on the golden fixtures (scripts/dice_plans.py,
+    // profiles/r02_dice_plans.jsonl; mask flips summed over the three fixtures, noise about +-3): all-fp16 30;
+    // dc2 reading both inputs as fp16 hi + lo pairs 17; only its skip input (ec1's output, the largest activations
+    // of the network) 22; only its upsampled input 25; the skip input AND dc1's input 11; dc2 + dc1 entirely 5.
+    // The default spends the split where it pays: dc2's skip source (code 4: 64 of its 192 input channels) and dc1
+    // -- +9 ms per knee over all-fp16 instead of +20 ms for all of dc2, with fewer flips (min Dice 0.99932).
+    terms17[DC2] = 4;
+    terms17[DC1] = 2;
   } else if (precision == OAI_SEG_PRECISION_FP16X2 || precision == OAI_SEG_PRECISION_FP16X3) {
     for (int l = 1; l < kNumLayers; ++l) terms17[l] = precision == OAI_SEG_PRECISION_FP16X2 ? 2 : 3;
   }

@@ -37,7 +37,7 @@ class UNet:
         self.BN = BN
         self.device = torch.device("cpu")
         # "mixed" (default) meets the north-star Dice bar: fp16 operands (TF32's mantissa, the reference's own cuDNN
-        # default) except that dc2, the full-resolution 192->64 decoder layer, reads fp16 hi+lo activations.  "fp16" is the fast
+        # default) except that the two full-resolution decoder layers read fp16 hi+lo activations (dc2: its skip input; dc1).  "fp16" is the fast
         # all-16-bit plan, "fp16x2" / "fp16x3" split every layer (x3 is fp32-faithful), "bf16" for range over precision.
         self.precision = os.environ.get("OAI_B200_SEG_PRECISION", "mixed")
         self._sd = self._blank_state_dict()

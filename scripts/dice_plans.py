@@ -17,9 +17,14 @@ def main():
     from oracle import seg_oracle
     names = ["ec0", "ec1", "ec2", "ec3", "ec4", "ec5", "ec6", "ec7", "dc9", "dc8", "dc7", "dc6", "dc5", "dc4", "dc3",
              "dc2", "dc1"]
-    plans = {"fp16": {}, "dc1": {"dc1": 2}, "dc2": {"dc2": 2}, "dc1+dc2 (mixed)": {"dc1": 2, "dc2": 2},
-             "dc2 skip only": {"dc2": 4}, "dc2 skip + dc1": {"dc2": 4, "dc1": 2}, "dc2 up only": {"dc2": 5}, "dc1+dc2+ec1": {"dc1": 2, "dc2": 2, "ec1": 2}, "fp16x2": {n: 2 for n in names[1:]},
-             "fp16x3": {n: 3 for n in names[1:]}}
+    plans = {"fp16": {}, "dc2 (mixed)": {"dc2": 2}, "dc1+dc2": {"dc1": 2, "dc2": 2},
+             "dc2 skip only": {"dc2": 4}, "dc2 skip + dc1": {"dc2": 4, "dc1": 2}, "dc2 up only": {"dc2": 5},
+             "dc2 skip + dc1 x3": {"dc2": 4, "dc1": 3}, "dc2 skip + dc1 + ec1": {"dc2": 4, "dc1": 2, "ec1": 2},
+             "dc2 skip + dc1 + dc5 skip": {"dc2": 4, "dc1": 2, "dc5": 4}, "dc2 up + dc1": {"dc2": 5, "dc1": 2},
+             "dc2 skip + dc1 + ec2": {"dc2": 4, "dc1": 2, "ec2": 2},
+             "fp16x2": {n: 2 for n in names[1:]}, "fp16x3": {n: 3 for n in names[1:]}}
+    if len(sys.argv) > 1:
+        plans = {k: v for k, v in plans.items() if any(a in k for a in sys.argv[1:])}
     for fx in ("seg_small_pertap", "seg_small_nobn", "seg_prod_tile"):
         z, m = load_golden(fx)
         sd = seg_oracle.make_unet_state_dict(m["seed"], 1, 2, m["bias"], m["BN"], True, m["head_gain"], m["head_bias"])
