@@ -353,6 +353,48 @@ int stem_launch(const StemParams& p, cudaStream_t st) {
 // in: [N,D,H,W,Cin8*8] of which the first C8*8 channels are pooled (a [hi | lo] tensor pooled through its hi plane:
 // rounding is monotonic, so max(hi) is the hi of the max).  With split != 0 the tensor is [hi | lo] on both sides and
 // the winner is chosen by hi + lo; its two halves are copied unchanged.
+// packed 2 x 16-bit maximum without leaving the storage format (HMNMX2)
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b, int fmt) {
+  if (fmt == 0) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// The common case (one 16-bit plane in and out): the eight 16-byte loads of a window are issued back to back and
+// reduced with packed maxima -- ~100 instructions and 40 registers per thread.  The first version converted every
+// value to fp32 (500 instructions, 64 registers, half occupancy) and reached 60 % of the HBM rate
+// (profiles/r02_ncu_pool_stem.txt).
+__global__ void __launch_bounds__(256) maxpool2_packed_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                              int N, int D, int H, int W, int C8, int Cin8, int fmt) {
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(N) * Do * Ho * Wo * C8;
+  const size_t sW = Cin8, sH = static_cast<size_t>(W) * Cin8, sD = static_cast<size_t>(H) * W * Cin8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int c = r % C8; r /= C8;
+    const int w = r % Wo; r /= Wo;
+    const int h = r % Ho; r /= Ho;
+    const int d = r % Do; r /= Do;
+    const uint4* p = in + (((static_cast<size_t>(r) * D + 2 * d) * H + 2 * h) * W + 2 * w) * Cin8 + c;
+    const uint4 v0 = __ldg(p), v1 = __ldg(p + sW), v2 = __ldg(p + sH), v3 = __ldg(p + sH + sW);
+    const uint4 v4 = __ldg(p + sD), v5 = __ldg(p + sD + sW), v6 = __ldg(p + sD + sH), v7 = __ldg(p + sD + sH + sW);
+    uint4 o;
+    o.x = max16x2(max16x2(max16x2(v0.x, v1.x, fmt), max16x2(v2.x, v3.x, fmt), fmt),
+                  max16x2(max16x2(v4.x, v5.x, fmt), max16x2(v6.x, v7.x, fmt), fmt), fmt);
+    o.y = max16x2(max16x2(max16x2(v0.y, v1.y, fmt), max16x2(v2.y, v3.y, fmt), fmt),
+                  max16x2(max16x2(v4.y, v5.y, fmt), max16x2(v6.y, v7.y, fmt), fmt), fmt);
+    o.z = max16x2(max16x2(max16x2(v0.z, v1.z, fmt), max16x2(v2.z, v3.z, fmt), fmt),
+                  max16x2(max16x2(v4.z, v5.z, fmt), max16x2(v6.z, v7.z, fmt), fmt), fmt);
+    o.w = max16x2(max16x2(max16x2(v0.w, v1.w, fmt), max16x2(v2.w, v3.w, fmt), fmt),
+                  max16x2(max16x2(v4.w, v5.w, fmt), max16x2(v6.w, v7.w, fmt), fmt), fmt);
+    out[i] = o;
+  }
+}
+
 __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N,
                                                        int D, int H, int W, int C8, int Cin8, int split, int fmt) {
   const int Do = D / 2, Ho = H / 2, Wo = W / 2;
@@ -417,6 +459,11 @@ int maxpool2_launch(const void* in, void* out, int N, int D, int H, int W, int C
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
+  if (!out_split) {
+    maxpool2_packed_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        static_cast<const uint4*>(in), static_cast<uint4*>(out), N, D, H, W, C / 8, (in_split ? 2 : 1) * (C / 8), fmt);
+    return launched("maxpool2_packed_kernel");
+  }
   maxpool2_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const uint4*>(in),
                                                                    static_cast<uint4*>(out), N, D, H, W, C / 8,
                                                                    (in_split ? 2 : 1) * (C / 8), out_split, fmt);
