@@ -24,6 +24,7 @@ constexpr int kFlagForceKd1 = 4;
 constexpr int kFlagNoFastPath = 8;
 constexpr int kFlagWideN = 16;     // A/B: keep 256-wide N tiles for 3x3x3 layers with cout >= 256 (one kd per weight block)
 constexpr int kFlagWideRows = 32;  // A/B: keep 128-byte rows (zero-filled upper half) for a 32-channel source
+constexpr int kFlagNoPingPong = 128;  // A/B: k2s2 units use every TMEM column (no accumulator ping-pong)
 constexpr int kFlagOneKhRow = 64;  // A/B: one kh row per A stage even where the three-row stage applies
 constexpr size_t kSmemBudget = 232448 - 1024 - 48 * 8 - 2112 - 2048;  // 227 KB minus alignment slack, barriers, head weights, bias
 
@@ -38,6 +39,7 @@ struct Chunk {
 struct Plan {
   int mode, kd_per_block, R, Rd, up_groups, nhalf, cph, nblk, nch, k16, row_bytes, TW, TH, n_wbuf, n_astage;
   int nkh;   // kh rows per A stage at launch (the packed image is the same: three consecutive kh blocks form one)
+  int pingpong;  // kModeUp2: accumulator halves alternate between consecutive units
   uint32_t wblock_bytes, astage_bytes, astage_stride;
   Chunk chunks[kMaxChunks];
 };
@@ -102,6 +104,7 @@ int make_plan(const ConvSpec& s, Plan* pl, int d_cnt = 0) {
   pl->R = R;
   pl->Rd = R;
   pl->up_groups = 1;
+  pl->pingpong = 0;
   if (build_chunks(s, pl)) return 1;
   const int c0v = split_src(s.terms, 0) ? 2 * c0 : c0;  // channels the first source's chunks run over
   pl->k16 = (c1 == 0 && c0v <= 32) ? (c0v <= 16 ? 1 : 2) : 4;
@@ -114,6 +117,13 @@ int make_plan(const ConvSpec& s, Plan* pl, int d_cnt = 0) {
     pl->mode = kModeUp2;
     pl->kd_per_block = 1;
     pl->R = 512 / pl->cph < 8 ? 512 / pl->cph : 8;
+    // All accumulators of a k2s2 unit complete together (one K pass over the input channels), so with every TMEM
+    // column in use the next unit's first MMA waits for the whole epilogue.  Half the taps per unit and alternating
+    // accumulator halves let the tensor pipe run through the epilogue of the previous unit.
+    if (pl->R >= 2 && !(flags & (kFlagNoFastPath | kFlagBaseOffFormula | kFlagNoPingPong))) {
+      pl->R /= 2;
+      pl->pingpong = 1;
+    }
     pl->Rd = 1;
     pl->up_groups = 8 / pl->R;
     pl->wblock_bytes = pl->R * pl->cph * rb;
@@ -371,6 +381,7 @@ int conv_run(const ConvSpec& s, const ConvLaunch& a, cudaStream_t st) {
   p.mode = pl.mode; p.kd_per_block = pl.kd_per_block; p.nblk = pl.nblk / pl.nkh;
   p.wblock_bytes = pl.wblock_bytes * pl.nkh; p.n_wbuf = pl.n_wbuf; p.n_astage = pl.n_astage;
   p.nkh = pl.nkh;
+  p.acc_pingpong = pl.pingpong;
   p.w_resident = (p.nblk == 1 && pl.nhalf == 1 && pl.up_groups == 1 && pl.n_wbuf == 1) ? 1 : 0;
   p.astage_bytes = pl.astage_bytes; p.astage_stride = pl.astage_stride;
   p.ab_format = s.fmt; p.relu = a.relu;

@@ -264,10 +264,10 @@ __device__ __forceinline__ void issue_first(const IssueConsts& c, uint32_t tmem_
 }
 
 template <int NKW, int K16N, int PER, int NKH>
-__device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const uint32_t tmem_base, uint8_t* abuf,
+__device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const uint32_t tmem_base0, uint8_t* abuf,
                                                 uint8_t* wbuf, const uint32_t wstride, uint64_t* full_a,
                                                 uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
-                                                uint64_t* acc_full, uint64_t* acc_empty) {
+                                                uint64_t* acc_full0, uint64_t* acc_empty0) {
   const int mode = p.mode, R_acc = p.R, nblk = p.nblk, nst = p.n_astage, nwb = p.n_wbuf, Dm1 = p.D - 1;
   const uint32_t rowb = static_cast<uint32_t>(p.row_bytes), sbo = 8u * rowb, lay = rowb == 128u ? 2u : 4u;
   IssueConsts c;
@@ -291,12 +291,22 @@ __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const 
   bool have_w = false;
   const bool leader = elect_one();
   int stage = 0, wb = 0;
-  uint32_t aphase = 0, wphase = 0, use_bits = 0;  // use_bits: per-accumulator mbarrier phase (flips per use)
+  uint32_t aphase = 0, wphase = 0;
+  uint32_t ub0 = 0, ub1 = 0;                      // per-accumulator mbarrier phase (flips per use), per TMEM half
   uint32_t a_lo = a_lo0;                          // descriptor low word of the current A stage
+  int half = 0;
   for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
     const UnitInfo ui = decode_unit(p, u);
     const int d0 = ui.d0, ra = ui.ra, rd = ui.rd;
     const uint32_t all_acc = (1u << ra) - 1u;
+    // accumulator ping-pong (kModeUp2): this unit's accumulators are the half `half` of TMEM / of the barrier arrays
+    const int ab = half * R_acc;
+    const uint32_t tmem_base = tmem_base0 + static_cast<uint32_t>(ab) * c.cout;
+    uint64_t* const acc_full = acc_full0 + ab;
+    uint64_t* const acc_empty = acc_empty0 + ab;
+    const int this_half = half;
+    const uint32_t use_bits = this_half ? ub1 : ub0;
+    if (p.acc_pingpong) half ^= 1;
     uint32_t touched = 0, signaled = 0;
     int kd_it = 0;  // kd counter of the one-kd-per-block schedule (fastest block index there)
     for (int b = 0; b < nblk; ++b) {
@@ -359,7 +369,8 @@ __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const 
       for (int a = 0; a < ra; ++a)
         if (!((signaled >> a) & 1u)) umma_commit(&acc_full[a]);
     }
-    use_bits ^= all_acc;
+    if (this_half) ub1 = use_bits ^ all_acc;
+    else ub0 = use_bits ^ all_acc;
   }
   __syncwarp();
 }
@@ -595,14 +606,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     const uint32_t s_bias_addr = smem_u32(s_bias), s_head_addr = smem_u32(s_head);
     const int m = q * 32 + lane;
     const int th = m / p.TW, tw = m % p.TW;
-    uint32_t use_bits = 0;
+    uint32_t ub0 = 0, ub1 = 0;
+    int half = 0;
+    const uint32_t tmem_base0 = tmem_base;
+    uint64_t* const acc_full0 = acc_full;
+    uint64_t* const acc_empty0 = acc_empty;
     uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
     float amax = 0.f;   // largest |activation| this thread rounded to 16 bits
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
       const UnitInfo ui = decode_unit(p, u);
+      // accumulator ping-pong (kModeUp2): same half selection as the MMA warp
+      const int ab = half * p.R;
+      const uint32_t tmem_base = tmem_base0 + static_cast<uint32_t>(ab * p.cout);
+      uint64_t* const acc_full = acc_full0 + ab;
+      uint64_t* const acc_empty = acc_empty0 + ab;
+      const int this_half = half;
+      const uint32_t use_bits = this_half ? ub1 : ub0;
+      if (p.acc_pingpong) half ^= 1;
       const long long off0 = p.obase + ui.n * p.osN + (ui.h0 + th) * p.osH + (ui.w0 + tw) * p.osW +
                              static_cast<long long>(ui.nh) * p.cout;
-      for (int a = eg; a < ui.ra; a += kEpiGroups) {
+      for (int a = 0; a < ui.ra; ++a) {
+        if (((ab + a) % kEpiGroups) != eg) continue;   // the groups share the PHYSICAL accumulators round-robin
         mbar_wait(&acc_full[a], (use_bits >> a) & 1u, 600 + a);
         tc_fence_after();
         if (p.head.enabled) {
@@ -675,7 +699,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[a]);
       }
-      use_bits ^= (1u << ui.ra) - 1u;
+      if (this_half) ub1 = use_bits ^ ((1u << ui.ra) - 1u);
+      else ub0 = use_bits ^ ((1u << ui.ra) - 1u);
     }
     if (p.ab_format == 0 && !(amax <= 65504.f)) atomicAdd(&g_fp16_overflow, 1u);   // also catches NaN
   }

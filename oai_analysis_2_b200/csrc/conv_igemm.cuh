@@ -57,6 +57,8 @@ struct ConvIgemmParams {
   int nkh;          // row-shared mode: kh rows of an input slice held by ONE A stage (1, or 3 for a 32-channel source:
                     // the stage is a 3 x 130-voxel box and the weight block is the whole 27-tap image)
   int w_resident;   // the layer has a single weight block: loaded once per CTA, never released
+  int acc_pingpong; // kModeUp2: a unit uses R of the 2R accumulators TMEM holds, consecutive units of a CTA alternate
+                    // between the two halves, so the MMAs of one unit overlap the epilogue of the previous one
   int n_astage;     // A ring depth
   uint32_t astage_bytes;  // bytes landed per A stage (expect_tx)
   uint32_t astage_stride; // smem stride between A stages (1024-aligned)
