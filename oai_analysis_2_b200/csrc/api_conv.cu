@@ -40,6 +40,7 @@ struct Plan {
   int mode, kd_per_block, R, Rd, up_groups, nhalf, cph, nblk, nch, k16, row_bytes, TW, TH, n_wbuf, n_astage;
   int nkh;   // kh rows per A stage at launch (the packed image is the same: three consecutive kh blocks form one)
   int pingpong;  // kModeUp2: accumulator halves alternate between consecutive units
+  int stationary;  // one shared-memory buffer per weight block of a (N split, tap group); units ordered group-major
   uint32_t wblock_bytes, astage_bytes, astage_stride;
   Chunk chunks[kMaxChunks];
 };
@@ -160,6 +161,16 @@ int make_plan(const ConvSpec& s, Plan* pl, int d_cnt = 0) {
   pl->astage_bytes = (pl->mode == kModeRowShared ? 130 : 128) * rb * pl->nkh;
   pl->astage_stride = (pl->astage_bytes + 1023u) & ~1023u;
   const size_t wstride = (static_cast<size_t>(pl->wblock_bytes) * pl->nkh + 1023u) & ~size_t(1023);
+  // Stationary weights: a k2s2 unit is one K pass over a 128-voxel tile, so streaming its weight blocks per unit costs
+  // ~64 B/clk/SM of L2 bandwidth (dc6: 128 KB per 2048-clock unit); when all blocks of a tap group fit beside four A
+  // stages they get one buffer each and stay put while the CTA walks its tiles.  The three-row ec1 plan is the same
+  // thing with a single group.
+  pl->stationary = 0;
+  if (pl->nkh == 3) pl->stationary = 1;
+  if (pl->mode == kModeUp2 && pl->pingpong && pl->nblk <= 4 && pl->nblk * wstride + 4 * pl->astage_stride <= kSmemBudget) {
+    pl->stationary = 1;
+    pl->n_wbuf = pl->nblk;
+  }
   const size_t left = kSmemBudget - pl->n_wbuf * wstride;
   int ns = static_cast<int>(left / pl->astage_stride);
   if (ns > 8) ns = 8;
@@ -382,7 +393,7 @@ int conv_run(const ConvSpec& s, const ConvLaunch& a, cudaStream_t st) {
   p.wblock_bytes = pl.wblock_bytes * pl.nkh; p.n_wbuf = pl.n_wbuf; p.n_astage = pl.n_astage;
   p.nkh = pl.nkh;
   p.acc_pingpong = pl.pingpong;
-  p.w_resident = (p.nblk == 1 && pl.nhalf == 1 && pl.up_groups == 1 && pl.n_wbuf == 1) ? 1 : 0;
+  p.w_stationary = pl.stationary;
   p.astage_bytes = pl.astage_bytes; p.astage_stride = pl.astage_stride;
   p.ab_format = s.fmt; p.relu = a.relu;
   p.base_off_mode = (s.flags & kFlagBaseOffFormula) ? 1 : 0;

@@ -86,10 +86,18 @@ __device__ __forceinline__ UnitInfo decode_unit(const ConvIgemmParams& p, int u)
   UnitInfo ui;
   const int npw = p.W / p.TW;
   const int np = npw * p.hp_cnt, ndg = (p.d_cnt + p.Rd - 1) / p.Rd;
-  ui.nh = u % p.nhalf;
-  u /= p.nhalf;
-  ui.tg = u % p.up_groups;
-  u /= p.up_groups;
+  if (p.w_stationary) {   // (N split, tap group) slowest: consecutive units of a CTA share their weight blocks
+    const int per_key = np * ndg * p.NT;
+    const int key = u / per_key;
+    u -= key * per_key;
+    ui.tg = key % p.up_groups;
+    ui.nh = key / p.up_groups;
+  } else {
+    ui.nh = u % p.nhalf;
+    u /= p.nhalf;
+    ui.tg = u % p.up_groups;
+    u /= p.up_groups;
+  }
   const int patch = u % np;
   u /= np;
   ui.d0 = p.d_lo + (u % ndg) * p.Rd;
@@ -287,8 +295,8 @@ __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const 
   c.b_kw = static_cast<uint32_t>(ns) * c.tap16;
   c.kh_a = (130u * rowb) >> 4;
   c.kh_b = 3u * c.b_kw;
-  const bool resident = p.w_resident != 0;
-  bool have_w = false;
+  const bool stationary = p.w_stationary != 0;
+  int prev_key = -1;
   const bool leader = elect_one();
   int stage = 0, wb = 0;
   uint32_t aphase = 0, wphase = 0;
@@ -309,6 +317,16 @@ __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const 
     if (p.acc_pingpong) half ^= 1;
     uint32_t touched = 0, signaled = 0;
     int kd_it = 0;  // kd counter of the one-kd-per-block schedule (fastest block index there)
+    // stationary weights: wait for the blocks only when this unit's group differs from the previous unit's, release
+    // them only when the next unit's does (the weight producer applies the same rule)
+    const int key = ui.nh * p.up_groups + ui.tg;
+    const bool reload = !(stationary && key == prev_key);
+    prev_key = key;
+    bool release = true;
+    if (stationary && u + static_cast<int>(gridDim.x) < p.nunits) {
+      const UnitInfo un = decode_unit(p, u + static_cast<int>(gridDim.x));
+      release = un.nh * p.up_groups + un.tg != key;
+    }
     for (int b = 0; b < nblk; ++b) {
       int kdlo = 0, kdhi = 2;
       if (one_kd) { kdlo = 1; kdhi = 1; }
@@ -316,8 +334,7 @@ __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const 
       const int dlo = max(0, d0 + kdlo - 1);
       const int dhi = min(Dm1, d0 + rd - 1 + kdhi - 1);
       const bool last_blk = b == nblk - 1;
-      if (!(resident && have_w)) mbar_wait(&full_w[wb], wphase, 300 + wb);
-      have_w = true;
+      if (reload) mbar_wait(&full_w[wb], wphase, 300 + wb);
       const uint32_t w_lo = w_lo0 + static_cast<uint32_t>(wb) * w_step;
       int a_first = up2 ? 0 : dlo - kdhi + 1 - d0;  // accumulator hit by the first stacked tap
       for (int dp = dlo; dp <= dhi; ++dp, a_first += a_inc) {
@@ -357,12 +374,10 @@ __device__ __forceinline__ void mma_issuer_fast(const ConvIgemmParams& p, const 
           a_lo = a_lo0;
         }
       }
-      if (!resident) {
-        if (leader) umma_commit(&empty_w[wb]);
-        if (++wb == nwb) {
-          wb = 0;
-          wphase ^= 1u;
-        }
+      if (release && leader) umma_commit(&empty_w[wb]);
+      if (++wb == nwb) {
+        wb = 0;
+        if (reload) wphase ^= 1u;   // one phase per (re)load of the buffers
       }
     }
     if (leader && signaled != all_acc) {
@@ -556,12 +571,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------ weight producer
     if (lane == 0) {
-      int wb = 0;
+      int wb = 0, prev_key = -1;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
         const UnitInfo ui = decode_unit(p, u);
         const uint8_t* src = p.wpack + static_cast<size_t>(ui.nh * p.up_groups + ui.tg) * p.nblk * p.wblock_bytes;
-        if (p.w_resident && u != static_cast<int>(blockIdx.x)) break;   // the single block stays in shared memory
+        const int key = ui.nh * p.up_groups + ui.tg;
+        if (p.w_stationary && key == prev_key) continue;   // this group's blocks are still in shared memory
+        prev_key = key;
         for (int b = 0; b < p.nblk; ++b) {
           mbar_wait(&empty_w[wb], phase ^ 1u, 200 + wb);
           mbar_arrive_expect_tx(&full_w[wb], p.wblock_bytes);

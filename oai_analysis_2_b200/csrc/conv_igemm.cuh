@@ -56,7 +56,9 @@ struct ConvIgemmParams {
   int n_wbuf;       // weight buffers in smem
   int nkh;          // row-shared mode: kh rows of an input slice held by ONE A stage (1, or 3 for a 32-channel source:
                     // the stage is a 3 x 130-voxel box and the weight block is the whole 27-tap image)
-  int w_resident;   // the layer has a single weight block: loaded once per CTA, never released
+  int w_stationary; // every weight block of a (N split, tap group) has its own shared-memory buffer (n_wbuf == nblk) and the
+                    // units are ordered split / tap-group major: the blocks are (re)loaded only when a CTA's next unit
+                    // belongs to another group -- once per kernel for a single-group layer (ec1), eight times for dc6
   int acc_pingpong; // kModeUp2: a unit uses R of the 2R accumulators TMEM holds, consecutive units of a CTA alternate
                     // between the two halves, so the MMAs of one unit overlap the epilogue of the previous one
   int n_astage;     // A ring depth
