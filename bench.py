@@ -259,7 +259,8 @@ def run_full(args):
         mark = {}
 
         def on_record():
-            _lib.lib.oai_profile_begin()
+            if not os.environ.get("OAI_BENCH_NO_CONV_EVENTS"):   # A/B: what the 32 event-record nodes in the graph cost
+                _lib.lib.oai_profile_begin()
             mark["n0"] = _lib.launch_count()
 
         pipe.capture(vols_d[0].shape, geom, verts_d.shape[0], on_record, overlap_registration=args.overlap_registration)
