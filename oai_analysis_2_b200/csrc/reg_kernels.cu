@@ -90,49 +90,57 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
     for (int c = ks; c < nci; c += KS) {
       const float* plane = in_n + (ci0 + c) * p.in_cstride;
       const float* wc = s_w + c * 27 * CO_T;
+      // one (kd, kh) input row: NIN x-adjacent samples (zeros outside the volume), leaky ReLU applied on load
+      auto load_row = [&](int r, float (&xin)[NIN]) {
+        const int z = zi0 + r / 3, y = yi0 + r % 3;
+        if (z < 0 || z >= p.Di || y < 0 || y >= p.Hi) {
 #pragma unroll
-      for (int kd = 0; kd < 3; ++kd) {
-        const int z = zi0 + kd;
-        if (z < 0 || z >= p.Di) continue;
+          for (int i = 0; i < NIN; ++i) xin[i] = 0.f;
+          return;
+        }
+        const float* row = plane + (static_cast<size_t>(z) * p.Hi + y) * p.Wi;
+        if (XS * STRIDE % 4 == 0 && vec_ok) {
+          // xi0 + 1 is a multiple of 4: aligned float4 loads for the body, scalars for the two halo samples
+          xin[0] = xi0 >= 0 ? __ldg(row + xi0) : 0.f;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const int y = yi0 + kh;
-          if (y < 0 || y >= p.Hi) continue;
-          const float* row = plane + (static_cast<size_t>(z) * p.Hi + y) * p.Wi;
-          float xin[NIN];
-          if (XS * STRIDE % 4 == 0 && vec_ok) {
-            // xi0 + 1 is a multiple of 4: aligned float4 loads for the body, scalars for the two halo samples
-            xin[0] = xi0 >= 0 ? __ldg(row + xi0) : 0.f;
-#pragma unroll
-            for (int i = 0; i < (NIN - 1) / 4; ++i) {
-              const float4 m = (xi0 + 1 + 4 * i < p.Wi) ? __ldg(reinterpret_cast<const float4*>(row + xi0 + 1) + i)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-              xin[1 + 4 * i] = m.x; xin[2 + 4 * i] = m.y; xin[3 + 4 * i] = m.z; xin[4 + 4 * i] = m.w;
-            }
-#pragma unroll
-            for (int i = 1 + 4 * ((NIN - 1) / 4); i < NIN; ++i) xin[i] = (xi0 + i < p.Wi) ? __ldg(row + xi0 + i) : 0.f;
-          } else {
-#pragma unroll
-            for (int i = 0; i < NIN; ++i) {
-              const int x = xi0 + i;
-              xin[i] = (x >= 0 && x < p.Wi) ? __ldg(row + x) : 0.f;
-            }
-          }
-          if (p.leaky_in) {
-#pragma unroll
-            for (int i = 0; i < NIN; ++i) xin[i] = leaky(xin[i]);
+          for (int i = 0; i < (NIN - 1) / 4; ++i) {
+            const float4 m = (xi0 + 1 + 4 * i < p.Wi) ? __ldg(reinterpret_cast<const float4*>(row + xi0 + 1) + i)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            xin[1 + 4 * i] = m.x; xin[2 + 4 * i] = m.y; xin[3 + 4 * i] = m.z; xin[4 + 4 * i] = m.w;
           }
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const float* wk = wc + ((kd * 3 + kh) * 3 + kw) * CO_T;
-            float wv[CO_T];
+          for (int i = 1 + 4 * ((NIN - 1) / 4); i < NIN; ++i) xin[i] = (xi0 + i < p.Wi) ? __ldg(row + xi0 + i) : 0.f;
+        } else {
 #pragma unroll
-            for (int j = 0; j < CO_T; ++j) wv[j] = wk[j];
-#pragma unroll
-            for (int i = 0; i < XS; ++i)
-#pragma unroll
-              for (int j = 0; j < CO_T; ++j) acc[i][j] = fmaf(xin[i * STRIDE + kw], wv[j], acc[i][j]);
+          for (int i = 0; i < NIN; ++i) {
+            const int x = xi0 + i;
+            xin[i] = (x >= 0 && x < p.Wi) ? __ldg(row + x) : 0.f;
           }
+        }
+        if (p.leaky_in) {
+#pragma unroll
+          for (int i = 0; i < NIN; ++i) xin[i] = leaky(xin[i]);
+        }
+      };
+      // The nine rows are software-pipelined: row r + 1 is in flight while row r feeds its 3 * XS * CO_T FMAs.  Loading
+      // and consuming one row at a time left every warp waiting a full L2 round trip per row (the 18 -> 3 last conv of
+      // tallUNet2 ran at a third of the FMA rate).
+      float xr[2][NIN];
+      load_row(0, xr[0]);
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        if (r + 1 < 9) load_row(r + 1, xr[(r + 1) & 1]);
+        const float (&xin)[NIN] = xr[r & 1];
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float* wk = wc + (r * 3 + kw) * CO_T;
+          float wv[CO_T];
+#pragma unroll
+          for (int j = 0; j < CO_T; ++j) wv[j] = wk[j];
+#pragma unroll
+          for (int i = 0; i < XS; ++i)
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) acc[i][j] = fmaf(xin[i * STRIDE + kw], wv[j], acc[i][j]);
         }
       }
     }
