@@ -20,10 +20,14 @@ def image_normalize(image, window_min_perc, window_max_perc, output_min, output_
 def deform_probmap(phi_AB, image_A, image_B, prob, image_type="FC"):
     """dask_processing.py:95-111 (deform_probmap_delayed): resample `prob` (on image_A's grid) through phi_AB onto
     image_B's grid with linear interpolation and default pixel 0.  Returns an image like image_B (float64)."""
-    arr = np.ascontiguousarray(itk_compat.array_from_image(prob), dtype=np.float32)
-    src = torch.from_numpy(arr).to(phi_AB.disp.device)[None]
+    # float64 host image -> float32 device tensor through a cached pinned staging buffer (itk_compat.to_device_f32);
+    # only the float64 result the reference's contract asks for is a fresh host allocation
+    src = itk_compat.to_device_f32(prob, phi_AB.disp.device, "deform_in")[None]
     out = phi_AB.resample_device(src, Geometry.of(prob), Geometry.of(image_B))
-    return itk_compat.image_from_array(out[0].cpu().to(torch.float64).numpy(), like=image_B)
+    pin_out = itk_compat.pinned_buffer("deform_out", out.shape[1:])
+    pin_out.copy_(out[0], non_blocking=True)
+    torch.cuda.current_stream(out.device).synchronize()
+    return itk_compat.image_from_array(pin_out.to(torch.float64).numpy(), like=image_B)
 
 
 deform_probmap_delayed = deform_probmap

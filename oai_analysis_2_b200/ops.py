@@ -110,10 +110,10 @@ class SegHandle:
         self.device = torch.device("cuda", torch.cuda.current_device())
         check(lib.oai_seg_create(ctypes.byref(cfg), arr, len(state_dict), ctypes.byref(self._h)), "seg_create")
 
-    def __del__(self):
+    def __del__(self, _destroy=lib.oai_seg_destroy):   # bound at class creation: module globals are gone at shutdown
         h, self._h = getattr(self, "_h", None), None
         if h:
-            lib.oai_seg_destroy(h)
+            _destroy(h)
 
     def num_tiles(self, vol_shape):
         return int(lib.oai_seg_num_tiles(self._h, ptr(np.asarray(vol_shape, dtype=np.int32))))

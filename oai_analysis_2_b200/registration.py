@@ -1,7 +1,6 @@
 """Drop-in for oai_analysis/registration.py (ICON_Registration) on B200."""
 import numpy as np
 
-from . import itk_compat
 from .icon_registration import itk_wrapper, pretrained_models
 
 
@@ -14,8 +13,11 @@ class ICON_Registration:
             pretrained=pretrained, weights_path=weights_path)
 
     def register(self, fixed_image, moving_image):
-        f, m = itk_compat.array_from_image(fixed_image), itk_compat.array_from_image(moving_image)
-        print("fixed range", np.min(f), np.max(f))
-        print("moving range", np.min(m), np.max(m))
-        phi_fixed_moving, _ = itk_wrapper.register_pair(self.register_module, fixed_image, moving_image)
+        # the reference prints the two intensity ranges before registering (registration.py:23-24); here they come from
+        # the device-side reduction register_pair needs anyway, so they are printed right after it
+        ranges = []
+        phi_fixed_moving, _ = itk_wrapper.register_pair(self.register_module, fixed_image, moving_image,
+                                                        ranges_out=ranges)
+        print("fixed range", np.float32(ranges[0]), np.float32(ranges[1]))
+        print("moving range", np.float32(ranges[2]), np.float32(ranges[3]))
         return phi_fixed_moving

@@ -77,8 +77,7 @@ class Segmenter3DInPatchClassWise(Segmenter3DInPatch):
     def segment(self, image, if_output_prob_map=False, if_output_itk=True):
         if not self.ready:
             self.pred_setup()
-        arr = np.ascontiguousarray(itk_compat.array_from_image(image), dtype=np.float32)
-        vol = torch.from_numpy(arr).to(self.device, non_blocking=True)
+        vol = itk_compat.to_device_f32(image, self.device, "seg_in")
         out = self.segment_device(vol, if_output_prob_map, self.config.get("tiles_per_batch"))
         # D2H through a cached pinned buffer, then the float64 the reference assembles into (np.zeros default, :493)
         # with torch's multi-threaded cast (a pageable .cpu() plus numpy's astype cost ~4x more per knee)
