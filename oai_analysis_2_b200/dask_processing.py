@@ -10,11 +10,13 @@ def image_normalize(image, window_min_perc, window_max_perc, output_min, output_
     """dask_processing.py:10-26: window the intensities between two percentiles (np.percentile, "linear" method) and
     rescale to [output_min, output_max] (itk.IntensityWindowingImageFilter).  Runs on the device (exact radix select,
     no sort); returns an image like `image` (float32 pixels, as at the segmentation call site :177)."""
-    arr = np.ascontiguousarray(itk_compat.array_from_image(image), dtype=np.float32)
-    vol = torch.from_numpy(arr).to(device, non_blocking=True)
+    vol = itk_compat.to_device_f32(image, device, "normalize_in")
     out = ops.intensity_window(vol, float(window_min_perc), float(window_max_perc), float(output_min),
                                float(output_max), out=vol)
-    return itk_compat.image_from_array(out.cpu().numpy(), like=image)
+    pin = itk_compat.pinned_buffer("normalize_out", out.shape)
+    pin.copy_(out, non_blocking=True)
+    torch.cuda.current_stream(out.device).synchronize()
+    return itk_compat.image_from_array(pin.numpy().copy(), like=image)
 
 
 def deform_probmap(phi_AB, image_A, image_B, prob, image_type="FC"):
