@@ -282,6 +282,49 @@ OAI_API int oai_avgpool3d_2_ceil(const float* in, int C, const int* in_dims, flo
 OAI_API int oai_displacement_field(const float* phi, const int* dims, float* disp, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Stage-level registration  (reference: ICON_Registration.__init__ / register, oai_analysis/registration.py:18-27,
+ * i.e. icon_registration.pretrained_models.OAI_knees_gradICON_model + itk_wrapper.register_pair; worker-side call
+ * sites oai_analysis/dask_processing.py:77,85): two calls register a pair in both directions; the module tree, the
+ * tallUNet2 layer order, concatenation buffers, BatchNorm folding, weight packing, the TwoStep / Downsample closures
+ * and the workspace layout live inside the library.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct oai_reg_handle* oai_reg_t;
+
+/* Host arithmetic only (no GPU): validates a regis_net state dict exactly as oai_reg_create does and writes the module
+ * tree it encodes, e.g. "TwoStep(TwoStep(Down(TwoStep(FFVF, FFVF)), FFVF), FFVF)".  Keys are icon's own paths
+ * ("regis_net." prefix optional): netPhi / netPsi = TwoStepRegistration children, net = DownsampleRegistration.net or,
+ * at the end of a path, FunctionFromVectorField.net (a tallUNet2: downConvs.N / upConvs.N / batchNorms.N / lastConv).
+ * "identity_map" buffers and "num_batches_tracked" counters are skipped; any other tensor outside a tallUNet2, an
+ * incomplete or mis-shaped tallUNet2, or a TwoStep with one child fails (nothing ever "loads" partially). */
+OAI_API int oai_reg_parse_tree(const oai_tensor* state_dict, int n_tensors, char* description,
+                               size_t description_bytes);
+/* pretrained_models.OAI_knees_gradICON_model's regis_net + assign_identity_map([1,1,*net_dims]) on the current device
+ * (net_dims z,y,x; the knee model uses 80,192,192).  The handle owns the packed weights (about 150 MB per tallUNet2);
+ * the state dict is not referenced after the call. */
+OAI_API int oai_reg_create(const oai_tensor* state_dict, int n_tensors, const int* net_dims, oai_reg_t* handle);
+OAI_API int oai_reg_destroy(oai_reg_t handle);
+OAI_API int oai_reg_describe(oai_reg_t handle, char* description, size_t description_bytes);
+OAI_API size_t oai_reg_workspace_bytes(oai_reg_t handle);
+/* itk_wrapper.register_pair(model, image_A, image_B) on device-resident float32 volumes [dims] (z,y,x) of any size:
+ * both are resized to net_dims (F.interpolate trilinear, align_corners=False), both directions run batched through
+ * the cascade.  Outputs, each optional (NULL): phi_AB / phi_BA = model.phi_AB(identity_map) / phi_BA(...), float32
+ * [3][net_dims] in [0,1] coordinates (channels z,y,x); disp_AB / disp_BA = create_itk_transform's displacement
+ * fields, float32 [net_dims][3] (x,y,z components, network-voxel units) as oai_warp_volume / oai_warp_points take
+ * them.  workspace: 256-byte aligned device memory of at least oai_reg_workspace_bytes(); asynchronous on `stream`.
+ * The cascade's own displacement fields stay in the workspace until the next forward (oai_reg_field). */
+OAI_API int oai_reg_forward(oai_reg_t handle, const float* image_A, const int* dims_A, const float* image_B,
+                            const int* dims_B, float* phi_AB, float* phi_BA, float* disp_AB, float* disp_BA,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* The cascade's displacement fields in application order (first applied first): field `index` is float32
+ * [2 directions][3][dims] at workspace + *workspace_offset (valid after oai_reg_forward on that workspace). */
+OAI_API int oai_reg_num_fields(oai_reg_t handle);
+OAI_API int oai_reg_field(oai_reg_t handle, int index, size_t* workspace_offset, int* dims);
+/* as_function(image)(phi(identity_map)) for the last pair registered on `workspace`: image [dims] (any size) warped
+ * by phi_AB (direction 0) or phi_BA (1), fused with the composition (no map is materialised). */
+OAI_API int oai_reg_warp_image(oai_reg_t handle, const float* image, const int* dims, int direction, float* out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * ITK-semantics warps  (reference: oai_analysis/dask_processing.py:95-111 deform_probmap_delayed,
  * test/test_all.py:42-52; transform = R_A o DisplacementFieldTransform o R_B^-1 built by create_itk_transform)
  * Affines are row-major 3x4 [M | t] in float64 acting on (x,y,z).

@@ -1708,11 +1708,15 @@ static int make_plane_tmap(CUtensorMap* tm, void* base, unsigned long long plane
 template <int TX>
 static int convt4_mma_dispatch(const ConvT4Params& p, cudaStream_t st) {
   using Cfg = ConvT4MmaCfg<TX>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(convt4_mma_kernel<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         static_cast<int>(Cfg::smem_bytes));
-    configured = true;
+  static bool configured[64] = {false};   // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(convt4_mma_kernel<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(Cfg::smem_bytes)),
+                            "convt4_mma: cudaFuncSetAttribute"))
+      return rc;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   CUtensorMap tm, tm_res;
   if (int rc = make_plane_tmap(&tm, p.xsplit, static_cast<unsigned long long>(2) * p.N * (p.cin / 2), 8, p, Cfg::SX,
@@ -1775,11 +1779,15 @@ int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
     // large levels: shared-memory tiled kernel (2 x 8 x 64 output voxels per block)
     constexpr int CO_T = 8;
     constexpr size_t smem = (2 * kTileCI * kTileIn + 2 * kTileCI * 64 * CO_T) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-      cudaFuncSetAttribute(convt4_tile_kernel<CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(smem));
-      configured = true;
+    static bool configured[64] = {false};   // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      if (int rc = check_cuda(cudaFuncSetAttribute(convt4_tile_kernel<CO_T>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)),
+                              "convt4_tile: cudaFuncSetAttribute"))
+        return rc;
+      if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int ntx = ((p.Wo + 1) / 2 + 31) / 32, nty = ((p.Ho + 1) / 2 + 3) / 4, ntz = (p.Do + 1) / 2;
     dim3 g(static_cast<unsigned>(ntx) * nty * ntz, p.cout / CO_T, p.N);

@@ -38,8 +38,6 @@ def register_pair(model, image_A, image_B, finetune_steps=None, return_artifacts
 
 
 def register_pair_device(model, A, B):
-    """A, B: float32 [D,H,W] cuda volumes at native resolution -> (phi_AB, phi_BA) [1,3,d,h,w] network maps."""
-    shape = tuple(model.identity_map.shape[2:])
-    A_r = ops.resize_trilinear(A, shape)
-    B_r = ops.resize_trilinear(B, shape)
-    return model(A_r, B_r)
+    """A, B: float32 [D,H,W] cuda volumes at native resolution -> (phi_AB, phi_BA) [1,3,d,h,w] network maps (the
+    F.interpolate(size=network shape, trilinear, align_corners=False) of register_pair runs inside the stage call)."""
+    return model.register_native(A, B)

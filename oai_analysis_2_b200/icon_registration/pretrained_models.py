@@ -91,6 +91,7 @@ class GradICONModel:
         self.device = torch.device("cpu")
         self.input_shape = list(INPUT_SHAPE)
         self._identity = None
+        self._handle, self._handle_key = None, None
         self.phi_AB_vectorfield = None
         self.phi_BA_vectorfield = None
 
@@ -143,65 +144,50 @@ class GradICONModel:
         self.phi_AB_vectorfield = self.phi_BA_vectorfield = None
         return self
 
-    # -- inference
-    def _run(self, node, src, tgt, fields_out):
-        """Evaluate one node of the tree on the batched pair (src -> tgt), both [2,D,H,W].  Returns the displacement
-        fields of its leaves in APPLICATION order (first applied first): TwoStep(phi, psi) returns c -> phi(psi(c))."""
-        kind = node[0]
-        if kind == "ffvf":
-            u = self.nets[node[1]](src, tgt)
-            fields_out[node[1]] = u
-            return [u]
-        if kind == "down":   # DownsampleRegistration: avg_pool3d(2, ceil_mode=True) on both images
-            lo_src = ops.avgpool2_ceil(src)
-            return self._run(node[1], lo_src, ops.avgpool2_ceil(tgt), fields_out)
-        f_phi = self._run(node[1], src, tgt, fields_out)
-        warped = self._warp(src, f_phi)              # as_function(image_A)(phi(identity_map))
-        f_psi = self._run(node[2], warped, tgt, fields_out)
-        return f_psi + f_phi
+    # -- inference: the cascade runs behind the stage-level C ABI (csrc/reg_net.cu: oai_reg_create / oai_reg_forward)
+    def _stage(self):
+        """The library-side model (packed weights + workspace), rebuilt when the weights, the network shape or the
+        device change (in-place edits of a UNet's tensors are seen through their version counters)."""
+        key = (tuple(self.input_shape[2:]), str(self.device), tuple(self.nets),
+               tuple((id(t), t._version) for net in self.nets.values() for t in net._sd.values()))
+        if self._handle is None or self._handle_key != key:
+            if self.device.type != "cuda":
+                raise RuntimeError("oai_analysis_2_b200 registration runs on CUDA (sm_100a) only")
+            self._handle = None   # release the old weights / workspace before allocating the new ones
+            self._handle = ops.RegHandle(self.state_dict(), self.input_shape[2:], self.device)
+            self._handle_key = key
+        return self._handle
 
-    @staticmethod
-    def _shortcut(fields, shape):
-        # FunctionFromVectorField adds its field without interpolation when handed the identity map of its own shape
-        return tuple(fields[0].shape[2:]) == tuple(shape)
-
-    def _warp(self, img, fields):
-        if len(fields) > 4:
-            raise NotImplementedError("registration trees with more than four cascaded fields")
-        shape = tuple(img.shape[1:])
-        out = torch.empty_like(img)
-        for k in range(img.shape[0]):
-            ops.compose(shape, [f[k] for f in fields], self._shortcut(fields, shape), img[k], want_phi=False,
-                        img_out=out[k])
-        return out
+    def register_native(self, A, B):
+        """A, B: float32 [D,H,W] cuda volumes of any size (register_pair resizes them to the network shape).  Runs both
+        directions batched through the cascade and stores phi_AB / phi_BA evaluated on the identity map."""
+        phi_AB, phi_BA, _, _ = self._stage().forward(A.contiguous().float(), B.contiguous().float())
+        self.phi_AB_vectorfield, self.phi_BA_vectorfield = phi_AB[None], phi_BA[None]
+        return self.phi_AB_vectorfield, self.phi_BA_vectorfield
 
     def forward(self, image_A, image_B):
-        """image_A/B: [1,1,D,H,W] (or [D,H,W]) float32 cuda at the network resolution.  Runs both directions
-        (batched through each UNet) and stores phi_AB / phi_BA evaluated on the identity map."""
-        A = image_A.reshape(image_A.shape[-3:]).contiguous().float()
-        B = image_B.reshape(image_B.shape[-3:]).contiguous().float()
-        full = tuple(A.shape)
-        if list(full) != self.input_shape[2:]:
-            raise ValueError(f"images must be resized to the network shape {self.input_shape[2:]}, got {list(full)}")
-        src = torch.stack((A, B))                    # direction 0 registers A->B, direction 1 B->A
-        tgt = torch.stack((B, A))
-        self.displacements = {}
-        fields = self._run(self.tree, src, tgt, self.displacements)
-        if len(fields) > 4:
-            raise NotImplementedError("registration trees with more than four cascaded fields")
-        maps = [ops.compose(full, [f[k] for f in fields], self._shortcut(fields, full))[0] for k in range(2)]
-        self.fields = fields   # the cascade's displacement fields, application order, [2 directions, 3, d, h, w] each
-        self.phi_AB_vectorfield, self.phi_BA_vectorfield = maps[0][None], maps[1][None]
-        return self.phi_AB_vectorfield, self.phi_BA_vectorfield
+        """image_A/B: [1,1,D,H,W] (or [D,H,W]) float32 cuda at the network resolution."""
+        A = image_A.reshape(image_A.shape[-3:])
+        B = image_B.reshape(image_B.shape[-3:])
+        if list(A.shape) != self.input_shape[2:]:
+            raise ValueError(f"images must be resized to the network shape {self.input_shape[2:]}, got {list(A.shape)}")
+        return self.register_native(A, B)
 
     __call__ = forward
 
+    @property
+    def fields(self):
+        """The cascade's displacement fields of the last pair, application order, [2 directions, 3, d, h, w] each
+        (views into the stage workspace: the next pair overwrites them)."""
+        return self._stage().fields()
+
     def warp_image(self, image, direction=0, out=None):
-        """as_function(image)(phi(identity_map)) for the last registered pair: `image` [D,H,W] at the network resolution
-        warped by phi_AB (direction 0) or phi_BA (1), fused with the composition (no map is materialised)."""
+        """as_function(image)(phi(identity_map)) for the last registered pair: `image` [D,H,W] (any size) warped by
+        phi_AB (direction 0) or phi_BA (1), fused with the composition (no map is materialised)."""
+        if self.phi_AB_vectorfield is None:
+            raise RuntimeError("call the model on an image pair first")
         shape = tuple(image.shape[-3:])
-        return ops.compose(shape, [f[direction] for f in self.fields], self._shortcut(self.fields, shape),
-                           image.reshape(shape), want_phi=False, img_out=out)[1]
+        return self._stage().warp_image(image.reshape(shape).contiguous(), direction, out)
 
     def _eval_on_identity(self, field, coords):
         if field is None:

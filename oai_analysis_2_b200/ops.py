@@ -254,6 +254,85 @@ def seg_head(act, w, b, out, geom, tile0, crop_zyx, out_mode=0, ab_format=0):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ stage-level registration
+def _tensor_array(state_dict):
+    keep, arr = [], (_Tensor * len(state_dict))()
+    for i, (k, v) in enumerate(state_dict.items()):
+        a = np.ascontiguousarray(torch.as_tensor(v).detach().cpu().numpy(), dtype=np.float32)
+        keep.append(a)
+        shape = list(a.shape)[:5] + [0] * max(0, 5 - a.ndim)
+        arr[i] = _Tensor(k.encode(), a.ctypes.data, a.ndim, (c_ll * 5)(*shape))
+    return keep, arr
+
+
+def reg_parse_tree(state_dict):
+    """Host-only: the module tree a regis_net state dict encodes, e.g. 'TwoStep(Down(FFVF), FFVF)'; raises OaiError
+    for anything oai_reg_create would refuse."""
+    keep, arr = _tensor_array(state_dict)
+    buf = ctypes.create_string_buffer(1024)
+    check(lib.oai_reg_parse_tree(arr, len(state_dict), buf, c_size(1024)), "reg_parse_tree")
+    return buf.value.decode()
+
+
+class RegHandle:
+    """oai_reg_create / oai_reg_forward / oai_reg_destroy: register_pair on the GradICON cascade behind one handle.
+    The workspace (concatenation buffers, intermediate images, the cascade's displacement fields) is owned here and
+    reused by every call, so a CUDA graph captured over the handle keeps valid pointers; one stream at a time."""
+
+    def __init__(self, state_dict, net_dims, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.net_dims = tuple(int(v) for v in net_dims)
+        keep, arr = _tensor_array(state_dict)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.oai_reg_create(arr, len(state_dict), ptr(_dims(*self.net_dims)), ctypes.byref(self._h)),
+                  "reg_create")
+        self._ws = torch.empty(int(lib.oai_reg_workspace_bytes(self._h)), dtype=torch.uint8, device=self.device)
+
+    def __del__(self, _destroy=lib.oai_reg_destroy):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _destroy(h)
+
+    def describe(self):
+        buf = ctypes.create_string_buffer(1024)
+        check(lib.oai_reg_describe(self._h, buf, c_size(1024)), "reg_describe")
+        return buf.value.decode()
+
+    def forward(self, A, B, want_phi=True, want_disp=False):
+        """A, B: float32 contiguous cuda volumes [D,H,W] (any size).  Returns (phi_AB, phi_BA, disp_AB, disp_BA) with
+        phi [3,d,h,w] and disp [d,h,w,3] on the network grid (None for what was not asked for)."""
+        for t in (A, B):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda and t.dim() == 3
+        d = self.net_dims
+        phi = [torch.empty((3,) + d, dtype=torch.float32, device=A.device) if want_phi else None for _ in range(2)]
+        disp = [torch.empty(d + (3,), dtype=torch.float32, device=A.device) if want_disp else None for _ in range(2)]
+        check(lib.oai_reg_forward(self._h, ptr(A), ptr(_dims(*A.shape)), ptr(B), ptr(_dims(*B.shape)), ptr(phi[0]),
+                                  ptr(phi[1]), ptr(disp[0]), ptr(disp[1]), ptr(self._ws), c_size(self._ws.numel()),
+                                  stream_ptr()), "reg_forward")
+        return phi[0], phi[1], disp[0], disp[1]
+
+    def fields(self):
+        """The cascade's displacement fields of the last forward, application order: views [2, 3, d, h, w] into the
+        workspace (overwritten by the next forward)."""
+        out = []
+        for i in range(int(lib.oai_reg_num_fields(self._h))):
+            off, dims = c_size(0), (c_int * 3)()
+            check(lib.oai_reg_field(self._h, i, ctypes.byref(off), dims), "reg_field")
+            n = 2 * 3 * dims[0] * dims[1] * dims[2] * 4
+            out.append(self._ws[off.value:off.value + n].view(torch.float32).view(2, 3, dims[0], dims[1], dims[2]))
+        return out
+
+    def warp_image(self, image, direction=0, out=None):
+        assert image.dtype == torch.float32 and image.is_contiguous() and image.is_cuda
+        shape = tuple(image.shape[-3:])
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=image.device)
+        check(lib.oai_reg_warp_image(self._h, ptr(image), ptr(_dims(*shape)), int(direction), ptr(out), ptr(self._ws),
+                                     c_size(self._ws.numel()), stream_ptr()), "reg_warp_image")
+        return out
+
+
 # ------------------------------------------------------------------------------------------------ registration
 def _dims(*v):
     return np.asarray(v, dtype=np.int32)

@@ -91,3 +91,36 @@ def test_oracle_tree_forward_equals_the_hand_written_cascade():
     a, b = reg_oracle.register_pair_maps(sd, A, B, shape)
     ta, tb = reg_oracle.register_pair_maps_tree(sd, A, B, shape)
     assert (a - ta).abs().max().item() < 1e-6 and (b - tb).abs().max().item() < 1e-6
+
+
+# ---- the same loader rules inside the library (oai_reg_parse_tree: host arithmetic of oai_reg_create, no GPU)
+@pytest.mark.parametrize("paths,desc", [
+    (reg_oracle.NET_PATHS, "TwoStep(TwoStep(Down(TwoStep(FFVF, FFVF)), FFVF), FFVF)"),
+    (reg_oracle.NET_PATHS_TWO_LEVEL, "TwoStep(TwoStep(Down(TwoStep(Down(FFVF), FFVF)), FFVF), FFVF)"),
+])
+@pytest.mark.parametrize("prefix", ["", "regis_net."])
+def test_library_parses_the_same_tree(paths, desc, prefix):
+    from oai_analysis_2_b200 import ops
+    sd = {prefix + k: v for k, v in reg_oracle.make_gradicon_state_dict(3, paths).items()}
+    sd["identity_map"] = torch.zeros(1, 3, 4, 4, 4)
+    sd[prefix + "netPsi.net.batchNorms.0.num_batches_tracked"] = torch.zeros(())
+    assert ops.reg_parse_tree(sd) == desc
+
+
+def test_library_refuses_wrong_layouts():
+    from oai_analysis_2_b200 import ops
+    from oai_analysis_2_b200._lib import OaiError
+    good = reg_oracle.make_gradicon_state_dict(5)
+    cases = [
+        ({k.replace("netPsi.net.", "netPsi.module.net.", 1) if k.startswith("netPsi.") else k: v
+          for k, v in good.items()}, "outside any tallUNet2"),
+        (dict(good, **{"similarity.kernel": torch.zeros(3)}), "outside any tallUNet2"),
+        ({k: v for k, v in good.items() if k != "netPsi.net.upConvs.3.bias"}, "missing keys"),
+        (dict(good, **{"netPsi.net.downConvs.7.weight": torch.zeros(2)}), "unexpected keys"),
+        ({k: v for k, v in good.items() if not k.startswith("netPsi.")}, "cannot interpret children"),
+        (dict(good, **{"netPsi.net.lastConv.bias": torch.zeros(4)}), "size mismatch"),
+        ({}, "no tallUNet2"),
+    ]
+    for sd, msg in cases:
+        with pytest.raises(OaiError, match=msg):
+            ops.reg_parse_tree(sd)

@@ -234,6 +234,87 @@ def test_two_level_downsample_tree_registers_like_its_oracle():
     assert ((flat - ref_AB) * vox).abs().max().item() > 0.05
 
 
+def test_stage_level_c_abi_registers_a_pair_in_two_calls():
+    """oai_reg_create + oai_reg_forward through ctypes alone (no icon_registration module on the path): the regis_net
+    state dict goes in with icon's key paths, the native-size pair goes in, maps, ITK displacement fields and a warped
+    image come out and agree with the oracle."""
+    _cuda()
+    import ctypes
+    from oai_analysis_2_b200._lib import lib
+    from oracle import reg_oracle
+
+    class Tensor(ctypes.Structure):
+        _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.c_void_p), ("ndim", ctypes.c_int),
+                    ("shape", ctypes.c_longlong * 5)]
+
+    def err():
+        return lib.oai_last_error().decode()
+
+    shape, native = (40, 48, 44), (80, 96, 88)
+    sd = {"regis_net." + k: v for k, v in reg_oracle.make_gradicon_state_dict(4321).items()}
+    keep = [np.ascontiguousarray(v.numpy(), dtype=np.float32) for v in sd.values()]
+    arr = (Tensor * len(sd))()
+    for i, (k, a) in enumerate(zip(sd, keep)):
+        arr[i] = Tensor(k.encode(), a.ctypes.data, a.ndim, (ctypes.c_longlong * 5)(*(list(a.shape) + [0] * (5 - a.ndim))))
+    dims = (ctypes.c_int * 3)(*shape)
+    nat = (ctypes.c_int * 3)(*native)
+    h = ctypes.c_void_p()
+    assert lib.oai_reg_create(arr, len(sd), dims, ctypes.byref(h)) == 0, err()
+    buf = ctypes.create_string_buffer(256)
+    assert lib.oai_reg_describe(h, buf, ctypes.c_size_t(256)) == 0
+    assert buf.value.decode() == "TwoStep(TwoStep(Down(TwoStep(FFVF, FFVF)), FFVF), FFVF)"
+    nbytes = lib.oai_reg_workspace_bytes(h)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    A = (_smooth(native, 40) * 0.3 + 0.5).clamp(0, 1)
+    B = (_smooth(native, 41) * 0.3 + 0.5).clamp(0, 1)
+    dA, dB = A.cuda(), B.cuda()
+    phi = torch.empty((2, 3) + shape, device="cuda")
+    disp = torch.empty((2,) + shape + (3,), device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.oai_reg_forward(h, P(dA), nat, P(dB), nat, P(phi[0]), P(phi[1]), P(disp[0]), P(disp[1]), P(ws),
+                               ctypes.c_size_t(nbytes), st) == 0, err()
+    ref_AB, ref_BA = reg_oracle.register_pair_maps({k[10:]: v for k, v in sd.items()}, A.numpy(), B.numpy(), shape)
+    vox = torch.tensor([s - 1 for s in shape], dtype=torch.float32).view(1, 3, 1, 1, 1)
+    e_ab = ((phi[0].cpu() - ref_AB) * vox).abs().max().item()
+    e_ba = ((phi[1].cpu() - ref_BA) * vox).abs().max().item()
+    assert e_ab < 2e-3 and e_ba < 2e-3, (e_ab, e_ba)
+    # create_itk_transform: disp[z,y,x,(x,y,z)] = (phi - identity)[(2,1,0)] * (N - 1)
+    ident = reg_oracle.identity_map(shape)
+    want = ((ref_AB - ident) * vox)[0].flip(0).permute(1, 2, 3, 0)
+    assert (disp[0].cpu() - want).abs().max().item() < 4e-3
+    # only the displacement fields asked for: the maps go through the workspace
+    disp2 = torch.empty_like(disp)
+    assert lib.oai_reg_forward(h, P(dA), nat, P(dB), nat, None, None, P(disp2[0]), P(disp2[1]), P(ws),
+                               ctypes.c_size_t(nbytes), st) == 0, err()
+    assert torch.equal(disp2, disp)
+    # as_function(image_A)(phi_AB(identity)) at the native size, fused with the composition
+    assert lib.oai_reg_num_fields(h) == 4
+    out = torch.empty(native, device="cuda")
+    assert lib.oai_reg_warp_image(h, P(dA), nat, 0, P(out), P(ws), ctypes.c_size_t(nbytes), st) == 0, err()
+    fields = []
+    for i in range(4):
+        off, fd = ctypes.c_size_t(0), (ctypes.c_int * 3)()
+        assert lib.oai_reg_field(h, i, ctypes.byref(off), fd) == 0
+        n = 2 * 3 * fd[0] * fd[1] * fd[2] * 4
+        fields.append(ws[off.value:off.value + n].view(torch.float32).view(2, 3, *fd)[0].cpu())
+    half = tuple((s + 1) // 2 for s in shape)
+    assert [tuple(f.shape[1:]) for f in fields] == [shape, shape, half, half]   # omega, xi, psi, phi
+    c = reg_oracle.identity_map(native)
+    for f in fields:
+        c = c + reg_oracle.sample(f[None], c)
+    ref_img = reg_oracle.sample(A[None, None], c)[0, 0]
+    assert (out.cpu() - ref_img).abs().max().item() < 1e-5
+    # a too-small workspace and a wrong layout are refused with a message
+    assert lib.oai_reg_forward(h, P(dA), nat, P(dB), nat, P(phi[0]), P(phi[1]), None, None, P(ws),
+                               ctypes.c_size_t(nbytes - 256), st) != 0 and "workspace" in err()
+    assert lib.oai_reg_destroy(h) == 0
+    bad = (Tensor * (len(sd) - 1))(*[arr[i] for i in range(len(sd) - 1)])
+    h2 = ctypes.c_void_p()
+    assert lib.oai_reg_create(bad, len(sd) - 1, dims, ctypes.byref(h2)) != 0 and "missing keys" in err()
+    assert not h2.value
+
+
 def _geoms():
     from oracle.warp_oracle import Geometry
     th = 0.05
