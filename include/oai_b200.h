@@ -257,6 +257,19 @@ OAI_API int oai_reg_convt4_mma(const float* in, long long in_nstride, long long 
                                long long out_cstride, int cout, const int* out_dims, int N, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* The same up step on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) for the wide levels:
+ * cout in {16, 32, 64}, cin a multiple of 16, cout <= cin, lattice at least 8 x 8.  Split-fp16 operands as above
+ * (fp32-level accuracy).  oai_reg_pack_convt4_umma turns w [cin][64][cout] fp32 (device) into the kernel's pre-swizzled
+ * weight blocks (oai_reg_convt4_umma_wbytes(cin, cout) bytes, 16-byte aligned; wexp as for oai_reg_pack_convt4).
+ * workspace: N * cin * D * H * W * 4 bytes, 128-byte aligned (the layer input as channels-last hi / lo fp16). */
+OAI_API size_t oai_reg_convt4_umma_wbytes(int cin, int cout);
+OAI_API int oai_reg_pack_convt4_umma(const float* w, int cin, int cout, int wexp, void* dst, void* stream);
+OAI_API int oai_reg_convt4_umma(const float* in, long long in_nstride, long long in_cstride, int cin,
+                                const int* in_dims, const void* wumma, int wexp, const float* bias,
+                                const float* bn_scale, const float* bn_shift, float* out, long long out_nstride,
+                                long long out_cstride, int cout, const int* out_dims, int N, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
 /* Bytes of caller-owned device scratch oai_reg_convt4_mma needs: the layer input rewritten once as leaky-ReLU'd
  * hi / lo fp16 channel pairs (N * cin * D * H * W * 4), or, for levels narrower than 12 points, the split-K partial
  * sums of their fp32 GEMM form. */

@@ -51,7 +51,7 @@ extern "C" int oai_reg_convt4(const float* in, long long in_nstride, long long i
   OAI_REQUIRE(cout <= cin, "reg_convt4: the residual keeps the first cout of cin channels (cout=%d cin=%d)", cout, cin);
   for (int a = 0; a < 3; ++a)
     OAI_REQUIRE(out_dims[a] >= 1 && out_dims[a] <= 2 * in_dims[a], "reg_convt4: output dim %d exceeds 2x input", a);
-  ConvT4Params p;
+  ConvT4Params p{};
   p.in = in; p.in_nstride = in_nstride; p.in_cstride = in_cstride; p.cin = cin;
   p.Di = in_dims[0]; p.Hi = in_dims[1]; p.Wi = in_dims[2];
   p.w = w; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
@@ -94,7 +94,7 @@ extern "C" int oai_reg_convt4_mma(const float* in, long long in_nstride, long lo
   OAI_REQUIRE((reinterpret_cast<uintptr_t>(wpk) & 15) == 0, "reg_convt4_mma: packed weights must be 16-byte aligned");
   for (int a = 0; a < 3; ++a)
     OAI_REQUIRE(out_dims[a] >= 1 && out_dims[a] <= 2 * in_dims[a], "reg_convt4_mma: output dim %d exceeds 2x input", a);
-  ConvT4Params p;
+  ConvT4Params p{};
   p.in = in; p.in_nstride = in_nstride; p.in_cstride = in_cstride; p.cin = cin;
   p.Di = in_dims[0]; p.Hi = in_dims[1]; p.Wi = in_dims[2];
   p.w = w; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
@@ -103,6 +103,40 @@ extern "C" int oai_reg_convt4_mma(const float* in, long long in_nstride, long lo
   p.wpk = static_cast<const uint4*>(wpk); p.wexp = wexp; p.xsplit = static_cast<uint32_t*>(workspace);
   p.xsplit_bytes = workspace_bytes; p.debug = 0;
   return convt4_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t oai_reg_convt4_umma_wbytes(int cin, int cout) { return convt4_umma_wbytes(cin, cout); }
+
+extern "C" int oai_reg_pack_convt4_umma(const float* w, int cin, int cout, int wexp, void* dst, void* stream) {
+  OAI_REQUIRE(w && dst, "reg_pack_convt4_umma: null pointer");
+  OAI_REQUIRE(cin > 0 && cin % 16 == 0 && (cout == 16 || cout == 32 || cout == 64),
+              "reg_pack_convt4_umma: cin must be a multiple of 16 and cout one of 16, 32, 64 (got %d, %d)", cin, cout);
+  OAI_REQUIRE(wexp >= -14 && wexp <= 30, "reg_pack_convt4_umma: scale exponent %d out of range", wexp);
+  OAI_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "reg_pack_convt4_umma: dst must be 16-byte aligned");
+  return reg_pack_convt4_umma_launch(w, cin, cout, wexp, dst, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int oai_reg_convt4_umma(const float* in, long long in_nstride, long long in_cstride, int cin,
+                                   const int* in_dims, const void* wumma, int wexp, const float* bias,
+                                   const float* bn_scale, const float* bn_shift, float* out, long long out_nstride,
+                                   long long out_cstride, int cout, const int* out_dims, int N, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  OAI_REQUIRE(in && in_dims && wumma && bias && bn_scale && bn_shift && out && out_dims && workspace,
+              "reg_convt4_umma: null pointer");
+  OAI_REQUIRE((reinterpret_cast<uintptr_t>(wumma) & 15) == 0, "reg_convt4_umma: weight blocks must be 16-byte aligned");
+  for (int a = 0; a < 3; ++a)
+    OAI_REQUIRE(out_dims[a] >= 1 && out_dims[a] <= 2 * in_dims[a], "reg_convt4_umma: output dim %d exceeds 2x input", a);
+  ConvT4Params p{};
+  p.in = in; p.in_nstride = in_nstride; p.in_cstride = in_cstride; p.cin = cin;
+  p.Di = in_dims[0]; p.Hi = in_dims[1]; p.Wi = in_dims[2];
+  p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
+  p.out = out; p.out_nstride = out_nstride; p.out_cstride = out_cstride; p.cout = cout;
+  p.Do = out_dims[0]; p.Ho = out_dims[1]; p.Wo = out_dims[2]; p.N = N;
+  p.wexp = wexp; p.wumma = wumma; p.xsplit = static_cast<uint32_t*>(workspace); p.xsplit_bytes = workspace_bytes;
+  OAI_REQUIRE(convt4_umma_eligible(p),
+              "reg_convt4_umma: needs cout in {16, 32, 64}, cin %% 16 == 0, cout <= cin and a lattice of at least 8 x 8 "
+              "(got cin=%d cout=%d dims %d x %d x %d)", cin, cout, p.Di, p.Hi, p.Wi);
+  return convt4_umma_launch(p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int oai_compose(const int* grid_dims, int nfields, const float* const* fields, const int* field_dims,

@@ -1746,6 +1746,11 @@ int reg_pack_convt4_launch(const float* w, int cin, int cout, int wexp, uint4* w
   return launched("reg_pack_convt4_kernel");
 }
 
+static bool convt4_umma_disabled() {
+  const char* e = getenv("OAI_B200_CONVT4_UMMA");
+  return e && e[0] == '0';
+}
+
 int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
   const long long nout = static_cast<long long>(p.Do) * p.Ho * p.Wo;
   // levels narrower than 12 lattice points (the two deepest): 3x3 / 6x6 planes fill too little of an MMA tile; with a
@@ -1767,6 +1772,10 @@ int convt4_launch(const ConvT4Params& p, cudaStream_t st) {
         p, reinterpret_cast<const float*>(p.xsplit), 8 * g.nsplit);
     return launched("deep_reduce_convt4_kernel");
   }
+  // tcgen05 path (reg_umma.cu): the wide levels with 16 - 64 output channels; OAI_B200_CONVT4_UMMA=0 is the A/B switch
+  if (p.wumma && p.xsplit && convt4_umma_eligible(p) && !convt4_umma_disabled() &&
+      p.xsplit_bytes >= static_cast<size_t>(p.N) * p.cin * p.Di * p.Hi * p.Wi * 4)
+    return convt4_umma_launch(p, st);
   // tensor path: rows must be 16-byte multiples for the TMA boxes (every tallUNet2 level that is wide enough is)
   if (p.wpk && p.xsplit && p.cin % 16 == 0 && p.cout % 16 == 0 && p.Wi >= 12 && p.Wi % 4 == 0 &&
       p.in_cstride == static_cast<long long>(p.Di) * p.Hi * p.Wi && p.in_nstride % p.in_cstride == 0 &&

@@ -45,7 +45,8 @@ struct ConvT4Params {
   int debug;         // development switches (OAI_CONVT4_DEBUG): 1 no residual, 2 no MMAs, 4 no staging, 8 no stores
   int res_planes_per_n;  // filled by the launcher: in_nstride / in_cstride
   size_t xsplit_bytes;
-  uint32_t* xsplit;  // workspace of N*cin*Di*Hi*Wi words for the mma.sync path: the layer input as hi / lo fp16 pairs
+  uint32_t* xsplit;  // workspace of N*cin*Di*Hi*Wi words for the tensor paths: the layer input as hi / lo fp16
+  const void* wumma = nullptr;  // optional weight blocks of the tcgen05 path (reg_pack_convt4_umma_launch)
 };
 
 struct ChainParams {
@@ -92,6 +93,11 @@ size_t conv3_splitk_bytes(const Conv3Params& p);
 size_t convt4_splitk_bytes(const ConvT4Params& p);
 int convt4_launch(const ConvT4Params& p, cudaStream_t st);
 int reg_pack_convt4_launch(const float* w, int cin, int cout, int wexp, uint4* wpk, cudaStream_t st);
+// tcgen05 path of the up step (reg_umma.cu): cout in {16, 32, 64}, cin a multiple of 16, lattice at least 8 x 8
+bool convt4_umma_eligible(const ConvT4Params& p);
+size_t convt4_umma_wbytes(int cin, int cout);
+int reg_pack_convt4_umma_launch(const float* w, int cin, int cout, int wexp, void* dst, cudaStream_t st);
+int convt4_umma_launch(const ConvT4Params& p, cudaStream_t st);
 int chain_launch(const ChainParams& p, cudaStream_t st);
 int resize_trilinear_launch(const float* in, int Di, int Hi, int Wi, float* out, int Do, int Ho, int Wo,
                             cudaStream_t st);

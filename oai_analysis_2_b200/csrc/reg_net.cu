@@ -247,6 +247,7 @@ struct UNetWeights {
   float *uw[5], *ub[5];            // up step d: [cin][64][cout], [cout]
   float *bs[5], *bt[5];            // folded BatchNorm(eval): scale, shift
   uint4* uq[5];                    // split-fp16 B fragments of uw for the mma.sync path
+  void* uu[5];                     // weight blocks of the tcgen05 path (wide levels with 16 - 64 output channels)
   int uexp[5];
   float *lw, *lb;                  // lastConv: [18][27][4] (3 channels padded to 4), [3]
 };
@@ -381,7 +382,7 @@ int unet_forward(Ctx& c, const UNetWeights& w, const float* src, const float* tg
     p.cout = kUpOut[d];
     p.Do = g.lv[d][0]; p.Ho = g.lv[d][1]; p.Wo = g.lv[d][2];
     p.N = kBatch;
-    p.wpk = w.uq[d]; p.wexp = w.uexp[d];
+    p.wpk = w.uq[d]; p.wexp = w.uexp[d]; p.wumma = w.uu[d];
     const int in_dims[3] = {p.Di, p.Hi, p.Wi};
     c.scratch_need = std::max(c.scratch_need, oai_reg_convt4_mma_workspace(p.cin, p.cout, in_dims, kBatch));
     p.xsplit = static_cast<uint32_t*>(c.scratch);
@@ -556,6 +557,12 @@ int upload_unet(oai_reg_handle* h, const TensorGroup& g, UNetWeights* w) {
       h->allocs.push_back(q);
       w->uq[d] = static_cast<uint4*>(q);
       RC(reg_pack_convt4_launch(w->uw[d], cin, cout, wexp, w->uq[d], nullptr));
+      w->uu[d] = nullptr;
+      if (cout <= 64) {
+        RC(check_cuda(cudaMalloc(&w->uu[d], convt4_umma_wbytes(cin, cout)), "reg_create: cudaMalloc"));
+        h->allocs.push_back(w->uu[d]);
+        RC(reg_pack_convt4_umma_launch(w->uw[d], cin, cout, wexp, w->uu[d], nullptr));
+      }
       // BatchNorm3d(eval) folded in float64
       const float* gamma = g.at("batchNorms." + D + ".weight")->data;
       const float* beta = g.at("batchNorms." + D + ".bias")->data;

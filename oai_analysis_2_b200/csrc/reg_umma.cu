@@ -1,0 +1,520 @@
+// tallUNet2 up step on the 5th-generation tensor cores: ConvTranspose3d(k4, s2, p1) + trilinear-upsample residual +
+// BatchNorm(eval) + crop (icon_registration networks.UNet2.forward, up path) as a tcgen05 implicit GEMM with
+// split-fp16 operands (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM: fp32-level accuracy).
+//
+// Formulation (input-lattice stationary, parity classes and d-shifts stacked along N):
+//   * out[2i + r] (r in {0,1}^3, the 8 parity classes of lattice point i) = sum over input shifts s in {-1,0,1}^3 of
+//     in[i + s] * w[k], k = r + 1 - 2s per axis (valid when 0 <= k <= 3): a class uses 2 of the 3 shifts per axis;
+//   * M tile = 128 lattice points of one z-slice (16 rows x 8 columns); the A operand of an in-plane shift (sy, sx) is
+//     the SAME halo'd 18 x 10 box of 32-byte channel rows (16 fp16 channels, SWIZZLE_32B) addressed (sy*10 + sx) rows
+//     further -- 8-row groups are the 8 x-adjacent points of one lattice row, SBO = 10 rows;
+//   * accumulators of one lattice slice = 8 classes x Cn output channels (columns class*Cn + co); consecutive lattice
+//     slices are adjacent in TMEM, so input slice zi updates [upper half of slice zi-1 | slice zi | lower half of
+//     slice zi+1] with ONE MMA of N = 16*Cn columns against weight rows stored in that order (invalid (class, shift)
+//     pairs are zero rows);
+//   * a unit = R lattice slices of one tile (R * 8 * Cn = 256 columns = half of TMEM); consecutive units of a CTA
+//     alternate between the two halves, so the epilogue of unit i overlaps the MMAs of unit i+1;
+//   * K loop: 16-channel chunks; per chunk the unit's R+2 input slices (hi and lo boxes) arrive by TMA and stay while
+//     the nine in-plane shifts stream their weight blocks (cp.async.bulk, pre-swizzled) through a ring;
+//   * warp roles: 0 = TMA producer, 1 = weight producer, 2 = MMA issuer + TMEM owner, 4..11 = two epilogue groups
+//     (TMEM -> registers -> 2^-wexp, bias, upsampled residual, BatchNorm -> planar fp32 stores, x-parity pairs as
+//     8-byte stores).
+#include "api_common.h"
+#include "ptx.cuh"
+#include "reg_kernels.cuh"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace oai {
+
+namespace {
+
+constexpr int kTX = 8, kTY = 16;                 // lattice tile: 128 points of one slice
+constexpr int kBX = kTX + 2, kBY = kTY + 2;      // halo'd TMA box
+constexpr int kRowB = 32;                        // 16 fp16 channels
+constexpr int kBoxBytes = kBX * kBY * kRowB;     // 5760
+constexpr int kSlotBytes = 6144;                 // box slot (1024-aligned)
+constexpr int kHalfCols = 256;
+constexpr int kUmmaThreads = 384;               // warps 0-2: producers + MMA issuer, 3: idle, 4-11: two epilogue groups
+constexpr uint32_t kLayoutSw32 = 6;              // UMMA shared-memory descriptor layout type: SWIZZLE_32B
+
+struct UmmaParams {
+  const float* in;              // raw layer input (planar fp32): residual source
+  long long in_nstride, in_cstride;
+  int cin, Di, Hi, Wi, N;
+  const uint8_t* wumma;         // [nsplit][nchunks][9] blocks of 2 x (16*Cn rows x 32 B), pre-swizzled
+  const float *bias, *bn_scale, *bn_shift;
+  float* out;
+  long long out_nstride, out_cstride;
+  int cout, Do, Ho, Wo;
+  int Cn, R, nsplit, nchunks, nb;
+  int nx, ny, nzg, nunits;
+  uint32_t bblock;              // bytes of one weight block
+  uint32_t abuf_bytes;          // (R + 2) * 2 * kSlotBytes
+  float inv;                    // 2^-wexp
+  int debug;                    // development switches (OAI_CONVT4_DEBUG): 1 no residual, 2 no MMAs, 8 no stores
+};
+
+struct Unit {
+  int n, h, z0, rd, y0, x0;
+};
+
+__device__ __forceinline__ Unit decode_unit(const UmmaParams& p, int u) {
+  Unit ui;
+  ui.x0 = (u % p.nx) * kTX; u /= p.nx;
+  ui.y0 = (u % p.ny) * kTY; u /= p.ny;
+  ui.z0 = (u % p.nzg) * p.R; u /= p.nzg;
+  ui.h = u % p.nsplit;
+  ui.n = u / p.nsplit;
+  ui.rd = min(p.R, p.Di - ui.z0);
+  return ui;
+}
+
+__device__ __forceinline__ float leaky_f(float v) { return v > 0.f ? v : 0.01f * v; }
+
+}  // namespace
+
+// Layer input [N][cin] planes (explicit strides) -> xcl [2 (hi, lo)][N][vol][cin] fp16 channels-last: leaky_relu, then
+// the hi / lo split; one thread moves 8 channels of one voxel (16-byte stores).
+__global__ void __launch_bounds__(256) reg_split_cl_kernel(const float* __restrict__ in, long long in_nstride,
+                                                           long long in_cstride, int N, int cin, long long vol,
+                                                           uint4* __restrict__ xcl) {
+  const int ng = cin / 8;
+  const long long total = static_cast<long long>(N) * ng * vol;
+  const long long plane = static_cast<long long>(N) * vol * ng;   // uint4 per precision plane
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long v = i % vol;
+    const int j = static_cast<int>((i / vol) % ng);
+    const long long n = i / (vol * ng);
+    const float* src = in + n * in_nstride + (8ll * j) * in_cstride + v;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x0 = leaky_f(__ldg(src + (2 * k) * in_cstride)), x1 = leaky_f(__ldg(src + (2 * k + 1) * in_cstride));
+      const __half2 h = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      hi[k] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[k] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const long long o = (n * vol + v) * ng + j;
+    xcl[o] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    xcl[plane + o] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// w [cin][64][cout] fp32 (tap = (kd*4+kh)*4+kw) -> the kernel's weight blocks: block (h, c, j) = co split h, 16-channel
+// chunk c, in-plane shift j = (sy+1)*3 + (sx+1); inside, plane 0 = rn16(w * 2^wexp), plane 1 = rn16 of the remainder;
+// row n = slot * Cn + co' with slot 0..3 = (s_d = +1, classes 4..7), 4..11 = (s_d = 0, classes 0..7), 12..15 =
+// (s_d = -1, classes 0..3); element k = channel within the chunk, stored with the SWIZZLE_32B pattern (16-byte halves
+// of a 32-byte row swapped in rows 4..7 of every 8).
+__global__ void reg_pack_convt4_umma_kernel(const float* __restrict__ w, int cin, int cout, int Cn, int wexp,
+                                            __half* __restrict__ dst) {
+  const int nchunks = cin / 16, nsplit = cout / Cn, rows = 16 * Cn;
+  const long long total = static_cast<long long>(nsplit) * nchunks * 9 * rows * 16;
+  const float sc = exp2f(static_cast<float>(wexp));
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int k = static_cast<int>(r % 16); r /= 16;
+    const int n = static_cast<int>(r % rows); r /= rows;
+    const int j = static_cast<int>(r % 9); r /= 9;
+    const int c = static_cast<int>(r % nchunks);
+    const int h = static_cast<int>(r / nchunks);
+    const int slot = n / Cn, co = h * Cn + n % Cn;
+    int sd, cls;
+    if (slot < 4) { sd = 1; cls = 4 + slot; }
+    else if (slot < 12) { sd = 0; cls = slot - 4; }
+    else { sd = -1; cls = slot - 12; }
+    const int sy = j / 3 - 1, sx = j % 3 - 1;
+    const int kd = (cls >> 2) + 1 - 2 * sd, kh = ((cls >> 1) & 1) + 1 - 2 * sy, kw = (cls & 1) + 1 - 2 * sx;
+    float v = 0.f;
+    if (kd >= 0 && kd < 4 && kh >= 0 && kh < 4 && kw >= 0 && kw < 4)
+      v = w[(static_cast<size_t>(c * 16 + k) * 64 + (kd * 4 + kh) * 4 + kw) * cout + co] * sc;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const size_t block = (static_cast<size_t>(h) * nchunks + c) * 9 + j;
+    const size_t off = static_cast<size_t>(n) * 16 + ((((k >> 3) ^ ((n >> 2) & 1))) << 3) + (k & 7);
+    __half* b = dst + block * (2 * static_cast<size_t>(rows) * 16);
+    b[off] = hi;
+    b[static_cast<size_t>(rows) * 16 + off] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+convt4_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ UmmaParams p) {
+  extern __shared__ uint8_t umma_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(umma_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bbuf = smem;                                                   // nb weight blocks
+  uint8_t* abuf = bbuf + static_cast<size_t>(p.nb) * p.bblock;            // 2 activation buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(abuf + 2 * static_cast<size_t>(p.abuf_bytes));
+  uint64_t* full_a = bars;         // [2]
+  uint64_t* empty_a = bars + 2;    // [2]
+  uint64_t* full_b = bars + 4;     // [8]
+  uint64_t* empty_b = bars + 12;   // [8]
+  uint64_t* acc_full = bars + 20;  // [2]
+  uint64_t* acc_empty = bars + 22; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Cn = p.Cn;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_a[i], 1);
+      mbar_init(&empty_a[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&full_b[i], 1);
+      mbar_init(&empty_b[i], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ activation producer: R+2 slices x (hi, lo) per chunk
+    if (lane == 0) {
+      int ab = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+        const Unit ui = decode_unit(p, u);
+        const int zlo = max(0, ui.z0 - 1), zhi = min(p.Di - 1, ui.z0 + ui.rd);
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(&empty_a[ab], ph ^ 1u, 100 + ab);
+          mbar_arrive_expect_tx(&full_a[ab], static_cast<uint32_t>(zhi - zlo + 1) * 2u * kBoxBytes);
+          uint8_t* base = abuf + static_cast<size_t>(ab) * p.abuf_bytes;
+          for (int zi = zlo; zi <= zhi; ++zi) {
+            const int slot = zi - (ui.z0 - 1);
+            tma_load_5d(base + (slot * 2) * kSlotBytes, &tm_x, &full_a[ab], c * 16, ui.x0 - 1, ui.y0 - 1, zi, ui.n);
+            tma_load_5d(base + (slot * 2 + 1) * kSlotBytes, &tm_x, &full_a[ab], c * 16, ui.x0 - 1, ui.y0 - 1, zi,
+                        p.N + ui.n);
+          }
+          if (++ab == 2) { ab = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ weight producer: nine blocks per chunk
+    if (lane == 0) {
+      int bb = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+        const Unit ui = decode_unit(p, u);
+        const uint8_t* src = p.wumma + static_cast<size_t>(ui.h) * p.nchunks * 9 * p.bblock;
+        for (int b = 0; b < p.nchunks * 9; ++b) {
+          mbar_wait(&empty_b[bb], ph ^ 1u, 200 + bb);
+          mbar_arrive_expect_tx(&full_b[bb], p.bblock);
+          bulk_load(bbuf + static_cast<size_t>(bb) * p.bblock, src + static_cast<size_t>(b) * p.bblock, p.bblock,
+                    &full_b[bb]);
+          if (++bb == p.nb) { bb = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ MMA issuer
+    const bool leader = elect_one();
+    const uint32_t abuf_addr = smem_u32(abuf), bbuf_addr = smem_u32(bbuf);
+    const uint32_t wlo_off = static_cast<uint32_t>(16 * Cn) * kRowB;   // lo weight plane inside a block
+    int ab = 0, bb = 0, it = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
+      const Unit ui = decode_unit(p, u);
+      const int half = it & 1;
+      const uint32_t use = (it >> 1) & 1u;
+      mbar_wait(&acc_empty[half], use ^ 1u, 500 + half);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + static_cast<uint32_t>(half * kHalfCols);
+      const int zlo = max(0, ui.z0 - 1), zhi = min(p.Di - 1, ui.z0 + ui.rd);
+      const int ncols = ui.rd * 8 * Cn;
+      int hw = 0;   // columns below hw hold partial sums of this unit, the rest is still the previous unit's
+      for (int c = 0; c < p.nchunks; ++c) {
+        mbar_wait(&full_a[ab], aph, 400 + ab);
+        tc_fence_after();
+        const uint32_t a_base = abuf_addr + static_cast<uint32_t>(ab) * p.abuf_bytes;
+        for (int j = 0; j < 9; ++j) {
+          mbar_wait(&full_b[bb], bph, 300 + bb);
+          tc_fence_after();
+          const uint32_t b_base = bbuf_addr + static_cast<uint32_t>(bb) * p.bblock;
+          const uint32_t a_shift = static_cast<uint32_t>((j / 3) * kBX + (j % 3)) * kRowB;
+          for (int zi = zlo; zi <= zhi; ++zi) {
+            const int slot = zi - (ui.z0 - 1);
+            const int start = (zi - 1 - ui.z0) * 8 * Cn + 4 * Cn;
+            const int c0 = max(start, 0), c1 = min(start + 16 * Cn, ncols);
+            if (c1 <= c0) continue;
+            const uint32_t a_hi = a_base + static_cast<uint32_t>(slot * 2) * kSlotBytes + a_shift;
+            const uint32_t b_row = b_base + static_cast<uint32_t>(c0 - start) * kRowB;
+            if (leader && !(p.debug & 2)) {
+#pragma unroll
+              for (int term = 0; term < 3; ++term) {
+                const uint32_t a_addr = a_hi + (term == 1 ? kSlotBytes : 0);
+                const uint32_t b_addr = b_row + (term == 2 ? wlo_off : 0u);
+                if (c == 0 && j == 0 && term == 0) {
+                  // first pass over the unit: columns from hw on are overwritten, the ones below accumulate
+                  const int mid = min(max(hw, c0), c1);
+                  if (mid > c0)
+                    umma_f16_ss(tbase + c0, umma_desc_kmajor(a_addr, kBX * kRowB, 0, kLayoutSw32),
+                                umma_desc_kmajor(b_addr, 8 * kRowB, 0, kLayoutSw32),
+                                umma_idesc_f16(128, mid - c0, 0), 1u);
+                  if (c1 > mid)
+                    umma_f16_ss(tbase + mid, umma_desc_kmajor(a_addr, kBX * kRowB, 0, kLayoutSw32),
+                                umma_desc_kmajor(b_addr + static_cast<uint32_t>(mid - c0) * kRowB, 8 * kRowB, 0,
+                                                 kLayoutSw32),
+                                umma_idesc_f16(128, c1 - mid, 0), 0u);
+                } else {
+                  umma_f16_ss(tbase + c0, umma_desc_kmajor(a_addr, kBX * kRowB, 0, kLayoutSw32),
+                              umma_desc_kmajor(b_addr, 8 * kRowB, 0, kLayoutSw32), umma_idesc_f16(128, c1 - c0, 0),
+                              1u);
+                }
+              }
+            }
+            if (c == 0 && j == 0) hw = max(hw, c1);
+          }
+          if (leader) umma_commit(&empty_b[bb]);
+          if (++bb == p.nb) { bb = 0; bph ^= 1u; }
+        }
+        if (leader) umma_commit(&empty_a[ab]);
+        if (++ab == 2) { ab = 0; aph ^= 1u; }
+      }
+      if (leader) umma_commit(&acc_full[half]);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: two groups of four warps
+    // A unit's accumulators are cut into four items of 8 output channels x 8 classes of one lattice slice
+    // (Cn = 16: 2 slices x 2 channel halves; Cn = 32: 1 slice x 4 channel quarters); group eg takes the items
+    // eg, eg + 2.  Per channel a thread reads the 3 x 3 x 3 raw neighbourhood of its lattice point once (27 loads,
+    // replicate-clamped) and interpolates all eight classes from it separably.
+    const int q = warp & 3, eg = (warp - 4) >> 2, m = q * 32 + lane;
+    const int ty = m >> 3, tx = m & 7;
+    const int per_slice = Cn / 8;   // items per lattice slice
+    int it = 0;
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
+      const Unit ui = decode_unit(p, u);
+      const int half = it & 1;
+      const uint32_t use = (it >> 1) & 1u;
+      mbar_wait(&acc_full[half], use, 600 + half);
+      tc_fence_after();
+      const int y = ui.y0 + ty, x = ui.x0 + tx;
+      const bool inside = y < p.Hi && x < p.Wi && 2 * x < p.Wo;
+      const int yc = min(y, p.Hi - 1), xc = min(x, p.Wi - 1);
+      const int xo3[3] = {max(xc - 1, 0), xc, min(xc + 1, p.Wi - 1)};
+      const int yr[3] = {max(yc - 1, 0) * p.Wi, yc * p.Wi, min(yc + 1, p.Hi - 1) * p.Wi};
+      const bool pair_ok = 2 * x + 1 < p.Wo;
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * kHalfCols);
+      for (int item = eg; item < ui.rd * per_slice; item += 2) {
+        const int a = item / per_slice, c8 = (item % per_slice) * 8;
+        const int z = ui.z0 + a;
+        uint32_t v[8][8];   // [class][channel]
+#pragma unroll
+        for (int cls = 0; cls < 8; ++cls) tmem_ld_32x8(t_lane + static_cast<uint32_t>(a * 8 * Cn + cls * Cn + c8), v[cls]);
+        tmem_ld_wait();
+        if (!inside || (p.debug & 8)) continue;
+        const int hw_i = p.Hi * p.Wi;
+        const int zr[3] = {max(z - 1, 0) * hw_i, z * hw_i, min(z + 1, p.Di - 1) * hw_i};
+        const int cog0 = ui.h * Cn + c8;
+        const float* raw_c = p.in + ui.n * p.in_nstride + static_cast<long long>(cog0) * p.in_cstride;
+        float* out_c = p.out + ui.n * p.out_nstride + static_cast<long long>(cog0) * p.out_cstride;
+        long long orow[4];
+        bool ook[4];
+#pragma unroll
+        for (int rp = 0; rp < 4; ++rp) {
+          const int zo = 2 * z + (rp >> 1), yo = 2 * y + (rp & 1);
+          ook[rp] = zo < p.Do && yo < p.Ho;
+          orow[rp] = (static_cast<long long>(zo) * p.Ho + yo) * p.Wo + 2 * x;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float* rc = raw_c + i * p.in_cstride;
+          // upsample2x (trilinear, align_corners=False) = per axis 0.75 * own sample + 0.25 * the neighbour on the
+          // class's side: x first (two parities per row), then y, then z
+          float ex[3][3][2];
+          if (!(p.debug & 1)) {
+            float raw[3][3][3];
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) raw[dz][dy][dx] = __ldg(rc + zr[dz] + yr[dy] + xo3[dx]);
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                const float c75 = 0.75f * raw[dz][dy][1];
+                ex[dz][dy][0] = fmaf(0.25f, raw[dz][dy][0], c75);
+                ex[dz][dy][1] = fmaf(0.25f, raw[dz][dy][2], c75);
+              }
+          } else {
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) ex[dz][dy][0] = ex[dz][dy][1] = 0.f;
+          }
+          float ey[3][2][2];   // [dz][rh][rw]
+#pragma unroll
+          for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int rw = 0; rw < 2; ++rw) {
+              const float c75 = 0.75f * ex[dz][1][rw];
+              ey[dz][0][rw] = fmaf(0.25f, ex[dz][0][rw], c75);
+              ey[dz][1][rw] = fmaf(0.25f, ex[dz][2][rw], c75);
+            }
+          const float bias = __ldg(p.bias + cog0 + i), bs = __ldg(p.bn_scale + cog0 + i), bt = __ldg(p.bn_shift + cog0 + i);
+          float* dst_c = out_c + i * p.out_cstride;
+#pragma unroll
+          for (int rp = 0; rp < 4; ++rp) {
+            const int rd = rp >> 1, rh = rp & 1;
+            float o[2];
+#pragma unroll
+            for (int rw = 0; rw < 2; ++rw) {
+              const float r = fmaf(0.25f, ey[rd ? 2 : 0][rh][rw], 0.75f * ey[1][rh][rw]);
+              o[rw] = (fmaf(__uint_as_float(v[rp * 2 + rw][i]), p.inv, bias) + r) * bs + bt;
+            }
+            if (!ook[rp]) continue;
+            float* dst = dst_c + orow[rp];
+            if (pair_ok && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+              *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+            } else {
+              dst[0] = o[0];
+              if (pair_ok) dst[1] = o[1];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[half]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+namespace {
+
+int umma_cn(int cout) { return cout >= 32 ? 32 : 16; }
+
+int make_xcl_tmap(CUtensorMap* tm, void* base, int cin, int Wi, int Hi, int Di, int planes) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess &&
+        r == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  if (!fn) return fail("convt4_umma: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)planes};
+  cuuint64_t strides[4] = {(cuuint64_t)cin * 2, (cuuint64_t)Wi * cin * 2, (cuuint64_t)Hi * Wi * cin * 2,
+                           (cuuint64_t)Di * Hi * Wi * cin * 2};
+  cuuint32_t box[5] = {16, kBX, kBY, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("convt4_umma: cuTensorMapEncodeTiled failed with %d (cin=%d W=%d H=%d D=%d planes=%d)", (int)r, cin, Wi,
+                Hi, Di, planes);
+  return 0;
+}
+
+}  // namespace
+
+bool convt4_umma_eligible(const ConvT4Params& p) {
+  return (p.cout == 16 || p.cout == 32 || p.cout == 64) && p.cin % 16 == 0 && p.cin >= 16 && p.Wi >= kTX &&
+         p.Hi >= kTX && p.cout <= p.cin;
+}
+
+size_t convt4_umma_wbytes(int cin, int cout) {
+  if (cin % 16 || cout % 16) return 0;
+  const int Cn = umma_cn(cout);
+  return static_cast<size_t>(cout / Cn) * (cin / 16) * 9 * 2 * (16 * Cn) * kRowB;
+}
+
+int reg_pack_convt4_umma_launch(const float* w, int cin, int cout, int wexp, void* dst, cudaStream_t st) {
+  const int Cn = umma_cn(cout);
+  const long long total = static_cast<long long>(cout / Cn) * (cin / 16) * 9 * (16 * Cn) * 16;
+  const unsigned blocks = static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148 * 16));
+  reg_pack_convt4_umma_kernel<<<blocks, 256, 0, st>>>(w, cin, cout, Cn, wexp, static_cast<__half*>(dst));
+  return launched("reg_pack_convt4_umma_kernel");
+}
+
+int convt4_umma_launch(const ConvT4Params& p, cudaStream_t st) {
+  const long long vol = static_cast<long long>(p.Di) * p.Hi * p.Wi;
+  if (p.xsplit_bytes < static_cast<size_t>(p.N) * p.cin * vol * 4 || (reinterpret_cast<uintptr_t>(p.xsplit) & 127))
+    return fail("convt4_umma: workspace of %zu bytes, 128-byte aligned, required",
+                static_cast<size_t>(p.N) * p.cin * vol * 4);
+  {
+    const long long total = static_cast<long long>(p.N) * (p.cin / 8) * vol;
+    const unsigned blocks = static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148 * 32));
+    reg_split_cl_kernel<<<blocks, 256, 0, st>>>(p.in, p.in_nstride, p.in_cstride, p.N, p.cin, vol,
+                                                reinterpret_cast<uint4*>(p.xsplit));
+    if (int rc = launched("reg_split_cl_kernel")) return rc;
+  }
+  UmmaParams q{};
+  q.in = p.in; q.in_nstride = p.in_nstride; q.in_cstride = p.in_cstride;
+  q.cin = p.cin; q.Di = p.Di; q.Hi = p.Hi; q.Wi = p.Wi; q.N = p.N;
+  q.wumma = static_cast<const uint8_t*>(p.wumma);
+  q.bias = p.bias; q.bn_scale = p.bn_scale; q.bn_shift = p.bn_shift;
+  q.out = p.out; q.out_nstride = p.out_nstride; q.out_cstride = p.out_cstride;
+  q.cout = p.cout; q.Do = p.Do; q.Ho = p.Ho; q.Wo = p.Wo;
+  q.Cn = umma_cn(p.cout);
+  q.R = kHalfCols / (8 * q.Cn);
+  q.nsplit = p.cout / q.Cn;
+  q.nchunks = p.cin / 16;
+  q.bblock = 2u * 16u * q.Cn * kRowB;
+  q.nb = q.Cn == 16 ? 6 : 4;   // weight blocks in flight (16 / 32 KB each): the stream is latency-bound below that
+  q.nx = (p.Wi + kTX - 1) / kTX; q.ny = (p.Hi + kTY - 1) / kTY; q.nzg = (p.Di + q.R - 1) / q.R;
+  const long long nunits = static_cast<long long>(p.N) * q.nsplit * q.nzg * q.ny * q.nx;
+  if (nunits > 0x7fffffffLL) return fail("convt4_umma: too many units");
+  q.nunits = static_cast<int>(nunits);
+  q.abuf_bytes = static_cast<uint32_t>((q.R + 2) * 2 * kSlotBytes);
+  q.inv = exp2f(static_cast<float>(-p.wexp));
+  {
+    const char* e = getenv("OAI_CONVT4_DEBUG");
+    q.debug = e ? atoi(e) : 0;
+  }
+  CUtensorMap tm;
+  if (int rc = make_xcl_tmap(&tm, p.xsplit, p.cin, p.Wi, p.Hi, p.Di, 2 * p.N)) return rc;
+  const size_t smem = 1024 + static_cast<size_t>(q.nb) * q.bblock + 2 * static_cast<size_t>(q.abuf_bytes) + 256;
+  static size_t configured[64] = {0};   // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || smem > configured[dev]) {
+    if (int rc = check_cuda(cudaFuncSetAttribute(convt4_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(smem)),
+                            "convt4_umma: cudaFuncSetAttribute"))
+      return rc;
+    if (dev >= 0 && dev < 64) configured[dev] = smem;
+  }
+  const int grid = std::min(q.nunits, num_sms());
+  convt4_umma_kernel<<<grid, kUmmaThreads, smem, st>>>(tm, q);
+  return launched("convt4_umma_kernel");
+}
+
+}  // namespace oai

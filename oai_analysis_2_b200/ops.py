@@ -384,6 +384,26 @@ def reg_convt4(x, cin, w, bias, bn_scale, bn_shift, out, cout, wpk=None, wexp=0,
     return out
 
 
+def reg_pack_convt4_umma(w, cin, cout, wexp):
+    """w: [cin, 64, cout] float32 cuda -> pre-swizzled weight blocks of the tcgen05 up step (uint8 tensor)."""
+    n = int(lib.oai_reg_convt4_umma_wbytes(cin, cout))
+    dst = torch.empty(n, dtype=torch.uint8, device=w.device)
+    check(lib.oai_reg_pack_convt4_umma(ptr(w), cin, cout, int(wexp), ptr(dst), stream_ptr()), "reg_pack_convt4_umma")
+    return dst
+
+
+def reg_convt4_umma(x, cin, wumma, wexp, bias, bn_scale, bn_shift, out, cout):
+    """The up step on tcgen05 (cout in {16, 32, 64}); x / out are views [N, C, D, H, W] as for reg_convt4."""
+    N, _, D, H, W = x.shape
+    need = N * cin * D * H * W * 4
+    ws = _scratch_buf(x.device, "convt4", need)
+    check(lib.oai_reg_convt4_umma(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(_dims(D, H, W)), ptr(wumma),
+                                  int(wexp), ptr(bias), ptr(bn_scale), ptr(bn_shift), ptr(out), c_ll(out.stride(0)),
+                                  c_ll(out.stride(1)), cout, ptr(_dims(*out.shape[2:])), N, ptr(ws),
+                                  c_size(ws.numel()), stream_ptr()), "reg_convt4_umma")
+    return out
+
+
 def reg_pack_convt4(w, cin, cout):
     """w: [cin, 64, cout] float32 cuda -> (wpk uint8 tensor, wexp) for reg_convt4(..., wpk=...)."""
     wmax = float(w.abs().max())

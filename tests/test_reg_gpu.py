@@ -138,6 +138,50 @@ def test_convt4_mma_matches_torch(cin, cout, dims, crop):
     assert out_buf[:, :2].abs().max() == 0
 
 
+@pytest.mark.parametrize("cin,cout,dims,crop", [
+    (48, 16, (3, 16, 8), (6, 32, 16)),      # one tile, R = 2: a full unit and a partial one
+    (48, 16, (5, 20, 24), (10, 40, 48)),    # ragged y tiles, several units per CTA (TMEM half ping-pong)
+    (96, 32, (4, 24, 24), (8, 48, 48)),     # Cn = 32: one lattice slice per unit, six chunks
+    (192, 64, (3, 12, 12), (5, 23, 24)),    # two output-channel splits, partial tiles, cropped output
+    (32, 16, (2, 9, 11), (4, 18, 21)),      # odd lattice, odd crop in x (scalar stores)
+    (48, 16, (10, 48, 48), (20, 96, 96)),   # more units than SMs
+])
+def test_convt4_umma_matches_torch(cin, cout, dims, crop):
+    """tcgen05 path of the up step (oai_reg_convt4_umma: split-fp16 operands, accumulators in TMEM) against torch fp64
+    and against the mma.sync path."""
+    _cuda()
+    from oai_analysis_2_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    N = 2
+    buf = torch.randn(N, cin + 3, *dims, generator=g) * 2.0
+    x = buf[:, 3:]
+    w, b = torch.randn(cin, cout, 4, 4, 4, generator=g) * 0.05, torch.randn(cout, generator=g) * 0.1
+    gam, bet = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    mean, var = torch.randn(cout, generator=g) * 0.1, torch.rand(cout, generator=g) + 0.5
+    y = F.conv_transpose3d(F.leaky_relu(x).double(), w.double(), b.double(), stride=2, padding=1)
+    ref = y + F.interpolate(x[:, :cout].double(), scale_factor=2, mode="trilinear", align_corners=False)
+    ref = F.batch_norm(ref, mean.double(), var.double(), gam.double(), bet.double(), training=False, eps=1e-5)
+    ref = ref[:, :, :crop[0], :crop[1], :crop[2]]
+    s = (gam.double() / torch.sqrt(var.double() + 1e-5)).float().cuda()
+    t = (bet.double() - mean.double() * s.cpu().double()).float().cuda()
+    wp = w.permute(0, 2, 3, 4, 1).reshape(cin, 64, cout).contiguous().cuda()
+    wpk, wexp = ops.reg_pack_convt4(wp, cin, cout)
+    wu = ops.reg_pack_convt4_umma(wp, cin, cout, wexp)
+    xc = buf.cuda()[:, 3:]
+    out_buf = torch.zeros(N, cout + 2, *crop).cuda()
+    ops.reg_convt4_umma(xc, cin, wu, wexp, b.cuda(), s, t, out_buf[:, 2:], cout)
+    torch.cuda.synchronize()
+    mma = torch.zeros(N, cout, *crop).cuda()
+    ops.reg_convt4(xc, cin, wp, b.cuda(), s, t, mma, cout, wpk, wexp)
+    e_umma = (out_buf[:, 2:].cpu().double() - ref).abs().max().item()
+    e_mma = (mma.cpu().double() - ref).abs().max().item()
+    print(f"convt4 {cin}->{cout} {dims}: max-abs error vs fp64 torch: tcgen05 {e_umma:.2e}, mma.sync {e_mma:.2e}")
+    scale = max(1.0, ref.abs().max().item())
+    # fp32-level: a few ulp of the largest output (the dropped lo * lo term grows with K = 8 * cin)
+    assert e_umma < 4e-6 * scale * max(1.0, cin / 96), (e_umma, e_mma, scale)
+    assert out_buf[:, :2].abs().max() == 0
+
+
 def test_tallunet2_matches_oracle():
     _cuda()
     from oai_analysis_2_b200.icon_registration.networks import TallUNet2
