@@ -72,6 +72,25 @@ def test_unet2_layers_match_torch():
     assert (out.cpu() - ref).abs().max() < 3e-5
 
 
+@pytest.mark.parametrize("dims", [(5, 9, 35), (4, 16, 64), (9, 21, 33)])
+def test_last_conv_matches_torch(dims):
+    """lastConv (18 -> 3, stride 1, times 0.1: the exact three-channel instantiation) inside a larger channel buffer,
+    against torch fp64."""
+    _cuda()
+    from oai_analysis_2_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    N, cin, cout = 2, 18, 3
+    buf = torch.randn(N, cin + 2, *dims, generator=g)
+    w, b = torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.1, torch.randn(cout, generator=g) * 0.1
+    ref = F.conv3d(buf[:, 2:].double(), w.double(), b.double(), padding=1) * 0.1
+    wp = torch.zeros(cin, 27, 4)
+    wp[:, :, :3] = w.permute(1, 2, 3, 4, 0).reshape(cin, 27, 3)
+    out_buf = torch.zeros(N, cout + 1, *dims).cuda()
+    ops.reg_conv3(buf.cuda()[:, 2:], cin, wp.contiguous().cuda(), b.cuda(), out_buf[:, 1:], cout, 1, False, False, 0.1)
+    assert (out_buf[:, 1:].cpu().double() - ref).abs().max().item() < 2e-6
+    assert out_buf[:, 0].abs().max() == 0
+
+
 @pytest.mark.parametrize("cin,cout,dims", [(64, 96, (5, 7, 9)), (256, 512, (6, 12, 12)), (128, 130, (3, 4, 5))])
 def test_conv3_deep_levels_split_k_matches_torch(cin, cout, dims):
     """Down-path layers with few voxels and many channels run as split-K GEMMs with a fixed-order reduction
