@@ -258,7 +258,7 @@ OAI_API int oai_reg_convt4_mma(const float* in, long long in_nstride, long long 
                                size_t workspace_bytes, void* stream);
 
 /* The same up step on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) for the wide levels:
- * cout in {16, 32, 64}, cin a multiple of 16, cout <= cin, lattice at least 8 x 8.  Split-fp16 operands as above
+ * cout in {16, 32, 64, 128}, cin a multiple of 16, cout <= cin, lattice at least 8 x 8.  Split-fp16 operands as above
  * (fp32-level accuracy).  oai_reg_pack_convt4_umma turns w [cin][64][cout] fp32 (device) into the kernel's pre-swizzled
  * weight blocks (oai_reg_convt4_umma_wbytes(cin, cout) bytes, 16-byte aligned; wexp as for oai_reg_pack_convt4).
  * workspace: N * cin * D * H * W * 4 bytes, 128-byte aligned (the layer input as channels-last hi / lo fp16). */

@@ -109,8 +109,9 @@ extern "C" size_t oai_reg_convt4_umma_wbytes(int cin, int cout) { return convt4_
 
 extern "C" int oai_reg_pack_convt4_umma(const float* w, int cin, int cout, int wexp, void* dst, void* stream) {
   OAI_REQUIRE(w && dst, "reg_pack_convt4_umma: null pointer");
-  OAI_REQUIRE(cin > 0 && cin % 16 == 0 && (cout == 16 || cout == 32 || cout == 64),
-              "reg_pack_convt4_umma: cin must be a multiple of 16 and cout one of 16, 32, 64 (got %d, %d)", cin, cout);
+  OAI_REQUIRE(cin > 0 && cin % 16 == 0 && (cout == 16 || cout == 32 || cout == 64 || cout == 128),
+              "reg_pack_convt4_umma: cin must be a multiple of 16 and cout one of 16, 32, 64, 128 (got %d, %d)", cin,
+              cout);
   OAI_REQUIRE(wexp >= -14 && wexp <= 30, "reg_pack_convt4_umma: scale exponent %d out of range", wexp);
   OAI_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "reg_pack_convt4_umma: dst must be 16-byte aligned");
   return reg_pack_convt4_umma_launch(w, cin, cout, wexp, dst, static_cast<cudaStream_t>(stream));
@@ -134,7 +135,7 @@ extern "C" int oai_reg_convt4_umma(const float* in, long long in_nstride, long l
   p.Do = out_dims[0]; p.Ho = out_dims[1]; p.Wo = out_dims[2]; p.N = N;
   p.wexp = wexp; p.wumma = wumma; p.xsplit = static_cast<uint32_t*>(workspace); p.xsplit_bytes = workspace_bytes;
   OAI_REQUIRE(convt4_umma_eligible(p),
-              "reg_convt4_umma: needs cout in {16, 32, 64}, cin %% 16 == 0, cout <= cin and a lattice of at least 8 x 8 "
+              "reg_convt4_umma: needs cout in {16, 32, 64, 128}, cin %% 16 == 0, cout <= cin and a lattice of at least 8 x 8 "
               "(got cin=%d cout=%d dims %d x %d x %d)", cin, cout, p.Di, p.Hi, p.Wi);
   return convt4_umma_launch(p, static_cast<cudaStream_t>(stream));
 }

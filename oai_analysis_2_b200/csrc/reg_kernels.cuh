@@ -93,7 +93,7 @@ size_t conv3_splitk_bytes(const Conv3Params& p);
 size_t convt4_splitk_bytes(const ConvT4Params& p);
 int convt4_launch(const ConvT4Params& p, cudaStream_t st);
 int reg_pack_convt4_launch(const float* w, int cin, int cout, int wexp, uint4* wpk, cudaStream_t st);
-// tcgen05 path of the up step (reg_umma.cu): cout in {16, 32, 64}, cin a multiple of 16, lattice at least 8 x 8
+// tcgen05 path of the up step (reg_umma.cu): cout in {16, 32, 64, 128}, cin a multiple of 16, lattice at least 8 x 8
 bool convt4_umma_eligible(const ConvT4Params& p);
 size_t convt4_umma_wbytes(int cin, int cout);
 int reg_pack_convt4_umma_launch(const float* w, int cin, int cout, int wexp, void* dst, cudaStream_t st);

@@ -247,7 +247,7 @@ struct UNetWeights {
   float *uw[5], *ub[5];            // up step d: [cin][64][cout], [cout]
   float *bs[5], *bt[5];            // folded BatchNorm(eval): scale, shift
   uint4* uq[5];                    // split-fp16 B fragments of uw for the mma.sync path
-  void* uu[5];                     // weight blocks of the tcgen05 path (wide levels with 16 - 64 output channels)
+  void* uu[5];                     // weight blocks of the tcgen05 path (levels with 16 - 128 output channels)
   int uexp[5];
   float *lw, *lb;                  // lastConv: [18][27][4] (3 channels padded to 4), [3]
 };
@@ -558,7 +558,7 @@ int upload_unet(oai_reg_handle* h, const TensorGroup& g, UNetWeights* w) {
       w->uq[d] = static_cast<uint4*>(q);
       RC(reg_pack_convt4_launch(w->uw[d], cin, cout, wexp, w->uq[d], nullptr));
       w->uu[d] = nullptr;
-      if (cout <= 64) {
+      if (cout <= 128) {
         RC(check_cuda(cudaMalloc(&w->uu[d], convt4_umma_wbytes(cin, cout)), "reg_create: cudaMalloc"));
         h->allocs.push_back(w->uu[d]);
         RC(reg_pack_convt4_umma_launch(w->uw[d], cin, cout, wexp, w->uu[d], nullptr));

@@ -23,7 +23,7 @@ for i in which:
     res = {}
     variants = [("mma", lambda: ops.reg_convt4(x, cin, w, b, s, t, out, cout, wpk=wpk, wexp=wexp)),
                 ("fp32", lambda: ops.reg_convt4(x, cin, w, b, s, t, out, cout))]
-    if cout <= 64:
+    if cout <= 128 and dims[2] >= 8:
         wu = ops.reg_pack_convt4_umma(w, cin, cout, wexp)
         variants.insert(0, ("umma", lambda: ops.reg_convt4_umma(x, cin, wu, wexp, b, s, t, out, cout)))
     if os.environ.get("OAI_BENCH_ONLY"):

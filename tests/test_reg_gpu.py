@@ -164,6 +164,7 @@ def test_convt4_mma_matches_torch(cin, cout, dims, crop):
     (192, 64, (3, 12, 12), (5, 23, 24)),    # two output-channel splits, partial tiles, cropped output
     (32, 16, (2, 9, 11), (4, 18, 21)),      # odd lattice, odd crop in x (scalar stores)
     (48, 16, (10, 48, 48), (20, 96, 96)),   # more units than SMs
+    (512, 128, (5, 12, 12), (10, 24, 24)),  # the 128-channel level: eight output-channel splits, 32 chunks
 ])
 def test_convt4_umma_matches_torch(cin, cout, dims, crop):
     """tcgen05 path of the up step (oai_reg_convt4_umma: split-fp16 operands, accumulators in TMEM) against torch fp64
