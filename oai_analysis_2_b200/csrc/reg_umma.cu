@@ -79,6 +79,13 @@ __device__ __forceinline__ Unit decode_unit(const UmmaParams& p, int u) {
 
 __device__ __forceinline__ float leaky_f(float v) { return v > 0.f ? v : 0.01f * v; }
 
+// one 32-byte global store (sm_100: STG.256); p must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 }  // namespace
 
 // Layer input [N][cin] planes (explicit strides) -> xcl [2 (hi, lo)][N][vol][cin] fp16 channels-last: leaky_relu, then
@@ -107,10 +114,8 @@ __global__ void __launch_bounds__(256) reg_split_cl_kernel(const float* __restri
       lo[k] = *reinterpret_cast<const uint32_t*>(&l);
     }
     const long long o = ((n * vol + v) * ng + j) * 2;
-    xcl[o] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    xcl[o + 1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    xcl[plane + o] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    xcl[plane + o + 1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    st_global_256(xcl + o, hi);           // one 32-byte store per plane: the sector is written whole
+    st_global_256(xcl + plane + o, lo);
   }
 }
 
