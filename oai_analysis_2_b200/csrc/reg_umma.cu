@@ -294,9 +294,10 @@ convt4_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           mbar_wait(&full_b[bb], bph, 300 + bb);
           tc_fence_after();
           const uint32_t b_blk = bbuf_lo + static_cast<uint32_t>(bb) * bblk_step;
-          if (leader && !(p.debug & 2)) {
-            if (c == 0 && j == 0) {
-              // first block of the unit: columns from hw on are overwritten, the ones below accumulate
+          const bool mma_on = !(p.debug & 2);
+          if (c == 0 && j == 0) {
+            // first block of the unit: columns from hw on are overwritten, the ones below accumulate
+            if (leader && mma_on) {
               int hw = 0;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -314,14 +315,18 @@ convt4_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 umma_f16_ss_lohi2(s_col[k], a0 + alo_off, a_hi, b0, b_hi, s_idesc[k], 1u);
                 umma_f16_ss_lohi2(s_col[k], a0, a_hi, b0 + wlo_off, b_hi, s_idesc[k], 1u);
               }
-            } else {
+            }
+          } else {
+            // the whole warp computes the (warp-uniform) operands so they live in uniform registers; one lane issues
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (!s_on[k]) continue;
-                const uint32_t a0 = a_chunk + s_abox[k] + a_shift, b0 = b_blk + s_brow[k];
-                umma_f16_ss_lohi2(s_col[k], a0, a_hi, b0, b_hi, s_idesc[k], 1u);             // hi * w_hi
-                umma_f16_ss_lohi2(s_col[k], a0 + alo_off, a_hi, b0, b_hi, s_idesc[k], 1u);   // lo * w_hi
-                umma_f16_ss_lohi2(s_col[k], a0, a_hi, b0 + wlo_off, b_hi, s_idesc[k], 1u);   // hi * w_lo
+            for (int k = 0; k < 4; ++k) {
+              if (!s_on[k]) continue;
+              const uint32_t a0 = a_chunk + s_abox[k] + a_shift, b0 = b_blk + s_brow[k];
+              const uint32_t d = s_col[k], id = s_idesc[k];
+              if (leader && mma_on) {
+                umma_f16_ss_lohi2(d, a0, a_hi, b0, b_hi, id, 1u);             // hi * w_hi
+                umma_f16_ss_lohi2(d, a0 + alo_off, a_hi, b0, b_hi, id, 1u);   // lo * w_hi
+                umma_f16_ss_lohi2(d, a0, a_hi, b0 + wlo_off, b_hi, id, 1u);   // hi * w_lo
               }
             }
           }
