@@ -108,7 +108,9 @@ class TallUNet2:
             cat = [torch.empty((N, UP_OUT[d] + DOWN[d]) + lv[d], dtype=torch.float32, device=self.device)
                    for d in range(5)]
             x5 = torch.empty((N, DOWN[5]) + lv[5], dtype=torch.float32, device=self.device)
-            self._bufs = {key: (lv, cat, x5)}  # one geometry cached at a time
+            if len(self._bufs) >= 4:           # a cascade has two or three geometries; bound the cache anyway
+                self._bufs.pop(next(iter(self._bufs)))
+            self._bufs[key] = (lv, cat, x5)
         return self._bufs[key]
 
     def forward(self, A, B, out=None):

@@ -342,12 +342,12 @@ _scratch = {}
 
 
 def _scratch_buf(device, tag, nbytes):
-    """Device scratch for the kernels that need a workspace.  Eager calls share one growing buffer per (device, tag);
-    while a CUDA graph is being captured the buffer comes from the graph's own memory pool instead, so replays never
+    """Device scratch for the kernels that need a workspace.  Eager calls share one growing buffer per (device, tag,
+    stream); while a CUDA graph is being captured the buffer comes from the graph's own memory pool instead, so replays never
     depend on the shared buffer (which a later, larger eager call may reallocate)."""
     if torch.cuda.is_current_stream_capturing():
         return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
-    key = (device, tag)
+    key = (device, tag, torch.cuda.current_stream(device).cuda_stream)   # one buffer per stream: no cross-stream reuse
     if key not in _scratch or _scratch[key].numel() < nbytes:
         _scratch[key] = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
     return _scratch[key]
