@@ -227,6 +227,20 @@ OAI_API int oai_reg_conv3(const float* in, long long in_nstride, long long in_cs
                           int cout, int cout_pad, int N, int stride, int leaky_in, int residual, float out_scale,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* The strided down step (stride 2, leaky input, avg-pool residual, out_scale 1) on the 5th-generation tensor cores
+ * (tcgen05.mma, accumulator in TMEM, split-fp16 operands: fp32-level accuracy) for cin a multiple of 16, cout 32 or a
+ * multiple of 64 (<= 512), cout >= cin and an output lattice of at least 8 x 8.  oai_reg_pack_conv3_umma turns
+ * w [cin][27][cout_pad] fp32 (device) into the kernel's pre-swizzled weight blocks (oai_reg_conv3_umma_wbytes bytes,
+ * 16-byte aligned; wexp chosen as for oai_reg_pack_convt4).  workspace: oai_reg_conv3_umma_workspace bytes, 128-byte
+ * aligned (the layer input as eight parity planes, channels-last hi / lo fp16). */
+OAI_API size_t oai_reg_conv3_umma_wbytes(int cin, int cout);
+OAI_API size_t oai_reg_conv3_umma_workspace(int cin, const int* in_dims, int N);
+OAI_API int oai_reg_pack_conv3_umma(const float* w, int cin, int cout, int cout_pad, int wexp, void* dst, void* stream);
+OAI_API int oai_reg_conv3_umma(const float* in, long long in_nstride, long long in_cstride, int cin,
+                               const int* in_dims, const void* wumma, int wexp, const float* bias, float* out,
+                               long long out_nstride, long long out_cstride, int cout, int N, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* Optional device scratch for oai_reg_conv3 (may be NULL / 0): with oai_reg_conv3_workspace(...) bytes the deep
  * levels (stride 2, cin >= 64, at most 4096 output voxels over the batch: weight-streaming GEMMs) run split-K over
  * blocks with a fixed-order (deterministic) reduction; returns 0 for layers that do not use it. */

@@ -33,6 +33,8 @@ lib.oai_reg_conv3_workspace.restype = ctypes.c_size_t
 lib.oai_seg_workspace_bytes.restype = ctypes.c_size_t
 lib.oai_reg_workspace_bytes.restype = ctypes.c_size_t
 lib.oai_reg_convt4_umma_wbytes.restype = ctypes.c_size_t
+lib.oai_reg_conv3_umma_wbytes.restype = ctypes.c_size_t
+lib.oai_reg_conv3_umma_workspace.restype = ctypes.c_size_t
 lib.oai_mc_workspace_bytes.restype = ctypes.c_size_t
 lib.oai_mesh_regions_workspace_bytes.restype = ctypes.c_size_t
 lib.oai_mesh_smooth_workspace_bytes.restype = ctypes.c_size_t

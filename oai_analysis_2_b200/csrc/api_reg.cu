@@ -32,7 +32,7 @@ extern "C" int oai_reg_conv3(const float* in, long long in_nstride, long long in
   OAI_REQUIRE(in && in_dims && w && bias && out, "reg_conv3: null pointer");
   OAI_REQUIRE(stride == 1 || stride == 2, "reg_conv3: stride %d unsupported", stride);
   OAI_REQUIRE(!residual || (stride == 2 && cout >= cin), "reg_conv3: residual needs stride 2 and cout >= cin");
-  Conv3Params p;
+  Conv3Params p{};
   p.in = in; p.in_nstride = in_nstride; p.in_cstride = in_cstride; p.cin = cin;
   p.Di = in_dims[0]; p.Hi = in_dims[1]; p.Wi = in_dims[2];
   p.w = w; p.bias = bias; p.out = out; p.out_nstride = out_nstride; p.out_cstride = out_cstride;
@@ -103,6 +103,47 @@ extern "C" int oai_reg_convt4_mma(const float* in, long long in_nstride, long lo
   p.wpk = static_cast<const uint4*>(wpk); p.wexp = wexp; p.xsplit = static_cast<uint32_t*>(workspace);
   p.xsplit_bytes = workspace_bytes; p.debug = 0;
   return convt4_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t oai_reg_conv3_umma_wbytes(int cin, int cout) { return conv3_umma_wbytes(cin, cout); }
+
+extern "C" size_t oai_reg_conv3_umma_workspace(int cin, const int* in_dims, int N) {
+  if (!in_dims || cin <= 0 || N <= 0) return 0;
+  Conv3Params p{};
+  p.cin = cin; p.N = N; p.Di = in_dims[0]; p.Hi = in_dims[1]; p.Wi = in_dims[2];
+  return conv3_umma_workspace(p);
+}
+
+extern "C" int oai_reg_pack_conv3_umma(const float* w, int cin, int cout, int cout_pad, int wexp, void* dst,
+                                       void* stream) {
+  OAI_REQUIRE(w && dst, "reg_pack_conv3_umma: null pointer");
+  OAI_REQUIRE(conv3_umma_wbytes(cin, cout) > 0 && cout_pad >= cout,
+              "reg_pack_conv3_umma: cin must be a multiple of 16 and cout 32 or a multiple of 64 (got %d, %d)", cin, cout);
+  OAI_REQUIRE(wexp >= -14 && wexp <= 30, "reg_pack_conv3_umma: scale exponent %d out of range", wexp);
+  OAI_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "reg_pack_conv3_umma: dst must be 16-byte aligned");
+  return reg_pack_conv3_umma_launch(w, cin, cout, cout_pad, wexp, dst, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int oai_reg_conv3_umma(const float* in, long long in_nstride, long long in_cstride, int cin,
+                                  const int* in_dims, const void* wumma, int wexp, const float* bias, float* out,
+                                  long long out_nstride, long long out_cstride, int cout, int N, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  OAI_REQUIRE(in && in_dims && wumma && bias && out && workspace, "reg_conv3_umma: null pointer");
+  OAI_REQUIRE((reinterpret_cast<uintptr_t>(wumma) & 15) == 0, "reg_conv3_umma: weight blocks must be 16-byte aligned");
+  Conv3Params p{};
+  p.in = in; p.in_nstride = in_nstride; p.in_cstride = in_cstride; p.cin = cin;
+  p.Di = in_dims[0]; p.Hi = in_dims[1]; p.Wi = in_dims[2];
+  p.bias = bias; p.out = out; p.out_nstride = out_nstride; p.out_cstride = out_cstride;
+  p.cout = cout; p.cout_pad = cout;
+  p.Do = (p.Di + 1) / 2; p.Ho = (p.Hi + 1) / 2; p.Wo = (p.Wi + 1) / 2;
+  p.N = N; p.stride = 2; p.leaky_in = 1; p.residual = 1; p.out_scale = 1.0f;
+  p.wumma = wumma; p.wexp = wexp; p.xsplit = workspace; p.xsplit_bytes = workspace_bytes;
+  OAI_REQUIRE(conv3_umma_eligible(p),
+              "reg_conv3_umma: needs cin %% 16 == 0, cout 32 or a multiple of 64 (<= 512), cout >= cin and an output "
+              "lattice of at least 8 x 8 (got cin=%d cout=%d input %d x %d x %d)", cin, cout, p.Di, p.Hi, p.Wi);
+  OAI_REQUIRE(workspace_bytes >= conv3_umma_workspace(p) && (reinterpret_cast<uintptr_t>(workspace) & 127) == 0,
+              "reg_conv3_umma: workspace of %zu bytes, 128-byte aligned, required", conv3_umma_workspace(p));
+  return conv3_umma_launch(p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t oai_reg_convt4_umma_wbytes(int cin, int cout) { return convt4_umma_wbytes(cin, cout); }

@@ -1640,6 +1640,9 @@ size_t convt4_splitk_bytes(const ConvT4Params& p) {
 
 int conv3_launch(const Conv3Params& p, cudaStream_t st) {
   const long long nvox = static_cast<long long>(p.Do) * p.Ho * p.Wo;
+  // tcgen05 path (reg_umma_down.cu): the strided levels with 16+ input channels; OAI_B200_CONV3_UMMA=0 is the A/B switch
+  if (p.wumma && p.xsplit && conv3_umma_eligible(p) && p.xsplit_bytes >= conv3_umma_workspace(p))
+    return conv3_umma_launch(p, st);
   const size_t need = conv3_splitk_bytes(p);
   if (need && p.splitk_ws && p.splitk_bytes >= need) {
     DeepGemmParams g;

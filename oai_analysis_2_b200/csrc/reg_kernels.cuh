@@ -24,6 +24,12 @@ struct Conv3Params {
   float out_scale;   // multiplies (acc + bias [+ residual])
   float* splitk_ws;  // optional workspace for the split-K path of the deep levels (conv3_splitk_bytes)
   size_t splitk_bytes;
+  // optional tcgen05 path of the strided down steps (reg_umma_down.cu): weight blocks, their scale exponent and a
+  // workspace of conv3_umma_workspace() bytes for the space-to-depth hi / lo copy of the layer input
+  const void* wumma = nullptr;
+  int wexp = 0;
+  void* xsplit = nullptr;
+  size_t xsplit_bytes = 0;
 };
 
 // Direct fp32 transposed convolution, kernel 4, stride 2, pad 1 (output = 2x input), fused with the icon UNet2 up-path:
@@ -98,6 +104,13 @@ bool convt4_umma_eligible(const ConvT4Params& p);
 size_t convt4_umma_wbytes(int cin, int cout);
 int reg_pack_convt4_umma_launch(const float* w, int cin, int cout, int wexp, void* dst, cudaStream_t st);
 int convt4_umma_launch(const ConvT4Params& p, cudaStream_t st);
+// tcgen05 path of the down step (reg_umma_down.cu): stride 2, leaky input, residual, cin % 16 == 0, cout 32 or a
+// multiple of 64, output lattice at least 8 x 8
+bool conv3_umma_eligible(const Conv3Params& p);
+size_t conv3_umma_wbytes(int cin, int cout);
+size_t conv3_umma_workspace(const Conv3Params& p);
+int reg_pack_conv3_umma_launch(const float* w, int cin, int cout, int cout_pad, int wexp, void* dst, cudaStream_t st);
+int conv3_umma_launch(const Conv3Params& p, cudaStream_t st);
 int chain_launch(const ChainParams& p, cudaStream_t st);
 int resize_trilinear_launch(const float* in, int Di, int Hi, int Wi, float* out, int Do, int Ho, int Wo,
                             cudaStream_t st);

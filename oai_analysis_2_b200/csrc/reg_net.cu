@@ -244,6 +244,8 @@ std::string describe(const Parsed& p, int node) {
 
 struct UNetWeights {
   float *dw[5], *db[5];            // down step d: [cin][27][cout], [cout]
+  void* du[5];                     // weight blocks of the tcgen05 down step (levels with 16+ input channels)
+  int dexp[5];
   float *uw[5], *ub[5];            // up step d: [cin][64][cout], [cout]
   float *bs[5], *bt[5];            // folded BatchNorm(eval): scale, shift
   uint4* uq[5];                    // split-fp16 B fragments of uw for the mma.sync path
@@ -366,6 +368,12 @@ int unet_forward(Ctx& c, const UNetWeights& w, const float* src, const float* tg
     c.scratch_need = std::max(c.scratch_need, need);
     p.splitk_ws = need ? static_cast<float*>(c.scratch) : nullptr;
     p.splitk_bytes = need ? c.scratch_bytes : 0;
+    p.wumma = w.du[d]; p.wexp = w.dexp[d];
+    if (p.wumma && conv3_umma_eligible(p)) {
+      c.scratch_need = std::max(c.scratch_need, conv3_umma_workspace(p));
+      p.xsplit = c.scratch;
+      p.xsplit_bytes = c.scratch_bytes;
+    }
     if (!c.dry) RC(conv3_launch(p, c.st));
   }
   for (int d = 4; d >= 0; --d) {
@@ -533,6 +541,17 @@ int upload_unet(oai_reg_handle* h, const TensorGroup& g, UNetWeights* w) {
             buf[(static_cast<size_t>(ci) * 27 + t) * cout + co] = src[(static_cast<size_t>(co) * cin + ci) * 27 + t];
       RC(upload(h, buf.data(), buf.size() * 4, reinterpret_cast<void**>(&w->dw[d])));
       RC(upload(h, g.at("downConvs." + D + ".bias")->data, sizeof(float) * cout, reinterpret_cast<void**>(&w->db[d])));
+      w->du[d] = nullptr;
+      w->dexp[d] = 0;
+      if (const size_t nb = conv3_umma_wbytes(cin, cout)) {
+        float wmax = 0.f;
+        for (float v : buf) wmax = std::max(wmax, std::fabs(v));
+        int wexp = wmax == 0.f ? 0 : static_cast<int>(13 - std::floor(std::log2(static_cast<double>(wmax))));
+        w->dexp[d] = std::max(-14, std::min(30, wexp));
+        RC(check_cuda(cudaMalloc(&w->du[d], nb), "reg_create: cudaMalloc"));
+        h->allocs.push_back(w->du[d]);
+        RC(reg_pack_conv3_umma_launch(w->dw[d], cin, cout, cout, w->dexp[d], w->du[d], nullptr));
+      }
     }
     {   // ConvTranspose3d weight [cin][cout][64] -> [cin][64][cout]
       const int cin = up_in(d), cout = kUpOut[d];

@@ -384,6 +384,27 @@ def reg_convt4(x, cin, w, bias, bn_scale, bn_shift, out, cout, wpk=None, wexp=0,
     return out
 
 
+def reg_pack_conv3_umma(w, cin, cout):
+    """w: [cin, 27, cout] float32 cuda -> (pre-swizzled weight blocks of the tcgen05 down step, wexp)."""
+    wmax = float(w.abs().max())
+    wexp = 0 if wmax == 0.0 else max(-14, min(30, int(13 - math.floor(math.log2(wmax)))))
+    dst = torch.empty(int(lib.oai_reg_conv3_umma_wbytes(cin, cout)), dtype=torch.uint8, device=w.device)
+    check(lib.oai_reg_pack_conv3_umma(ptr(w), cin, cout, w.shape[-1], wexp, ptr(dst), stream_ptr()),
+          "reg_pack_conv3_umma")
+    return dst, wexp
+
+
+def reg_conv3_umma(x, cin, wumma, wexp, bias, out, cout):
+    """The strided down step (leaky input, avg-pool residual) on tcgen05; x / out are views [N, C, D, H, W]."""
+    N, _, D, H, W = x.shape
+    need = int(lib.oai_reg_conv3_umma_workspace(cin, ptr(_dims(D, H, W)), N))
+    ws = _scratch_buf(x.device, "conv3u", need)
+    check(lib.oai_reg_conv3_umma(ptr(x), c_ll(x.stride(0)), c_ll(x.stride(1)), cin, ptr(_dims(D, H, W)), ptr(wumma),
+                                 int(wexp), ptr(bias), ptr(out), c_ll(out.stride(0)), c_ll(out.stride(1)), cout, N,
+                                 ptr(ws), c_size(ws.numel()), stream_ptr()), "reg_conv3_umma")
+    return out
+
+
 def reg_pack_convt4_umma(w, cin, cout, wexp):
     """w: [cin, 64, cout] float32 cuda -> pre-swizzled weight blocks of the tcgen05 up step (uint8 tensor)."""
     n = int(lib.oai_reg_convt4_umma_wbytes(cin, cout))

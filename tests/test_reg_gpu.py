@@ -72,6 +72,41 @@ def test_unet2_layers_match_torch():
     assert (out.cpu() - ref).abs().max() < 3e-5
 
 
+@pytest.mark.parametrize("cin,cout,dims", [
+    (16, 32, (6, 32, 16)),      # one chunk, whole tiles
+    (16, 32, (9, 21, 27)),      # odd extents: parity planes padded with zeros, clipped avg-pool windows, partial tiles
+    (32, 64, (8, 40, 48)),      # two chunks, Cn = 64, several units per CTA
+    (64, 256, (10, 24, 24)),    # four output-channel splits
+])
+def test_conv3_umma_matches_torch(cin, cout, dims):
+    """tcgen05 path of the strided down step (oai_reg_conv3_umma: split-fp16 operands, accumulator in TMEM) against
+    torch fp64 and the fp32 CUDA-core kernel, inside larger channel buffers."""
+    _cuda()
+    from oai_analysis_2_b200 import ops
+    from oracle.reg_oracle import pad_or_crop
+    g = torch.Generator().manual_seed(19)
+    N = 2
+    buf = torch.randn(N, cin + 5, *dims, generator=g) * 1.5
+    x = buf[:, 5:]
+    w, b = torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.1, torch.randn(cout, generator=g) * 0.1
+    y = F.conv3d(F.leaky_relu(x).double(), w.double(), b.double(), stride=2, padding=1)
+    ref = y + pad_or_crop(F.avg_pool3d(x.double(), 2, ceil_mode=True), cout)
+    wp = w.permute(1, 2, 3, 4, 0).reshape(cin, 27, cout).contiguous().cuda()
+    wu, wexp = ops.reg_pack_conv3_umma(wp, cin, cout)
+    bufc = buf.cuda()
+    out_buf = torch.zeros(N, cout + 3, *ref.shape[2:]).cuda()
+    ops.reg_conv3_umma(bufc[:, 5:], cin, wu, wexp, b.cuda(), out_buf[:, 3:], cout)
+    torch.cuda.synchronize()
+    f32 = torch.zeros(N, cout, *ref.shape[2:]).cuda()
+    ops.reg_conv3(bufc[:, 5:], cin, wp, b.cuda(), f32, cout, 2, True, True)
+    e_umma = (out_buf[:, 3:].cpu().double() - ref).abs().max().item()
+    e_f32 = (f32.cpu().double() - ref).abs().max().item()
+    print(f"conv3 s2 {cin}->{cout} {dims}: max-abs error vs fp64 torch: tcgen05 {e_umma:.2e}, fp32 kernel {e_f32:.2e}")
+    scale = max(1.0, ref.abs().max().item())
+    assert e_umma < 4e-6 * scale * max(1.0, cin / 32), (e_umma, e_f32, scale)
+    assert out_buf[:, :3].abs().max() == 0
+
+
 @pytest.mark.parametrize("dims", [(5, 9, 35), (4, 16, 64), (9, 21, 33)])
 def test_last_conv_matches_torch(dims):
     """lastConv (18 -> 3, stride 1, times 0.1: the exact three-channel instantiation) inside a larger channel buffer,
