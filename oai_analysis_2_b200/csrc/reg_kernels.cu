@@ -1663,7 +1663,9 @@ int conv3_launch(const Conv3Params& p, cudaStream_t st) {
   if (p.cout == 3) conv3_dispatch<3, 8, 1>(p, st);              // lastConv: 18 -> 3 at full resolution: no FMAs on a
                                                                  // padding channel (a row-walking variant with lanes along x
                                                                  // and 8 output rows per thread measured 2x slower:
-                                                                 // 1.31 vs 0.65 ms at 80x192x192, latency-bound)
+                                                                 // 1.31 vs 0.65 ms at 80x192x192, latency-bound; a
+                                                                 // 4-outputs-per-thread variant with lanes 16 bytes apart and
+                                                                 // the halo samples by shuffle: 0.86 ms, bit-identical)
   else if (p.cout <= 4) conv3_dispatch<4, 8, 1>(p, st);
   else if (nvox * ((p.cout + 7) / 8) >= (1 << 16)) conv3_dispatch<8, 4, 1>(p, st);
   else if (p.cin >= 32) conv3_dispatch<8, 1, 4>(p, st);          // deep levels: few voxels, many channels
