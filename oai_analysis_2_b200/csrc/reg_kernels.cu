@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
   constexpr int CI_CHUNK = KS > 1 ? 16 : 8;
   constexpr int NIN = (XS - 1) * STRIDE + 3;
   constexpr int NV = 128 / KS;
-  __shared__ __align__(16) float s_w[CI_CHUNK * 27 * CO_T];
+  constexpr int CO_S = CO_T == 3 ? 4 : CO_T;   // shared-memory stride of a tap's weights: three channels padded to one
+                                               // 16-byte vector (lastConv is bound by the L1 / shared-memory pipe)
+  __shared__ __align__(16) float s_w[CI_CHUNK * 27 * CO_S];
   __shared__ float s_red[KS > 1 ? (KS - 1) * NV * XS * CO_T : 1];
   const int co0 = blockIdx.y * CO_T;
   const int n = blockIdx.z;
@@ -80,16 +82,16 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
   for (int ci0 = 0; ci0 < p.cin; ci0 += CI_CHUNK) {
     const int nci = min(CI_CHUNK, p.cin - ci0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nci * 27 * CO_T; i += blockDim.x) {
-      const int j = i % CO_T, k = (i / CO_T) % 27, c = i / (CO_T * 27);
+    for (int i = threadIdx.x; i < nci * 27 * CO_S; i += blockDim.x) {
+      const int j = i % CO_S, k = (i / CO_S) % 27, c = i / (CO_S * 27);
       const int co = co0 + j;
-      s_w[i] = co < p.cout_pad ? p.w[(static_cast<size_t>(ci0 + c) * 27 + k) * p.cout_pad + co] : 0.f;
+      s_w[i] = (j < CO_T && co < p.cout_pad) ? p.w[(static_cast<size_t>(ci0 + c) * 27 + k) * p.cout_pad + co] : 0.f;
     }
     __syncthreads();
     if (!active) continue;
     for (int c = ks; c < nci; c += KS) {
       const float* plane = in_n + (ci0 + c) * p.in_cstride;
-      const float* wc = s_w + c * 27 * CO_T;
+      const float* wc = s_w + c * 27 * CO_S;
       // one (kd, kh) input row: NIN x-adjacent samples (zeros outside the volume), leaky ReLU applied on load
       auto load_row = [&](int r, float (&xin)[NIN]) {
         const int z = zi0 + r / 3, y = yi0 + r % 3;
@@ -133,10 +135,18 @@ __global__ void __launch_bounds__(128) conv3_kernel(const Conv3Params p) {
         const float (&xin)[NIN] = xr[r & 1];
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const float* wk = wc + (r * 3 + kw) * CO_T;
-          float wv[CO_T];
+          const float* wk = wc + (r * 3 + kw) * CO_S;
+          float wv[CO_S];
+          if (CO_S % 4 == 0) {   // one 16-byte shared-memory load per four channels
 #pragma unroll
-          for (int j = 0; j < CO_T; ++j) wv[j] = wk[j];
+            for (int j = 0; j < CO_S / 4; ++j) {
+              const float4 w4 = reinterpret_cast<const float4*>(wk)[j];
+              wv[4 * j] = w4.x; wv[4 * j + 1] = w4.y; wv[4 * j + 2] = w4.z; wv[4 * j + 3] = w4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) wv[j] = wk[j];
+          }
 #pragma unroll
           for (int i = 0; i < XS; ++i)
 #pragma unroll
