@@ -1675,7 +1675,10 @@ int conv3_launch(const Conv3Params& p, cudaStream_t st) {
                                                                  // and 8 output rows per thread measured 2x slower:
                                                                  // 1.31 vs 0.65 ms at 80x192x192, latency-bound; a
                                                                  // 4-outputs-per-thread variant with lanes 16 bytes apart and
-                                                                 // the halo samples by shuffle: 0.86 ms, bit-identical)
+                                                                 // the halo samples by shuffle: 0.86 ms, bit-identical;
+                                                                 // shuffled halos inside this kernel's pipelined row loads:
+                                                                 // 1.13 ms -- the shuffle waits for the load it forwards.
+                                                                 // ncu: L1 pipe 85 %, FMA pipe 43 %)
   else if (p.cout <= 4) conv3_dispatch<4, 8, 1>(p, st);
   else if (nvox * ((p.cout + 7) / 8) >= (1 << 16)) conv3_dispatch<8, 4, 1>(p, st);
   else if (p.cin >= 32) conv3_dispatch<8, 1, 4>(p, st);          // deep levels: few voxels, many channels

@@ -107,7 +107,7 @@ def test_conv3_umma_matches_torch(cin, cout, dims):
     assert out_buf[:, :3].abs().max() == 0
 
 
-@pytest.mark.parametrize("dims", [(5, 9, 35), (4, 16, 64), (9, 21, 33)])
+@pytest.mark.parametrize("dims", [(5, 9, 35), (4, 16, 64), (9, 21, 33), (3, 10, 44), (6, 7, 192)])
 def test_last_conv_matches_torch(dims):
     """lastConv (18 -> 3, stride 1, times 0.1: the exact three-channel instantiation) inside a larger channel buffer,
     against torch fp64."""
