@@ -22,6 +22,7 @@ def main():
              "dc2 skip + dc1 x3": {"dc2": 4, "dc1": 3}, "dc2 skip + dc1 + ec1": {"dc2": 4, "dc1": 2, "ec1": 2},
              "dc2 skip + dc1 + dc5 skip": {"dc2": 4, "dc1": 2, "dc5": 4}, "dc2 up + dc1": {"dc2": 5, "dc1": 2},
              "dc2 skip + dc1 + ec2": {"dc2": 4, "dc1": 2, "ec2": 2},
+             "dc1 only": {"dc1": 2}, "dc1 x3 only": {"dc1": 3},
              "fp16x2": {n: 2 for n in names[1:]}, "fp16x3": {n: 3 for n in names[1:]}}
     if len(sys.argv) > 1:
         plans = {k: v for k, v in plans.items() if any(a in k for a in sys.argv[1:])}
