@@ -88,9 +88,10 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
 
 }  // namespace
 
-// Layer input [N][cin] planes (explicit strides) -> xcl [2 (hi, lo)][N][vol][cin] fp16 channels-last: leaky_relu, then
-// the hi / lo split; one thread moves 16 channels of one voxel (sixteen coalesced plane reads, one whole 32-byte sector
-// written per precision plane).
+// Layer input [N][cin] planes (explicit strides) -> xcl [2 (hi, lo)][N][cin / 16][vol][16] fp16 (channels-last inside a
+// 16-channel chunk, chunks planar: the x-adjacent 32-byte rows a TMA box fetches are contiguous in memory, so a box is
+// a few dozen line requests instead of 180 sector requests): leaky_relu, then the hi / lo split; one thread moves the 16
+// channels of one voxel and chunk (sixteen coalesced plane reads, one whole 32-byte sector written per precision plane).
 __global__ void __launch_bounds__(256) reg_split_cl_kernel(const float* __restrict__ in, long long in_nstride,
                                                            long long in_cstride, int N, int cin, long long vol,
                                                            uint4* __restrict__ xcl) {
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) reg_split_cl_kernel(const float* __restri
       hi[k] = *reinterpret_cast<const uint32_t*>(&h);
       lo[k] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    const long long o = ((n * vol + v) * ng + j) * 2;
+    const long long o = ((n * ng + j) * vol + v) * 2;   // chunk-planar: x-adjacent rows of a chunk are contiguous
     st_global_256(xcl + o, hi);           // one 32-byte store per plane: the sector is written whole
     st_global_256(xcl + plane + o, lo);
   }
@@ -217,9 +218,10 @@ convt4_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           uint8_t* base = abuf + static_cast<size_t>(ab) * p.abuf_bytes;
           for (int zi = zlo; zi <= zhi; ++zi) {
             const int slot = zi - (ui.z0 - 1);
-            tma_load_5d(base + (slot * 2) * kSlotBytes, &tm_x, &full_a[ab], c * 16, ui.x0 - 1, ui.y0 - 1, zi, ui.n);
-            tma_load_5d(base + (slot * 2 + 1) * kSlotBytes, &tm_x, &full_a[ab], c * 16, ui.x0 - 1, ui.y0 - 1, zi,
-                        p.N + ui.n);
+            tma_load_5d(base + (slot * 2) * kSlotBytes, &tm_x, &full_a[ab], 0, ui.x0 - 1, ui.y0 - 1, zi,
+                        ui.n * p.nchunks + c);
+            tma_load_5d(base + (slot * 2 + 1) * kSlotBytes, &tm_x, &full_a[ab], 0, ui.x0 - 1, ui.y0 - 1, zi,
+                        (p.N + ui.n) * p.nchunks + c);
           }
           if (++ab == 2) { ab = 0; ph ^= 1u; }
         }
@@ -532,9 +534,9 @@ EncodeTiledFn encode_tiled() {
 int make_xcl_tmap(CUtensorMap* tm, void* base, int cin, int Wi, int Hi, int Di, int planes) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return fail("convt4_umma: cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)planes};
-  cuuint64_t strides[4] = {(cuuint64_t)cin * 2, (cuuint64_t)Wi * cin * 2, (cuuint64_t)Hi * Wi * cin * 2,
-                           (cuuint64_t)Di * Hi * Wi * cin * 2};
+  (void)cin;   // every plane is one 16-channel chunk
+  cuuint64_t dims[5] = {16, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)planes};
+  cuuint64_t strides[4] = {32, (cuuint64_t)Wi * 32, (cuuint64_t)Hi * Wi * 32, (cuuint64_t)Di * Hi * Wi * 32};
   cuuint32_t box[5] = {16, kBX, kBY, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr,
@@ -628,7 +630,7 @@ int convt4_umma_launch(const ConvT4Params& p, cudaStream_t st) {
     q.debug = e ? atoi(e) : 0;
   }
   CUtensorMap tm, tm_raw;
-  if (int rc = make_xcl_tmap(&tm, p.xsplit, p.cin, p.Wi, p.Hi, p.Di, 2 * p.N)) return rc;
+  if (int rc = make_xcl_tmap(&tm, p.xsplit, p.cin, p.Wi, p.Hi, p.Di, 2 * p.N * (p.cin / 16))) return rc;
   // residual source by TMA when the raw input is a stack of dense, 16-byte aligned planes (every tallUNet2 level is)
   q.stage_raw = p.in_cstride == vol && p.in_nstride % p.in_cstride == 0 && p.Wi % 4 == 0 &&
                 (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && !umma_gather_forced();

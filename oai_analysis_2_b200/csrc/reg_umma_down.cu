@@ -74,7 +74,7 @@ __device__ __forceinline__ void st_global_256d(void* p, const uint32_t* v) {
 
 }  // namespace
 
-// Layer input [N][cin] planes (explicit strides) -> xs [2 (hi, lo)][N][8 parity classes][Dc][Hc][Wc][cin] fp16
+// Layer input [N][cin] planes (explicit strides) -> xs [2 (hi, lo)][N][8 parity classes][cin / 16][Dc][Hc][Wc][16] fp16
 // (Dc = ceil(D / 2) ...; class = rz*4 + ry*2 + rx holds in[2zc + rz][2yc + ry][2xc + rx], zeros past the extent):
 // leaky_relu, then the hi / lo split; one thread moves 16 channels of one lattice point.
 __global__ void __launch_bounds__(256) reg_split_s2d_kernel(const float* __restrict__ in, long long in_nstride,
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) reg_split_s2d_kernel(const float* __restr
 #pragma unroll
       for (int k = 0; k < 8; ++k) hi[k] = lo[k] = 0u;
     }
-    const long long o = ((((n * 8 + cls) * Dc + zc) * Hc + yc) * Wc + xc) * ng * 2 + j * 2;
+    const long long o = (((((n * 8 + cls) * ng + j) * Dc + zc) * Hc + yc) * Wc + xc) * 2;   // chunk-planar
     st_global_256d(xs + o, hi);
     st_global_256d(xs + plane + o, lo);
   }
@@ -199,8 +199,8 @@ conv3s2_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             mbar_wait(&empty[st], ph ^ 1u, 100 + st);
             uint8_t* base = smem + static_cast<size_t>(st) * p.stage_bytes;
             mbar_arrive_expect_tx(&full[st], 2u * kDBox + p.bblock);
-            tma_load_5d(base, &tm_x, &full[st], c * 16, cx, cy, cz, ui.n * 8 + cls);
-            tma_load_5d(base + kDBox, &tm_x, &full[st], c * 16, cx, cy, cz, (p.N + ui.n) * 8 + cls);
+            tma_load_5d(base, &tm_x, &full[st], 0, cx, cy, cz, (ui.n * 8 + cls) * p.nchunks + c);
+            tma_load_5d(base + kDBox, &tm_x, &full[st], 0, cx, cy, cz, ((p.N + ui.n) * 8 + cls) * p.nchunks + c);
             bulk_load(base + 2 * kDBox, wsrc + static_cast<size_t>(c * 27 + t) * p.bblock, p.bblock, &full[st]);
             if (++st == kDStages) { st = 0; ph ^= 1u; }
           }
@@ -324,9 +324,9 @@ int make_s2d_tmap(CUtensorMap* tm, void* base, int cin, int Wc, int Hc, int Dc, 
       fn = reinterpret_cast<EncodeTiledFnD>(q);
   }
   if (!fn) return fail("conv3s2_umma: cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)Dc, (cuuint64_t)planes};
-  cuuint64_t strides[4] = {(cuuint64_t)cin * 2, (cuuint64_t)Wc * cin * 2, (cuuint64_t)Hc * Wc * cin * 2,
-                           (cuuint64_t)Dc * Hc * Wc * cin * 2};
+  (void)cin;   // every plane is one 16-channel chunk of one parity class
+  cuuint64_t dims[5] = {16, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)Dc, (cuuint64_t)planes};
+  cuuint64_t strides[4] = {32, (cuuint64_t)Wc * 32, (cuuint64_t)Hc * Wc * 32, (cuuint64_t)Dc * Hc * Wc * 32};
   cuuint32_t box[5] = {16, kDTX, kDTY, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr,
@@ -400,7 +400,7 @@ int conv3_umma_launch(const Conv3Params& p, cudaStream_t st) {
   q.inv = exp2f(static_cast<float>(-p.wexp));
   q.out_scale = p.out_scale;
   CUtensorMap tm;
-  if (int rc = make_s2d_tmap(&tm, p.xsplit, p.cin, Wc, Hc, Dc, 2 * p.N * 8)) return rc;
+  if (int rc = make_s2d_tmap(&tm, p.xsplit, p.cin, Wc, Hc, Dc, 2 * p.N * 8 * (p.cin / 16))) return rc;
   const size_t smem = 1024 + static_cast<size_t>(kDStages) * q.stage_bytes + 256;
   static size_t configured[64] = {0};   // the attribute is per device
   int dev = 0;
