@@ -12,7 +12,7 @@
 //   * a unit's accumulator is Cn columns of one TMEM half; consecutive units of a CTA alternate halves so the epilogue
 //     (2^-wexp, bias, avg_pool3d(2, ceil_mode) residual on the trailing channels, planar fp32 stores) runs under the
 //     next unit's MMAs;
-//   * warp roles: 0 = producer (TMA boxes + weight rows), 2 = MMA issuer + TMEM owner, 4..7 = epilogue.
+//   * warp roles: 0 = activation producer (TMA), 1 = weight producer, 2 = MMA issuer + TMEM owner, 4..7 = epilogue.
 #include "api_common.h"
 #include "ptx.cuh"
 #include "reg_kernels.cuh"
@@ -74,7 +74,7 @@ __device__ __forceinline__ void st_global_256d(void* p, const uint32_t* v) {
 
 }  // namespace
 
-// Layer input [N][cin] planes (explicit strides) -> xs [2 (hi, lo)][N][8 parity classes][cin / 16][Dc][Hc][Wc][16] fp16
+// Layer input [N][cin] planes (explicit strides) -> xs [N][8 parity classes][cin / 16][2 (hi, lo)][Dc][Hc][Wc][16] fp16
 // (Dc = ceil(D / 2) ...; class = rz*4 + ry*2 + rx holds in[2zc + rz][2yc + ry][2xc + rx], zeros past the extent):
 // leaky_relu, then the hi / lo split; one thread moves 16 channels of one lattice point.
 __global__ void __launch_bounds__(256) reg_split_s2d_kernel(const float* __restrict__ in, long long in_nstride,
@@ -84,7 +84,6 @@ __global__ void __launch_bounds__(256) reg_split_s2d_kernel(const float* __restr
   const int Dc = (Di + 1) / 2, Hc = (Hi + 1) / 2, Wc = (Wi + 1) / 2;
   const long long cvol = static_cast<long long>(Dc) * Hc * Wc;
   const long long total = static_cast<long long>(N) * 8 * cvol * ng;
-  const long long plane = total * 2;   // uint4 per precision plane
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     long long r = i;
@@ -111,9 +110,10 @@ __global__ void __launch_bounds__(256) reg_split_s2d_kernel(const float* __restr
 #pragma unroll
       for (int k = 0; k < 8; ++k) hi[k] = lo[k] = 0u;
     }
-    const long long o = (((((n * 8 + cls) * ng + j) * Dc + zc) * Hc + yc) * Wc + xc) * 2;   // chunk-planar
+    // chunk-planar, the hi and the lo plane of a (sample, class, chunk) adjacent: one TMA box fetches both
+    const long long o = ((((((n * 8 + cls) * ng + j) * 2) * Dc + zc) * Hc + yc) * Wc + xc) * 2;
     st_global_256d(xs + o, hi);
-    st_global_256d(xs + plane + o, lo);
+    st_global_256d(xs + o + cvol * 2, lo);
   }
 }
 
@@ -162,7 +162,7 @@ conv3s2_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kDStages; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], 2);    // the activation and the weight producer
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -183,13 +183,14 @@ conv3s2_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   const int nst = p.nchunks * 27;   // stages per unit
 
   if (warp == 0) {
-    // ------------------------------------------------------------ producer: per (chunk, tap) two boxes + weight rows
+    // ------------------------------------------------------------ activation producer: per (chunk, tap) one box holding
+    // the tap's hi and lo tiles.  (One thread issuing two boxes and the weight rows per stage was the kernel's pace: a
+    // bulk-copy instruction takes a few hundred nanoseconds to issue, the stages are 96 tensor clocks long.)
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
         const DUnit ui = decode_dunit(p, u);
-        const uint8_t* wsrc = p.wumma + static_cast<size_t>(ui.h) * nst * p.bblock;
         for (int c = 0; c < p.nchunks; ++c)
           for (int t = 0; t < 27; ++t) {
             const int kz = t / 9, ky = (t / 3) % 3, kx = t % 3;
@@ -197,13 +198,28 @@ conv3s2_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             const int cls = (((kz + 1) & 1) << 2) | (((ky + 1) & 1) << 1) | ((kx + 1) & 1);
             const int cz = ui.z - (kz == 0), cy = ui.y0 - (ky == 0), cx = ui.x0 - (kx == 0);
             mbar_wait(&empty[st], ph ^ 1u, 100 + st);
-            uint8_t* base = smem + static_cast<size_t>(st) * p.stage_bytes;
-            mbar_arrive_expect_tx(&full[st], 2u * kDBox + p.bblock);
-            tma_load_5d(base, &tm_x, &full[st], 0, cx, cy, cz, (ui.n * 8 + cls) * p.nchunks + c);
-            tma_load_5d(base + kDBox, &tm_x, &full[st], 0, cx, cy, cz, ((p.N + ui.n) * 8 + cls) * p.nchunks + c);
-            bulk_load(base + 2 * kDBox, wsrc + static_cast<size_t>(c * 27 + t) * p.bblock, p.bblock, &full[st]);
+            mbar_arrive_expect_tx(&full[st], 2u * kDBox);
+            tma_load_5d(smem + static_cast<size_t>(st) * p.stage_bytes, &tm_x, &full[st], 0, cx, cy, cz,
+                        ((ui.n * 8 + cls) * p.nchunks + c) * 2);
             if (++st == kDStages) { st = 0; ph ^= 1u; }
           }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ weight producer: the tap's rows (hi, lo)
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+        const DUnit ui = decode_dunit(p, u);
+        const uint8_t* wsrc = p.wumma + static_cast<size_t>(ui.h) * nst * p.bblock;
+        for (int s = 0; s < nst; ++s) {
+          mbar_wait(&empty[st], ph ^ 1u, 200 + st);
+          mbar_arrive_expect_tx(&full[st], p.bblock);
+          bulk_load(smem + static_cast<size_t>(st) * p.stage_bytes + 2 * kDBox, wsrc + static_cast<size_t>(s) * p.bblock,
+                    p.bblock, &full[st]);
+          if (++st == kDStages) { st = 0; ph ^= 1u; }
+        }
       }
     }
   } else if (warp == 2) {
@@ -327,7 +343,7 @@ int make_s2d_tmap(CUtensorMap* tm, void* base, int cin, int Wc, int Hc, int Dc, 
   (void)cin;   // every plane is one 16-channel chunk of one parity class
   cuuint64_t dims[5] = {16, (cuuint64_t)Wc, (cuuint64_t)Hc, (cuuint64_t)Dc, (cuuint64_t)planes};
   cuuint64_t strides[4] = {32, (cuuint64_t)Wc * 32, (cuuint64_t)Hc * Wc * 32, (cuuint64_t)Dc * Hc * Wc * 32};
-  cuuint32_t box[5] = {16, kDTX, kDTY, 1, 1};
+  cuuint32_t box[5] = {16, kDTX, kDTY, 1, 2};   // the hi and the lo plane in one box
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -400,7 +416,7 @@ int conv3_umma_launch(const Conv3Params& p, cudaStream_t st) {
   q.inv = exp2f(static_cast<float>(-p.wexp));
   q.out_scale = p.out_scale;
   CUtensorMap tm;
-  if (int rc = make_s2d_tmap(&tm, p.xsplit, p.cin, Wc, Hc, Dc, 2 * p.N * 8 * (p.cin / 16))) return rc;
+  if (int rc = make_s2d_tmap(&tm, p.xsplit, p.cin, Wc, Hc, Dc, p.N * 8 * (p.cin / 16) * 2)) return rc;
   const size_t smem = 1024 + static_cast<size_t>(kDStages) * q.stage_bytes + 256;
   static size_t configured[64] = {0};   // the attribute is per device
   int dev = 0;
